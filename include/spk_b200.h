@@ -1,0 +1,171 @@
+/*
+ * spk_b200.h -- C ABI of the B200-native (sm_100a) message-passing hot path for SchNetPack models.
+ *
+ * The reference (atomistic-machine-learning/schnetpack @ 4c967da) has NO native interface for this path: every op is
+ * an ATen kernel dispatched from Python ("CUDA kernel inventory: empty").  The entry points below
+ * are therefore what a ctypes binding inside the reference's own nn.Modules would bind (INTEGRATION.md shows the stub);
+ * each one cites the reference Python it replaces (paths relative to /root/reference/src/schnetpack).
+ *
+ * Conventions:
+ *   - every pointer is a DEVICE pointer to contiguous row-major data; floats are fp32, graph indices int32,
+ *     user-facing neighbour indices (idx_i/idx_j/idx_m/Z) int64 exactly as the reference's tensors;
+ *   - the caller owns every buffer (outputs and workspaces included); the library never allocates, never
+ *     synchronises, keeps no global mutable state and only enqueues work on the given stream (graph-capturable);
+ *   - return value: 0 = ok, SPK_ERR_ARG (-1) bad argument, SPK_ERR_UNSUPPORTED (-2) shape outside the compiled
+ *     templates, -(1000 + cudaError_t) if a launch failed.  Nothing throws.
+ *   - F = n_atom_basis (multiple of 32, <= 256), n_rbf <= 32, KP = SPK_KP(n_rbf) = n_rbf rounded up to 4.
+ */
+#ifndef SPK_B200_H
+#define SPK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* spk_stream_t; /* cudaStream_t */
+
+#define SPK_OK 0
+#define SPK_ERR_ARG (-1)
+#define SPK_ERR_UNSUPPORTED (-2)
+
+#define SPK_ACT_NONE 0
+#define SPK_ACT_SILU 1 /* torch.nn.functional.silu            (PaiNN, Atomwise)  */
+#define SPK_ACT_SSP 2  /* nn/activations.py:9-22 shifted_softplus (SchNet)        */
+
+#define SPK_RBF_GAUSSIAN 0 /* nn/radial.py:11-48  */
+#define SPK_RBF_BESSEL 1   /* nn/radial.py:82-110 */
+
+#define SPK_GEO_STRIDE 8 /* floats per edge in the geometry record: ux uy uz d fc dfc/dd 1/d 0 */
+
+int spk_version(void);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Graph structure.  Replaces the implicit ordering assumptions of index_select / index_add_ in
+ * nn/scatter.py:26-34, representation/painn.py:55-62, representation/schnet.py:65-67.
+ *   rowptr[N+1], slot_j[E], slot_eid[E] : edges grouped by receiver idx_i (CSR).  Slot s of row i holds the sender
+ *       slot_j[s] and the position slot_eid[s] of that edge in the caller's idx_i/idx_j arrays.  If idx_i is already
+ *       sorted (reference collate order) slots are the identity permutation; otherwise a stable grouping is built.
+ *   sptr[N+1], pos_slot[E], pos_i[E]    : the same edges grouped by sender idx_j (ascending slot inside a group).
+ *   status[4] (device int32): [0]=1 if idx_i was sorted, [1]=number of out-of-range indices (must be 0),
+ *       [2]=max receiver degree, [3]=max sender degree.
+ *   workspace: spk_graph_workspace_bytes(N, E) bytes.
+ * ------------------------------------------------------------------------------------------------------------- */
+size_t spk_graph_workspace_bytes(int64_t n_atoms, int64_t n_edges);
+int spk_graph_build(const int64_t* idx_i, const int64_t* idx_j, int64_t n_atoms, int64_t n_edges, int32_t* rowptr,
+                    int32_t* slot_j, int32_t* slot_eid, int32_t* sptr, int32_t* pos_slot, int32_t* pos_i,
+                    int32_t* status, void* workspace, size_t workspace_bytes, spk_stream_t stream);
+
+/* mol_ptr[B+1] from the sorted system index idx_m (atomistic/atomwise.py:79-81 uses idx_m with index_add). */
+int spk_segment_ptr(const int64_t* idx_m, int64_t n_atoms, int64_t n_mol, int32_t* mol_ptr, spk_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Geometry.  atomistic/distances.py:14-26 (PairwiseDistances), representation/painn.py:227-230,
+ * representation/schnet.py:156-158, nn/radial.py, nn/cutoff.py:14-33.
+ * ------------------------------------------------------------------------------------------------------------- */
+/* Rij[e] = R[idx_j[e]] - R[idx_i[e]] + offsets[e] */
+int spk_pairwise_fwd(const float* R, const int64_t* idx_i, const int64_t* idx_j, const float* offsets, int64_t n_edges,
+                     float* r_ij, spk_stream_t stream);
+/* dE/dR[a] = sum_{e: j(e)=a} g[e] - sum_{e: i(e)=a} g[e]   (deterministic, no atomics); out = sign * that */
+int spk_pairwise_bwd(const float* g_rij, const int32_t* rowptr, const int32_t* slot_eid, const int32_t* sptr,
+                     const int32_t* pos_slot, int64_t n_atoms, float sign, float* g_R, spk_stream_t stream);
+/* per CSR slot s (edge slot_eid[s]): phi[s,0:n_rbf] radial basis (zero padded to KP), dphi = d phi/dd,
+ * geo[s] = (ux, uy, uz, d, fc, dfc/dd, 1/d, 0).  rbf_p0/p1 = offsets/widths (gaussian) or freqs/NULL (bessel). */
+int spk_edge_geometry(const float* r_ij, const int32_t* slot_eid, int64_t n_edges, int rbf_kind, int n_rbf,
+                      const float* rbf_p0, const float* rbf_p1, float cutoff, float* phi, float* dphi, float* geo,
+                      spk_stream_t stream);
+/* standalone radial basis / cutoff / activation (nn.GaussianRBF, nn.BesselRBF, nn.CosineCutoff, shifted_softplus
+ * forward + derivative, used by the nn.* module mirrors).  d: [n]; out: [n, n_rbf]; dout nullable */
+int spk_rbf_fwd(const float* d, int64_t n, int rbf_kind, int n_rbf, const float* rbf_p0, const float* rbf_p1,
+                float* out, float* dout, spk_stream_t stream);
+int spk_cosine_cutoff_fwd(const float* d, int64_t n, float cutoff, float* out, float* dout, spk_stream_t stream);
+int spk_act_fwd(const float* x, int64_t n, int act, float* y, float* dy, spk_stream_t stream);
+/* out[a, :] = table[Z[a], :]   (nn.Embedding in representation/painn.py:239, schnet.py:161) */
+int spk_embedding(const float* table, const int64_t* Z, int64_t n_atoms, int F, int n_rows, float* out,
+                  spk_stream_t stream);
+/* out[idx[r], :] += x[r, :] for sorted-or-not idx via a row-pointer (deterministic): generic nn/scatter.py:7-34.
+ * rowptr/slot_eid from spk_graph_build-style grouping of idx.  out[n_out, C] is fully overwritten. */
+int spk_segment_sum(const float* x, const int32_t* rowptr, const int32_t* slot_eid, int64_t n_out, int C, float* out,
+                    spk_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Dense layers.  nn/base.py:52-55 (Dense.forward = activation(F.linear(x, W, b))).
+ *   Y[M,N] = act( A[M,K] * B[K,N] + bias[N] ) + addend[M,N]
+ * B is the TRANSPOSED torch weight (W^T, [in,out] row-major) for a forward layer, or the weight itself for the
+ * input-gradient of a layer ( gX = (gY .* act'(pre)) W ).  If a_pre != NULL the A operand is multiplied on load by
+ * act'(a_pre) with activation a_act (the backward prologue).  y_pre (nullable) receives the pre-activation.
+ * ------------------------------------------------------------------------------------------------------------- */
+int spk_dense(const float* A, int64_t M, int K, int64_t lda, const float* a_pre, int a_act, const float* B, int N,
+              const float* bias, int act, const float* addend, int64_t ld_add, float* Y, int64_t ldy, float* y_pre,
+              spk_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * PaiNN.  representation/painn.py:31-67 (PaiNNInteraction.forward) and :92-117 (PaiNNMixing.forward).
+ * ------------------------------------------------------------------------------------------------------------- */
+/* Fused per-edge kernel of one interaction block (painn.py:55-65 + the filter of :232-236 recomputed on the fly):
+ *   W_s   = fc_s * (bf + phi_s Wf^T)                       [3F]   (never materialised)
+ *   q_out[i]  = q[i]  + sum_{s in row i} W_s[0:F]   * x[j_s, 0:F]
+ *   mu_out[i] = mu[i] + sum_{s in row i} W_s[F:2F]  * x[j_s, F:2F] (x) u_s + W_s[2F:3F] * x[j_s, 2F:3F] * mu[j_s]
+ * x = interatomic_context_net(q) [N,3F]; mu [N,3,F] may be NULL (== zeros, first block); wf [3F, n_rbf] and bf [3F]
+ * are this block's rows of filter_net.{weight,bias}.  q_out may alias q; mu_out must not alias mu. */
+int spk_painn_edge_fwd(const float* x, const float* mu, const float* q, const float* phi, const float* geo,
+                       const int32_t* rowptr, const int32_t* slot_j, const float* wf, const float* bf, int64_t n_atoms,
+                       int64_t n_edges, int F, int n_rbf, float* q_out, float* mu_out, spk_stream_t stream);
+/* Reverse of the above grouped by SENDER (no atomics): given g_q = dE/dq_out [N,F], g_mu = dE/dmu_out [N,3,F]:
+ *   g_x[j]     = sum_{edges with sender j} ...                                   [N,3F]  (overwritten)
+ *   g_mu_in[j] = g_mu[j] + sum ...                                               [N,3,F] (nullable when mu == NULL)
+ *   g_rij[eid] (+)= dE/dr_ij through d (phi, fc) and u                           [E,3]   (accumulate != 0 -> +=)
+ * The residual dE/dq_in = g_q is the caller's (identity).  */
+int spk_painn_edge_bwd(const float* x, const float* mu, const float* g_q, const float* g_mu, const float* phi,
+                       const float* dphi, const float* geo, const int32_t* sptr, const int32_t* pos_slot,
+                       const int32_t* pos_i, const int32_t* slot_eid, const float* wf, const float* bf,
+                       int64_t n_atoms, int64_t n_edges, int F, int n_rbf, float* g_x, float* g_mu_in, float* g_rij,
+                       int accumulate, spk_stream_t stream);
+/* painn.py:104-107: ctx[a] = [ q[a] | sqrt(sum_d V[a,d]^2 + eps) ], VW = mu_channel_mix(mu) [N,3,2F] */
+int spk_painn_mix_ctx(const float* q, const float* VW, int64_t n_atoms, int F, float eps, float* ctx,
+                      spk_stream_t stream);
+/* painn.py:110-116: q_out = q + s1 + s3 * sum_d V_d W_d ; mu_out[d] = mu[d] + s2 * W_d ; s [N,3F] */
+int spk_painn_mix_update(const float* q, const float* mu, const float* s, const float* VW, int64_t n_atoms, int F,
+                         float* q_out, float* mu_out, spk_stream_t stream);
+/* reverse of mix_update: g_s [N,3F]; g_VW [N,3,2F] (without the norm path) */
+int spk_painn_mix_update_bwd(const float* g_q, const float* g_mu, const float* s, const float* VW, int64_t n_atoms,
+                             int F, float* g_s, float* g_VW, spk_stream_t stream);
+/* reverse of mix_ctx: g_q_out = g_q + g_ctx[:, :F]; g_VW[:, d, :F] += g_ctx[:, F:] * V_d / n */
+int spk_painn_mix_ctx_bwd(const float* g_ctx, const float* g_q, const float* VW, int64_t n_atoms, int F, float eps,
+                          float* g_q_out, float* g_VW, spk_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * SchNet.  representation/schnet.py:41-70 (SchNetInteraction.forward).
+ * ------------------------------------------------------------------------------------------------------------- */
+/* continuous-filter convolution (schnet.py:62-67): m[i] = sum_{s in row i} h[j_s] * Wraw[s] * fc_s ; Wraw [E,F] is
+ * the filter-network output per CSR slot. */
+int spk_cfconv_fwd(const float* h, const float* w_raw, const float* geo, const int32_t* rowptr, const int32_t* slot_j,
+                   int64_t n_atoms, int64_t n_edges, int F, float* m, spk_stream_t stream);
+/* reverse grouped by sender: g_h[j] = sum W fc g_m[i];  g_wraw[s] = h[j] g_m[i] fc_s;
+ * g_fc[s] = sum_c h[j,c] g_m[i,c] Wraw[s,c] */
+int spk_cfconv_bwd(const float* h, const float* w_raw, const float* geo, const float* g_m, const int32_t* sptr,
+                   const int32_t* pos_slot, const int32_t* pos_i, int64_t n_atoms, int64_t n_edges, int F, float* g_h,
+                   float* g_wraw, float* g_fc, spk_stream_t stream);
+/* g_rij[eid] (+)= ( sum_k g_phi[s,k] dphi[s,k] + g_fc[s] dfc_s ) * u_s      (d-only dependence of SchNet) */
+int spk_radial_bwd(const float* g_phi, const float* g_fc, const float* dphi, const float* geo, const int32_t* slot_eid,
+                   int64_t n_edges, int n_rbf, float* g_rij, int accumulate, spk_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Atomwise head.  atomistic/atomwise.py:69-88: y = outnet(q); E[m] = sum_{a in m} y[a].
+ * ------------------------------------------------------------------------------------------------------------- */
+/* y[a] = hid[a,:] . w1 + b1 ; energy[m] = sum_{a in mol m} y[a]   (hid = silu(Dense_0(q)) [N,H]); y nullable */
+int spk_atomwise_out(const float* hid, const float* w1, const float* b1, const int32_t* mol_ptr, int64_t n_atoms,
+                     int64_t n_mol, int H, float* y, float* energy, spk_stream_t stream);
+/* g_hid[a,:] = g_energy[mol(a)] * w1   (g_energy nullable == ones) */
+int spk_atomwise_out_bwd(const float* g_energy, const int64_t* idx_m, const float* w1, int64_t n_atoms, int H,
+                         float* g_hid, spk_stream_t stream);
+
+/* elementwise helpers for residual streams: out = a + b (b nullable -> copy), may alias */
+int spk_add(const float* a, const float* b, int64_t n, float* out, spk_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPK_B200_H */

@@ -1,0 +1,97 @@
+"""ctypes binding of the C-ABI library ``csrc/libspk_b200.so`` (declared in ``include/spk_b200.h``).
+
+There is NO fallback: if the library is missing (not built) importing any op raises, and every op raises when it is
+handed a non-CUDA tensor.  torch is used only as the owner of device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_float, c_int, c_int64, c_size_t, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libspk_b200.so")
+
+SPK_OK = 0
+ACT_NONE, ACT_SILU, ACT_SSP = 0, 1, 2
+RBF_GAUSSIAN, RBF_BESSEL = 0, 1
+GEO_STRIDE = 8
+
+P = c_void_p  # device pointers and the stream travel as void*
+
+# name -> argument ctypes (return type is int unless listed in _RESTYPE)
+SIGNATURES = {
+    "spk_version": [],
+    "spk_graph_workspace_bytes": [c_int64, c_int64],
+    "spk_graph_build": [P, P, c_int64, c_int64, P, P, P, P, P, P, P, P, c_size_t, P],
+    "spk_segment_ptr": [P, c_int64, c_int64, P, P],
+    "spk_pairwise_fwd": [P, P, P, P, c_int64, P, P],
+    "spk_pairwise_bwd": [P, P, P, P, P, c_int64, c_float, P, P],
+    "spk_edge_geometry": [P, P, c_int64, c_int, c_int, P, P, c_float, P, P, P, P],
+    "spk_rbf_fwd": [P, c_int64, c_int, c_int, P, P, P, P, P],
+    "spk_cosine_cutoff_fwd": [P, c_int64, c_float, P, P, P],
+    "spk_act_fwd": [P, c_int64, c_int, P, P, P],
+    "spk_embedding": [P, P, c_int64, c_int, c_int, P, P],
+    "spk_segment_sum": [P, P, P, c_int64, c_int, P, P],
+    "spk_dense": [P, c_int64, c_int, c_int64, P, c_int, P, c_int, P, c_int, P, c_int64, P, c_int64, P, P],
+    "spk_painn_edge_fwd": [P, P, P, P, P, P, P, P, P, c_int64, c_int64, c_int, c_int, P, P, P],
+    "spk_painn_edge_bwd": [P, P, P, P, P, P, P, P, P, P, P, P, P, c_int64, c_int64, c_int, c_int, P, P, P, c_int, P],
+    "spk_painn_mix_ctx": [P, P, c_int64, c_int, c_float, P, P],
+    "spk_painn_mix_update": [P, P, P, P, c_int64, c_int, P, P, P],
+    "spk_painn_mix_update_bwd": [P, P, P, P, c_int64, c_int, P, P, P],
+    "spk_painn_mix_ctx_bwd": [P, P, P, c_int64, c_int, c_float, P, P, P],
+    "spk_cfconv_fwd": [P, P, P, P, P, c_int64, c_int64, c_int, P, P],
+    "spk_cfconv_bwd": [P, P, P, P, P, P, P, c_int64, c_int64, c_int, P, P, P, P],
+    "spk_radial_bwd": [P, P, P, P, P, c_int64, c_int, P, c_int, P],
+    "spk_atomwise_out": [P, P, P, P, c_int64, c_int64, c_int, P, P, P],
+    "spk_atomwise_out_bwd": [P, P, P, c_int64, c_int, P, P],
+    "spk_add": [P, P, c_int64, P, P],
+}
+_RESTYPE = {"spk_graph_workspace_bytes": c_size_t}
+
+_lib = None
+
+
+class SpkLibraryError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (once) and return the ctypes handle; raises SpkLibraryError if the CUDA library has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SpkLibraryError(
+            f"{LIB_PATH} not found: build it with `python -m schnetpack_b200.build` (needs nvcc). "
+            "schnetpack_b200 has no CPU fallback."
+        )
+    h = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(h, name)  # AttributeError if the .so is stale / symbol missing
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPE.get(name, c_int)
+    _lib = h
+    return h
+
+
+def check(rc: int, name: str):
+    if rc == SPK_OK:
+        return
+    if rc == -1:
+        raise ValueError(f"{name}: invalid argument (SPK_ERR_ARG)")
+    if rc == -2:
+        raise NotImplementedError(f"{name}: shape outside the compiled sm_100a templates (SPK_ERR_UNSUPPORTED)")
+    raise RuntimeError(f"{name}: CUDA error {-rc - 1000}")
+
+
+# kernels launched per C-ABI call (default 1); bench.py reports the running total as ``gpu_launches``
+LAUNCHES = {"spk_graph_build": 7, "spk_atomwise_out": 2}
+launch_count = 0
+
+
+def call(name: str, *args):
+    global launch_count
+    rc = getattr(lib(), name)(*args)
+    check(rc, name)
+    launch_count += LAUNCHES.get(name, 1)

@@ -1,0 +1,73 @@
+// Shared device/host helpers for the sm_100a kernels of the SchNetPack hot path.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/spk_b200.h"
+
+#define SPK_CUDA_ERR(e) (-(1000 + (int)(e)))
+
+#define SPK_LAUNCH_CHECK()                               \
+    do {                                                 \
+        cudaError_t _e = cudaGetLastError();             \
+        if (_e != cudaSuccess) return SPK_CUDA_ERR(_e);  \
+    } while (0)
+
+static inline cudaStream_t spk_st(spk_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+static inline int64_t spk_cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+constexpr int SPK_NUM_SMS = 148;  // B200: 2 dies x 74 SMs
+
+__host__ __device__ __forceinline__ int spk_kp(int n_rbf) { return (n_rbf + 3) & ~3; }
+
+// ---- activations (match torch fp32 semantics) --------------------------------------------------------------------
+// silu(x) = x * sigmoid(x); torch: x / (1 + exp(-x))
+__device__ __forceinline__ float spk_silu(float x) { return x / (1.0f + expf(-x)); }
+__device__ __forceinline__ float spk_silu_grad(float x) {
+    float s = 1.0f / (1.0f + expf(-x));
+    return s * (1.0f + x * (1.0f - s));
+}
+// shifted softplus: softplus(x) - ln2, torch softplus threshold = 20 (nn/activations.py:22)
+__device__ __forceinline__ float spk_ssp(float x) {
+    float sp = (x > 20.0f) ? x : log1pf(expf(x));
+    return sp - 0.6931471805599453f;
+}
+__device__ __forceinline__ float spk_ssp_grad(float x) { return (x > 20.0f) ? 1.0f : 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float spk_act(float x, int act) {
+    if (act == SPK_ACT_SILU) return spk_silu(x);
+    if (act == SPK_ACT_SSP) return spk_ssp(x);
+    return x;
+}
+__device__ __forceinline__ float spk_act_grad(float x, int act) {
+    if (act == SPK_ACT_SILU) return spk_silu_grad(x);
+    if (act == SPK_ACT_SSP) return spk_ssp_grad(x);
+    return 1.0f;
+}
+
+__device__ __forceinline__ float spk_warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// first index r in [0, n] with ptr[r] >= target (ptr non-decreasing, length n+1)
+__device__ __forceinline__ int spk_lower_bound(const int32_t* __restrict__ ptr, int n, int target) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (ptr[mid] < target) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// Edge-balanced split of rows [0,n) over nb blocks: block b gets rows [row_begin(b), row_begin(b+1)).
+__device__ __forceinline__ int spk_block_row_begin(const int32_t* __restrict__ ptr, int n, int n_edges, int nb, int b) {
+    if (b <= 0) return 0;
+    if (b >= nb) return n;
+    long long target = ((long long)n_edges * b) / nb;
+    // mix rows and edges so that edge-free rows are spread as well
+    int r_e = spk_lower_bound(ptr, n, (int)target);
+    return r_e;
+}

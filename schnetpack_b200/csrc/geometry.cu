@@ -1,0 +1,258 @@
+// Edge geometry, radial basis, cutoff, embedding and force assembly kernels (HBM-bound elementwise / segmented work).
+// Reference: atomistic/distances.py:14-26, representation/painn.py:227-230, schnet.py:156-158, nn/radial.py,
+// nn/cutoff.py:14-33, nn/activations.py:9-22, nn/scatter.py:26-34.
+#include "common.cuh"
+
+namespace {
+
+constexpr float kPi = 3.14159265358979323846f;
+
+// radial basis value and derivative for one (d, k)
+__device__ __forceinline__ void rbf_eval(int kind, float d, float p0, float p1, float& v, float& dv) {
+    if (kind == SPK_RBF_GAUSSIAN) {
+        // nn/radial.py:11-15: coeff = -0.5 / w^2 ; exp(coeff * (d - mu)^2)
+        float coeff = -0.5f / (p1 * p1);
+        float diff = d - p0;
+        v = expf(coeff * diff * diff);
+        dv = 2.0f * coeff * diff * v;
+    } else {
+        // nn/radial.py:105-110: sin(f d) / d, d == 0 -> sin(f d) / 1
+        float s, c;
+        sincosf(p0 * d, &s, &c);
+        if (d == 0.0f) {
+            v = s;
+            dv = p0 * c;
+        } else {
+            float inv = 1.0f / d;
+            v = s * inv;
+            dv = (p0 * c - v) * inv;
+        }
+    }
+}
+
+__device__ __forceinline__ void cutoff_eval(float d, float rc, float& fc, float& dfc) {
+    // nn/cutoff.py:30-32: 0.5 (cos(d pi / rc) + 1) * (d < rc)
+    float t = d * kPi / rc;
+    float s, c;
+    sincosf(t, &s, &c);
+    bool in = d < rc;
+    fc = in ? 0.5f * (c + 1.0f) : 0.0f;
+    dfc = in ? (-0.5f * kPi / rc) * s : 0.0f;
+}
+
+__global__ void k_pairwise_fwd(const float* __restrict__ R, const int64_t* __restrict__ idx_i,
+                               const int64_t* __restrict__ idx_j, const float* __restrict__ off, int64_t n_edges,
+                               float* __restrict__ r_ij) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n_edges * 3) return;
+    int64_t e = t / 3;
+    int c = (int)(t - e * 3);
+    float o = off ? off[t] : 0.0f;
+    r_ij[t] = R[idx_j[e] * 3 + c] - R[idx_i[e] * 3 + c] + o;
+}
+
+// one thread per (atom, component): deterministic sums over the receiver row and the sender row
+__global__ void k_pairwise_bwd(const float* __restrict__ g, const int* __restrict__ rowptr,
+                               const int* __restrict__ slot_eid, const int* __restrict__ sptr,
+                               const int* __restrict__ pos_slot, int64_t n_atoms, float sign,
+                               float* __restrict__ gR) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n_atoms * 3) return;
+    int64_t a = t / 3;
+    int c = (int)(t - a * 3);
+    float acc = 0.0f;
+    for (int p = sptr[a]; p < sptr[a + 1]; ++p) acc += g[(int64_t)slot_eid[pos_slot[p]] * 3 + c];
+    float sub = 0.0f;
+    for (int s = rowptr[a]; s < rowptr[a + 1]; ++s) sub += g[(int64_t)slot_eid[s] * 3 + c];
+    gR[t] = sign * (acc - sub);
+}
+
+// one thread per slot computes the geometry record, then KP threads-worth of radial values are produced by a loop
+__global__ void k_edge_geometry(const float* __restrict__ r_ij, const int* __restrict__ slot_eid, int64_t n_edges,
+                                int kind, int n_rbf, int KP, const float* __restrict__ p0, const float* __restrict__ p1,
+                                float rc, float* __restrict__ phi, float* __restrict__ dphi, float* __restrict__ geo) {
+    // thread (s, k): k in [0, KP)
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n_edges * KP) return;
+    int64_t s = t / KP;
+    int k = (int)(t - s * KP);
+    int64_t e = slot_eid ? (int64_t)slot_eid[s] : s;
+    float x = r_ij[e * 3 + 0], y = r_ij[e * 3 + 1], z = r_ij[e * 3 + 2];
+    float d = sqrtf(x * x + y * y + z * z);  // torch.norm(r_ij, dim=1)
+    float v = 0.0f, dv = 0.0f;
+    if (k < n_rbf) rbf_eval(kind, d, p0[k], p1 ? p1[k] : 0.0f, v, dv);
+    phi[t] = v;
+    if (dphi) dphi[t] = dv;
+    if (k == 0) {
+        float fc, dfc;
+        cutoff_eval(d, rc, fc, dfc);
+        float inv = 1.0f / d;  // d == 0 -> inf/NaN exactly like painn.py:228 (r_ij / d_ij)
+        float4 g0 = make_float4(x * inv, y * inv, z * inv, d);
+        float4 g1 = make_float4(fc, dfc, inv, 0.0f);
+        float4* gp = reinterpret_cast<float4*>(geo + s * SPK_GEO_STRIDE);
+        gp[0] = g0;
+        gp[1] = g1;
+    }
+}
+
+__global__ void k_rbf(const float* __restrict__ d, int64_t n, int kind, int n_rbf, const float* __restrict__ p0,
+                      const float* __restrict__ p1, float* __restrict__ out, float* __restrict__ dout) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n * n_rbf) return;
+    int64_t r = t / n_rbf;
+    int k = (int)(t - r * n_rbf);
+    float v, dv;
+    rbf_eval(kind, d[r], p0[k], p1 ? p1[k] : 0.0f, v, dv);
+    out[t] = v;
+    if (dout) dout[t] = dv;
+}
+
+__global__ void k_cutoff(const float* __restrict__ d, int64_t n, float rc, float* __restrict__ out,
+                         float* __restrict__ dout) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    float fc, dfc;
+    cutoff_eval(d[t], rc, fc, dfc);
+    out[t] = fc;
+    if (dout) dout[t] = dfc;
+}
+
+__global__ void k_act(const float* __restrict__ x, int64_t n, int act, float* __restrict__ y, float* __restrict__ dy) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    float v = x[t];
+    if (y) y[t] = spk_act(v, act);
+    if (dy) dy[t] = spk_act_grad(v, act);
+}
+
+__global__ void k_embedding(const float* __restrict__ table, const int64_t* __restrict__ Z, int64_t n_atoms, int F4,
+                            int n_rows, float* __restrict__ out) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n_atoms * F4) return;
+    int64_t a = t / F4;
+    int c = (int)(t - a * F4);
+    int64_t z = Z[a];
+    if (z < 0) z = 0;
+    if (z >= n_rows) z = n_rows - 1;
+    reinterpret_cast<float4*>(out)[t] = reinterpret_cast<const float4*>(table)[z * F4 + c];
+}
+
+// out[r, c] = sum_{s in row r} x[slot_eid[s], c]; thread per (r, c)
+__global__ void k_segment_sum(const float* __restrict__ x, const int* __restrict__ rowptr,
+                              const int* __restrict__ slot_eid, int64_t n_out, int C, float* __restrict__ out) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n_out * C) return;
+    int64_t r = t / C;
+    int c = (int)(t - r * C);
+    float acc = 0.0f;
+    for (int s = rowptr[r]; s < rowptr[r + 1]; ++s) {
+        int64_t e = slot_eid ? (int64_t)slot_eid[s] : (int64_t)s;
+        acc += x[e * C + c];
+    }
+    out[t] = acc;
+}
+
+__global__ void k_add(const float* __restrict__ a, const float* __restrict__ b, int64_t n, float* __restrict__ out) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    out[t] = b ? a[t] + b[t] : a[t];
+}
+
+}  // namespace
+
+#define GRID1D(n, T) (unsigned)spk_cdiv((n), (T)), (T), 0, spk_st(stream)
+
+extern "C" int spk_pairwise_fwd(const float* R, const int64_t* idx_i, const int64_t* idx_j, const float* offsets,
+                                int64_t n_edges, float* r_ij, spk_stream_t stream) {
+    if (n_edges < 0) return SPK_ERR_ARG;
+    if (n_edges == 0) return SPK_OK;
+    if (!R || !idx_i || !idx_j || !r_ij) return SPK_ERR_ARG;
+    k_pairwise_fwd<<<GRID1D(n_edges * 3, 256)>>>(R, idx_i, idx_j, offsets, n_edges, r_ij);
+    SPK_LAUNCH_CHECK();
+    return SPK_OK;
+}
+
+extern "C" int spk_pairwise_bwd(const float* g_rij, const int32_t* rowptr, const int32_t* slot_eid, const int32_t* sptr,
+                                const int32_t* pos_slot, int64_t n_atoms, float sign, float* g_R, spk_stream_t stream) {
+    if (n_atoms < 0) return SPK_ERR_ARG;
+    if (n_atoms == 0) return SPK_OK;
+    if (!rowptr || !sptr || !g_R) return SPK_ERR_ARG;
+    k_pairwise_bwd<<<GRID1D(n_atoms * 3, 128)>>>(g_rij, rowptr, slot_eid, sptr, pos_slot, n_atoms, sign, g_R);
+    SPK_LAUNCH_CHECK();
+    return SPK_OK;
+}
+
+extern "C" int spk_edge_geometry(const float* r_ij, const int32_t* slot_eid, int64_t n_edges, int rbf_kind, int n_rbf,
+                                 const float* rbf_p0, const float* rbf_p1, float cutoff, float* phi, float* dphi,
+                                 float* geo, spk_stream_t stream) {
+    if (n_edges < 0 || n_rbf <= 0) return SPK_ERR_ARG;
+    if (n_rbf > 32) return SPK_ERR_UNSUPPORTED;
+    if (rbf_kind != SPK_RBF_GAUSSIAN && rbf_kind != SPK_RBF_BESSEL) return SPK_ERR_ARG;
+    if (n_edges == 0) return SPK_OK;
+    if (!r_ij || !rbf_p0 || !phi || !geo) return SPK_ERR_ARG;
+    if (rbf_kind == SPK_RBF_GAUSSIAN && !rbf_p1) return SPK_ERR_ARG;
+    int KP = spk_kp(n_rbf);
+    k_edge_geometry<<<GRID1D(n_edges * KP, 256)>>>(r_ij, slot_eid, n_edges, rbf_kind, n_rbf, KP, rbf_p0, rbf_p1,
+                                                   cutoff, phi, dphi, geo);
+    SPK_LAUNCH_CHECK();
+    return SPK_OK;
+}
+
+extern "C" int spk_rbf_fwd(const float* d, int64_t n, int rbf_kind, int n_rbf, const float* rbf_p0,
+                           const float* rbf_p1, float* out, float* dout, spk_stream_t stream) {
+    if (n < 0 || n_rbf <= 0) return SPK_ERR_ARG;
+    if (rbf_kind != SPK_RBF_GAUSSIAN && rbf_kind != SPK_RBF_BESSEL) return SPK_ERR_ARG;
+    if (n == 0) return SPK_OK;
+    if (!d || !rbf_p0 || !out || (rbf_kind == SPK_RBF_GAUSSIAN && !rbf_p1)) return SPK_ERR_ARG;
+    k_rbf<<<GRID1D(n * n_rbf, 256)>>>(d, n, rbf_kind, n_rbf, rbf_p0, rbf_p1, out, dout);
+    SPK_LAUNCH_CHECK();
+    return SPK_OK;
+}
+
+extern "C" int spk_cosine_cutoff_fwd(const float* d, int64_t n, float cutoff, float* out, float* dout,
+                                     spk_stream_t stream) {
+    if (n < 0) return SPK_ERR_ARG;
+    if (n == 0) return SPK_OK;
+    if (!d || !out) return SPK_ERR_ARG;
+    k_cutoff<<<GRID1D(n, 256)>>>(d, n, cutoff, out, dout);
+    SPK_LAUNCH_CHECK();
+    return SPK_OK;
+}
+
+extern "C" int spk_act_fwd(const float* x, int64_t n, int act, float* y, float* dy, spk_stream_t stream) {
+    if (n < 0 || act < 0 || act > 2) return SPK_ERR_ARG;
+    if (n == 0) return SPK_OK;
+    if (!x) return SPK_ERR_ARG;
+    k_act<<<GRID1D(n, 256)>>>(x, n, act, y, dy);
+    SPK_LAUNCH_CHECK();
+    return SPK_OK;
+}
+
+extern "C" int spk_embedding(const float* table, const int64_t* Z, int64_t n_atoms, int F, int n_rows, float* out,
+                             spk_stream_t stream) {
+    if (n_atoms < 0 || F <= 0 || (F & 3) || n_rows <= 0) return SPK_ERR_ARG;
+    if (n_atoms == 0) return SPK_OK;
+    if (!table || !Z || !out) return SPK_ERR_ARG;
+    k_embedding<<<GRID1D(n_atoms * (F / 4), 256)>>>(table, Z, n_atoms, F / 4, n_rows, out);
+    SPK_LAUNCH_CHECK();
+    return SPK_OK;
+}
+
+extern "C" int spk_segment_sum(const float* x, const int32_t* rowptr, const int32_t* slot_eid, int64_t n_out, int C,
+                               float* out, spk_stream_t stream) {
+    if (n_out < 0 || C <= 0) return SPK_ERR_ARG;
+    if (n_out == 0) return SPK_OK;
+    if (!rowptr || !out) return SPK_ERR_ARG;
+    k_segment_sum<<<GRID1D(n_out * C, 256)>>>(x, rowptr, slot_eid, n_out, C, out);
+    SPK_LAUNCH_CHECK();
+    return SPK_OK;
+}
+
+extern "C" int spk_add(const float* a, const float* b, int64_t n, float* out, spk_stream_t stream) {
+    if (n < 0) return SPK_ERR_ARG;
+    if (n == 0) return SPK_OK;
+    if (!a || !out) return SPK_ERR_ARG;
+    k_add<<<GRID1D(n, 256)>>>(a, b, n, out);
+    SPK_LAUNCH_CHECK();
+    return SPK_OK;
+}

@@ -1,0 +1,294 @@
+"""Kernel pipelines of the hot path (forward and reverse sweeps) and their ``torch.autograd.Function`` wrappers.
+
+The pipelines call only the C-ABI kernels of ``ops``; autograd is used as plumbing so that the reference's own
+``Forces`` logic (``torch.autograd.grad(E, R)``, /root/reference/src/schnetpack/atomistic/response.py:59-76) works
+unchanged on top of them.  First-order gradients w.r.t. ``_Rij`` / ``_positions`` (forces, stress through
+``_offsets``) are implemented; weight gradients / double backward (training) are not -- the modules
+refuse to run in training mode instead of silently returning wrong gradients.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+
+from . import ops
+from .ops import ACT_NONE, ACT_SILU, ACT_SSP
+
+Tensor = torch.Tensor
+
+
+def _c(t: Tensor) -> Tensor:
+    return t.detach().contiguous()
+
+
+def _ct(t: Tensor) -> Tensor:
+    return t.detach().t().contiguous()
+
+
+class ParamPack:
+    """Device-resident, kernel-ready copies of a module's weights (W and W^T), rebuilt when any parameter changes."""
+
+    def __init__(self):
+        self._sig = None
+
+    @staticmethod
+    def signature(tensors: List[Tensor]):
+        return tuple((t.data_ptr(), t._version, t.device, t.dtype) for t in tensors)
+
+    def stale(self, tensors: List[Tensor]) -> bool:
+        return self._sig != self.signature(tensors)
+
+    def mark(self, tensors: List[Tensor]):
+        self._sig = self.signature(tensors)
+
+
+ACT_CODES = {"silu": ACT_SILU, "ssp": ACT_SSP, None: ACT_NONE, "none": ACT_NONE}
+
+
+# =====================================================================================================================
+# PaiNN  (representation/painn.py:207-256)
+# =====================================================================================================================
+class PaiNNPack(ParamPack):
+    def build(self, mod):
+        F, T = mod.n_atom_basis, mod.n_interactions
+        self.F, self.T = F, T
+        self.eps = float(mod.mixing[0].epsilon)
+        self.emb = _c(mod.embedding.weight)
+        fw, fb = _c(mod.filter_net.weight), _c(mod.filter_net.bias)
+        self.wf, self.bf = [], []
+        for t in range(T):
+            if mod.share_filters:
+                self.wf.append(fw)
+                self.bf.append(fb)
+            else:
+                self.wf.append(fw[t * 3 * F:(t + 1) * 3 * F].contiguous())
+                self.bf.append(fb[t * 3 * F:(t + 1) * 3 * F].contiguous())
+        self.blocks = []
+        for t in range(T):
+            it, mx = mod.interactions[t], mod.mixing[t]
+            c0, c1 = it.interatomic_context_net[0], it.interatomic_context_net[1]
+            m0, m1 = mx.intraatomic_context_net[0], mx.intraatomic_context_net[1]
+            self.blocks.append(dict(
+                c0_t=_ct(c0.weight), c0=_c(c0.weight), c0_b=_c(c0.bias),
+                c1_t=_ct(c1.weight), c1=_c(c1.weight), c1_b=_c(c1.bias),
+                mix_t=_ct(mx.mu_channel_mix.weight), mix=_c(mx.mu_channel_mix.weight),
+                m0_t=_ct(m0.weight), m0=_c(m0.weight), m0_b=_c(m0.bias),
+                m1_t=_ct(m1.weight), m1=_c(m1.weight), m1_b=_c(m1.bias),
+            ))
+
+
+def painn_forward(pk: PaiNNPack, q0: Tensor, r_ij: Tensor, graph: ops.EdgeGraph, rbf_kind: int, n_rbf: int,
+                  rbf_p0: Tensor, rbf_p1: Optional[Tensor], cutoff: float, act: int, need_grad: bool):
+    """Returns q [N,F], mu [N,3,F] and the tape needed by painn_backward."""
+    F = pk.F
+    N = q0.shape[0]
+    phi, dphi, geo = ops.edge_geometry(r_ij, graph, rbf_kind, n_rbf, rbf_p0, rbf_p1, cutoff, need_grad)
+    q, mu = q0, None
+    tape = []
+    for t in range(pk.T):
+        b = pk.blocks[t]
+        a, hpre = ops.dense(q, b["c0_t"], b["c0_b"], act, save_pre=True)                     # painn.py:54
+        x = ops.dense(a, b["c1_t"], b["c1_b"])
+        q1, mu1 = ops.painn_edge_fwd(x, mu, q, phi, geo, graph, pk.wf[t], pk.bf[t], F, n_rbf)   # :55-65
+        VW = ops.dense(mu1.view(3 * N, F), b["mix_t"])                                       # :103  [3N,2F]
+        ctx = ops.painn_mix_ctx(q1, VW, F, pk.eps)                                           # :104-107
+        c, cpre = ops.dense(ctx, b["m0_t"], b["m0_b"], act, save_pre=True)                   # :108
+        s = ops.dense(c, b["m1_t"], b["m1_b"])
+        q2, mu2 = ops.painn_mix_update(q1, mu1, s, VW, F)                                    # :110-116
+        if need_grad:
+            tape.append((hpre, x, mu, VW, cpre, s))
+        q, mu = q2, mu2
+    return q, mu, (phi, dphi, geo, tape)
+
+
+def painn_backward(pk: PaiNNPack, saved, graph: ops.EdgeGraph, n_rbf: int, act: int, g_q: Tensor,
+                   g_mu: Optional[Tensor], n_edges_total: int) -> Tensor:
+    """dE/dr_ij [E,3] (in the caller's edge order) from dE/dq [N,F], dE/dmu [N,3,F]."""
+    F = pk.F
+    phi, dphi, geo, tape = saved
+    N = g_q.shape[0]
+    dev = g_q.device
+    g_rij = torch.empty((n_edges_total, 3), dtype=torch.float32, device=dev)
+    if g_mu is None:
+        g_mu = torch.zeros((N, 3, F), dtype=torch.float32, device=dev)
+    for t in reversed(range(pk.T)):
+        b = pk.blocks[t]
+        hpre, x, mu_in, VW, cpre, s = tape[t]
+        # --- mixing (painn.py:103-116) reversed
+        g_s, g_VW = ops.painn_mix_update_bwd(g_q, g_mu, s, VW, F)
+        g_c = ops.dense(g_s, b["m1"])                                                        # [N,3F]x[3F,F]
+        g_ctx = ops.dense(g_c, b["m0"], a_pre=cpre, a_act=act)                               # [N,F]x[F,2F]
+        g_q1 = ops.painn_mix_ctx_bwd(g_ctx, g_q, VW, g_VW, F, pk.eps)
+        g_mu1 = ops.dense(g_VW.view(3 * N, 2 * F), b["mix"], addend=g_mu.view(3 * N, F)).view(N, 3, F)
+        # --- interaction (painn.py:54-65) reversed
+        g_x, g_mu0 = ops.painn_edge_bwd(x, mu_in, g_q1, g_mu1, phi, dphi, geo, graph, pk.wf[t], pk.bf[t], F, n_rbf,
+                                        g_rij, accumulate=(t != pk.T - 1))
+        g_a = ops.dense(g_x, b["c1"])                                                        # [N,3F]x[3F,F]
+        g_q = ops.dense(g_a, b["c0"], a_pre=hpre, a_act=act, addend=g_q1)                    # [N,F]x[F,F] + residual
+        g_mu = g_mu0
+    return g_rij
+
+
+class PaiNNFunction(torch.autograd.Function):
+    """(q0 [N,F], r_ij [E,3]) -> (q, mu); backward gives dE/dr_ij (q0 = embedding output is treated as constant)."""
+
+    @staticmethod
+    def forward(ctx, r_ij, q0, holder):
+        mod, graph = holder["module"], holder["graph"]
+        pk = mod._pack()
+        need = r_ij.requires_grad
+        q, mu, saved = painn_forward(pk, q0, r_ij.detach(), graph, mod._rbf_kind, mod._n_rbf, mod._rbf_p0,
+                                     mod._rbf_p1, mod._cutoff_value, mod._act, need)
+        ctx.holder = dict(pk=pk, saved=saved, graph=graph, n_rbf=mod._n_rbf, act=mod._act, E=r_ij.shape[0])
+        ctx.set_materialize_grads(False)
+        return q, mu
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_q, g_mu):
+        h = ctx.holder
+        g_q = g_q.contiguous() if g_q is not None else None
+        if g_q is None:
+            g_q = torch.zeros((h["graph"].n_atoms, h["pk"].F), dtype=torch.float32, device=g_mu.device)
+        g_mu = g_mu.contiguous() if g_mu is not None else None
+        g_rij = painn_backward(h["pk"], h["saved"], h["graph"], h["n_rbf"], h["act"], g_q, g_mu, h["E"])
+        return g_rij, None, None
+
+
+# =====================================================================================================================
+# SchNet  (representation/schnet.py:147-173)
+# =====================================================================================================================
+class SchNetPack(ParamPack):
+    def build(self, mod):
+        self.F, self.T, self.NF = mod.n_atom_basis, len(mod.interactions), mod.n_filters
+        self.emb = _c(mod.embedding.weight)
+        self.blocks = []
+        for it in mod.interactions:
+            f0, f1 = it.filter_network[0], it.filter_network[1]
+            o0, o1 = it.f2out[0], it.f2out[1]
+            self.blocks.append(dict(
+                in2f_t=_ct(it.in2f.weight), in2f=_c(it.in2f.weight),
+                f0_t=_ct(f0.weight), f0=_c(f0.weight), f0_b=_c(f0.bias),
+                f1_t=_ct(f1.weight), f1=_c(f1.weight), f1_b=_c(f1.bias),
+                o0_t=_ct(o0.weight), o0=_c(o0.weight), o0_b=_c(o0.bias),
+                o1_t=_ct(o1.weight), o1=_c(o1.weight), o1_b=_c(o1.bias),
+            ))
+
+
+def schnet_forward(pk: SchNetPack, x0: Tensor, r_ij: Tensor, graph: ops.EdgeGraph, rbf_kind: int, n_rbf: int,
+                   rbf_p0, rbf_p1, cutoff: float, act: int, need_grad: bool):
+    NF = pk.NF
+    phi, dphi, geo = ops.edge_geometry(r_ij, graph, rbf_kind, n_rbf, rbf_p0, rbf_p1, cutoff, need_grad)
+    x = x0
+    tape = []
+    for t in range(pk.T):
+        b = pk.blocks[t]
+        h = ops.dense(x, b["in2f_t"])                                                        # schnet.py:60
+        w0, w0pre = ops.dense_strided(phi, n_rbf, b["f0_t"], bias=b["f0_b"], act=act, save_pre=True)   # :61
+        w_raw = ops.dense(w0, b["f1_t"], b["f1_b"])                                          # [E,NF]
+        m = ops.cfconv_fwd(h, w_raw, geo, graph, NF)                                         # :62-67
+        v0, v0pre = ops.dense(m, b["o0_t"], b["o0_b"], act, save_pre=True)                   # :69
+        x_new = ops.dense(v0, b["o1_t"], b["o1_b"], addend=x)                                # :69 + :168 residual
+        if need_grad:
+            tape.append((h, w0pre, w_raw, v0pre))
+        x = x_new
+    return x, (phi, dphi, geo, tape)
+
+
+def schnet_backward(pk: SchNetPack, saved, graph: ops.EdgeGraph, n_rbf: int, act: int, g_x: Tensor,
+                    n_edges_total: int) -> Tensor:
+    NF = pk.NF
+    phi, dphi, geo, tape = saved
+    dev = g_x.device
+    g_rij = torch.empty((n_edges_total, 3), dtype=torch.float32, device=dev)
+    KP = ops.kp(n_rbf)
+    for t in reversed(range(pk.T)):
+        b = pk.blocks[t]
+        h, w0pre, w_raw, v0pre = tape[t]
+        g_v0 = ops.dense(g_x, b["o1"])                                                       # [N,F]x[F,F]
+        g_m = ops.dense(g_v0, b["o0"], a_pre=v0pre, a_act=act)                               # [N,F]x[F,NF]
+        g_h, g_wraw, g_fc = ops.cfconv_bwd(h, w_raw, geo, g_m, graph, NF)
+        g_w0 = ops.dense(g_wraw, b["f1"])                                                    # [E,NF]x[NF,NF]
+        E = g_w0.shape[0]
+        g_phi = torch.empty((E, KP), dtype=torch.float32, device=dev)
+        ops.dense_into(g_w0, b["f0"], g_phi, KP, a_pre=w0pre, a_act=act)                     # [E,NF]x[NF,n_rbf]
+        ops.radial_bwd(g_phi, g_fc, dphi, geo, graph, n_rbf, g_rij, accumulate=(t != pk.T - 1))
+        g_x = ops.dense(g_h, b["in2f"], addend=g_x)                                          # + residual
+    return g_rij
+
+
+class SchNetFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, r_ij, x0, holder):
+        mod, graph = holder["module"], holder["graph"]
+        pk = mod._pack()
+        need = r_ij.requires_grad
+        x, saved = schnet_forward(pk, x0, r_ij.detach(), graph, mod._rbf_kind, mod._n_rbf, mod._rbf_p0, mod._rbf_p1,
+                                  mod._cutoff_value, mod._act, need)
+        ctx.holder = dict(pk=pk, saved=saved, graph=graph, n_rbf=mod._n_rbf, act=mod._act, E=r_ij.shape[0])
+        return x
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_x):
+        h = ctx.holder
+        g_rij = schnet_backward(h["pk"], h["saved"], h["graph"], h["n_rbf"], h["act"], g_x.contiguous(), h["E"])
+        return g_rij, None, None
+
+
+# =====================================================================================================================
+# Atomwise (atomistic/atomwise.py:69-88) and PairwiseDistances (atomistic/distances.py:14-26)
+# =====================================================================================================================
+class AtomwiseFunction(torch.autograd.Function):
+    """q [N,F] -> (y [N], energy [B]) for outnet = Dense(F->H, silu) -> Dense(H->1)."""
+
+    @staticmethod
+    def forward(ctx, q, holder):
+        pk, idx_m, n_mol, act = holder["pack"], holder["idx_m"], holder["n_mol"], holder["act"]
+        qd = q.detach().contiguous()
+        hid, hpre = ops.dense(qd, pk["w0_t"], pk["b0"], act, save_pre=True)
+        mol_ptr = ops.segment_ptr(idx_m, n_mol) if idx_m is not None else None
+        y, energy = ops.atomwise_out(hid, pk["w1"], pk["b1"], mol_ptr, n_mol)
+        ctx.holder = dict(pk=pk, hpre=hpre, idx_m=idx_m, act=act, N=q.shape[0])
+        ctx.set_materialize_grads(False)
+        if energy is None:
+            energy = y.new_zeros((0,))
+        return y, energy
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_y, g_e):
+        h = ctx.holder
+        pk = h["pk"]
+        H = pk["w1"].shape[0]
+        g_hid = None
+        if h["idx_m"] is not None and g_e is not None and g_e.numel() > 0:
+            g_hid = ops.atomwise_out_bwd(g_e.contiguous(), h["idx_m"], pk["w1"], h["N"], H)
+        if g_y is not None:  # per-atom output used downstream (rare): g_hid += g_y (x) w1  -- plumbing-level torch op
+            extra = g_y.contiguous()[:, None] * pk["w1"][None, :]
+            g_hid = extra if g_hid is None else g_hid + extra
+        if g_hid is None:
+            return None, None
+        g_q = ops.dense(g_hid.contiguous(), pk["w0"], a_pre=h["hpre"], a_act=h["act"])
+        return g_q, None
+
+
+class PairwiseDistancesFunction(torch.autograd.Function):
+    """Rij = R[idx_j] - R[idx_i] + offsets; backward assembles dE/dR per atom from the CSR/CSC views (no atomics)."""
+
+    @staticmethod
+    def forward(ctx, R, offsets, holder):
+        idx_i, idx_j = holder["idx_i"], holder["idx_j"]
+        ctx.holder = holder
+        ctx.off_grad = offsets is not None and offsets.requires_grad
+        return ops.pairwise_fwd(R.detach().contiguous(), idx_i, idx_j,
+                                offsets.detach().contiguous() if offsets is not None else None)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_rij):
+        g_rij = g_rij.contiguous()
+        graph = ctx.holder["graph"]
+        g_R = ops.pairwise_bwd(g_rij, graph, 1.0)
+        return g_R, (g_rij if ctx.off_grad else None), None

@@ -1,0 +1,211 @@
+"""Minimal mirror of the boundary caller ``schnetpack.model.NeuralNetworkPotential``
+(/root/reference/src/schnetpack/model/base.py:16-190) so that the B200 modules can be assembled and driven exactly
+like the reference's (input modules -> representation -> output modules -> postprocessors) on a box where the
+reference package is absent, plus ``convert_model`` which swaps the hot-path modules of an already-loaded reference
+model for their B200 counterparts (identical ``state_dict`` keys)."""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import atomistic, representation
+from . import nn as snn
+
+__all__ = ["AtomisticModel", "NeuralNetworkPotential", "convert_model"]
+
+
+class AtomisticModel(nn.Module):
+    """model/base.py:16-129."""
+
+    def __init__(self, postprocessors: Optional[List[nn.Module]] = None, input_dtype_str: str = "float32",
+                 do_postprocessing: bool = True):
+        super().__init__()
+        self.input_dtype_str = input_dtype_str
+        self.do_postprocessing = do_postprocessing
+        self.postprocessors = nn.ModuleList(postprocessors)
+        self.required_derivatives: Optional[List[str]] = None
+        self.model_outputs: Optional[List[str]] = None
+
+    def collect_derivatives(self) -> List[str]:
+        self.required_derivatives = None
+        required_derivatives = set()
+        for m in self.modules():
+            if hasattr(m, "required_derivatives") and m.required_derivatives is not None:
+                required_derivatives.update(m.required_derivatives)
+        self.required_derivatives = list(required_derivatives)
+        return self.required_derivatives
+
+    def collect_outputs(self) -> List[str]:
+        self.model_outputs = None
+        model_outputs = set()
+        for m in self.modules():
+            if hasattr(m, "model_outputs") and m.model_outputs is not None:
+                model_outputs.update(m.model_outputs)
+        self.model_outputs = list(model_outputs)
+        return self.model_outputs
+
+    def initialize_derivatives(self, inputs: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        for p in self.required_derivatives:
+            if p in inputs.keys():
+                inputs[p].requires_grad_()
+        return inputs
+
+    def postprocess(self, inputs: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        if self.do_postprocessing:
+            for pp in self.postprocessors:
+                inputs = pp(inputs)
+        return inputs
+
+    def extract_outputs(self, inputs: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        return {k: inputs[k] for k in self.model_outputs}
+
+
+class NeuralNetworkPotential(AtomisticModel):
+    """model/base.py:132-190."""
+
+    def __init__(self, representation: nn.Module, input_modules: List[nn.Module] = None,
+                 output_modules: List[nn.Module] = None, postprocessors: Optional[List[nn.Module]] = None,
+                 input_dtype_str: str = "float32", do_postprocessing: bool = True):
+        super().__init__(input_dtype_str=input_dtype_str, postprocessors=postprocessors,
+                         do_postprocessing=do_postprocessing)
+        self.representation = representation
+        self.input_modules = nn.ModuleList(input_modules)
+        self.output_modules = nn.ModuleList(output_modules)
+        self.collect_derivatives()
+        self.collect_outputs()
+
+    def forward(self, inputs: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        inputs = self.initialize_derivatives(inputs)
+        for m in self.input_modules:
+            inputs = m(inputs)
+        inputs = self.representation(inputs)
+        for m in self.output_modules:
+            inputs = m(inputs)
+        inputs = self.postprocess(inputs)
+        return self.extract_outputs(inputs)
+
+
+# --------------------------------------------------------------------------------------------------------- conversion
+def _convert_rbf(rb):
+    name = type(rb).__name__
+    if name == "GaussianRBF":
+        out = snn.GaussianRBF(rb.n_rbf, 1.0, trainable=isinstance(rb.widths, nn.Parameter))
+    elif name == "BesselRBF":
+        out = snn.BesselRBF(rb.n_rbf, 1.0)
+    else:
+        raise NotImplementedError(f"radial basis {name} has no B200 kernel")
+    out.load_state_dict(rb.state_dict())
+    return out
+
+
+def _convert_representation(rep):
+    name = type(rep).__name__
+    rbf = _convert_rbf(rep.radial_basis)
+    cut = snn.CosineCutoff(float(rep.cutoff_fn.cutoff))
+    if type(rep.cutoff_fn).__name__ != "CosineCutoff":
+        raise NotImplementedError(f"cutoff {type(rep.cutoff_fn).__name__} has no B200 kernel")
+    emb = rep.embedding if not isinstance(rep.embedding, nn.Embedding) else None
+    eemb = list(rep.electronic_embeddings) if len(getattr(rep, "electronic_embeddings", [])) else None
+    if name == "PaiNN":
+        shared = len(rep.interactions) > 1 and rep.interactions[0] is rep.interactions[1]
+        act = rep.interactions[0].interatomic_context_net[0].activation
+        new = representation.PaiNN(rep.n_atom_basis, rep.n_interactions, rbf, cut, activation=_map_act(act),
+                                   shared_interactions=shared, shared_filters=rep.share_filters,
+                                   epsilon=rep.mixing[0].epsilon, nuclear_embedding=emb, electronic_embeddings=eemb)
+    elif name == "SchNet":
+        shared = len(rep.interactions) > 1 and rep.interactions[0] is rep.interactions[1]
+        act = rep.interactions[0].f2out[0].activation
+        new = representation.SchNet(rep.n_atom_basis, len(rep.interactions), rbf, cut, n_filters=rep.n_filters,
+                                    shared_interactions=shared, activation=_map_act(act), nuclear_embedding=emb,
+                                    electronic_embeddings=eemb)
+    else:
+        raise NotImplementedError(f"representation {name} is outside the B200 hot path")
+    new.load_state_dict(rep.state_dict())
+    return new
+
+
+def _map_act(act):
+    import torch.nn.functional as F
+    code = snn.activation_code(act)
+    return {0: None, 1: F.silu, 2: snn.shifted_softplus}[code]
+
+
+def convert_model(model: nn.Module) -> NeuralNetworkPotential:
+    """Build a B200 ``NeuralNetworkPotential`` from a loaded reference model (duck-typed on class names; weights are
+    copied through ``state_dict`` whose keys are identical).  Modules outside the hot path (postprocessors, custom
+    embeddings, other output heads) are reused as they are."""
+    in_mods = []
+    for m in model.input_modules:
+        in_mods.append(atomistic.PairwiseDistances() if type(m).__name__ == "PairwiseDistances" else m)
+    out_mods = []
+    for m in model.output_modules:
+        n = type(m).__name__
+        if n == "Atomwise" and m.n_out == 1 and len(m.outnet) == 2:
+            act = _map_act(m.outnet[0].activation)
+            new = atomistic.Atomwise(m.outnet[0].in_features, 1, n_hidden=m.outnet[0].out_features, n_layers=2,
+                                     activation=act, aggregation_mode=m.aggregation_mode, output_key=m.output_key,
+                                     per_atom_output_key=m.per_atom_output_key)
+            new.load_state_dict(m.state_dict())
+            out_mods.append(new)
+        elif n == "Forces":
+            out_mods.append(atomistic.Forces(m.calc_forces, m.calc_stress, m.energy_key, m.force_key, m.stress_key))
+        else:
+            out_mods.append(m)
+    new = NeuralNetworkPotential(_convert_representation(model.representation), in_mods, out_mods,
+                                 list(model.postprocessors), getattr(model, "input_dtype_str", "float32"),
+                                 getattr(model, "do_postprocessing", True))
+    new.eval()
+    return new
+
+
+def from_spec(spec: dict, params: Optional[dict] = None, device=None) -> NeuralNetworkPotential:
+    """Assemble [PairwiseDistances] -> {PaiNN|SchNet} -> [Atomwise(energy), Forces] from a ``synthetic.model_spec``
+    dictionary and (optionally) a flat weight dictionary with the reference ``state_dict`` keys."""
+    import numpy as np
+
+    if spec["rbf"] == "gaussian":
+        rbf = snn.GaussianRBF(n_rbf=spec["n_rbf"], cutoff=spec["cutoff"])
+    else:
+        rbf = snn.BesselRBF(n_rbf=spec["n_rbf"], cutoff=spec["cutoff"])
+    cut = snn.CosineCutoff(spec["cutoff"])
+    if spec["kind"] == "painn":
+        rep = representation.PaiNN(spec["n_atom_basis"], spec["n_interactions"], rbf, cut,
+                                   shared_interactions=spec["shared_interactions"],
+                                   shared_filters=spec["shared_filters"], epsilon=spec["epsilon"])
+    else:
+        rep = representation.SchNet(spec["n_atom_basis"], spec["n_interactions"], rbf, cut,
+                                    n_filters=spec["n_filters"], shared_interactions=spec["shared_interactions"])
+    outs: List[nn.Module] = [atomistic.Atomwise(n_in=spec["n_atom_basis"], output_key="energy")]
+    if spec.get("forces", True):
+        outs.append(atomistic.Forces(energy_key="energy", force_key="forces"))
+    model = NeuralNetworkPotential(rep, [atomistic.PairwiseDistances()], outs, postprocessors=[],
+                                   do_postprocessing=False)
+    if params is not None:
+        import re
+        sd = model.state_dict()
+        new = {}
+        for k in sd:
+            kk = k
+            if k not in params and spec["shared_interactions"]:
+                kk = re.sub(r"\.(interactions|mixing)\.\d+\.", r".\1.0.", k)
+            new[k] = torch.as_tensor(np.asarray(params[kk])).to(sd[k].dtype)
+        model.load_state_dict(new)
+    model.eval()
+    if device is not None:
+        model = model.to(device)
+    return model
+
+
+def batch_to_device(batch: dict, device, pin: bool = False) -> Dict[str, torch.Tensor]:
+    """numpy batch (``synthetic``) -> dict of tensors on ``device`` (fp32 / int64 like the reference's collate)."""
+    out = {}
+    for k, v in batch.items():
+        t = torch.as_tensor(v)
+        if t.is_floating_point():
+            t = t.float()
+        if pin:
+            t = t.pin_memory()
+        out[k] = t.to(device, non_blocking=pin)
+    return out

@@ -1,0 +1,331 @@
+"""Python-side plumbing over the C ABI: tensor checks, buffer allocation (torch owns device memory), stream handoff.
+
+Every function here launches hand-written sm_100a kernels from ``csrc/`` through ``include/spk_b200.h``; there is no
+torch arithmetic on the hot path and no CPU fallback (non-CUDA tensors raise).
+"""
+from __future__ import annotations
+
+import weakref
+from ctypes import c_void_p
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import ACT_NONE, ACT_SILU, ACT_SSP, GEO_STRIDE, RBF_BESSEL, RBF_GAUSSIAN  # noqa: F401
+
+Tensor = torch.Tensor
+
+
+def _p(t: Optional[Tensor]):
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def _stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _chk(t: Tensor, dtype, name: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"schnetpack_b200: '{name}' must be a CUDA tensor (no CPU fallback); got {t.device}")
+    if t.dtype != dtype:
+        raise TypeError(f"schnetpack_b200: '{name}' must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"schnetpack_b200: '{name}' must be contiguous")
+    return t
+
+
+def f32(t: Tensor, name: str = "tensor") -> Tensor:
+    return _chk(t, torch.float32, name)
+
+
+def i64(t: Tensor, name: str = "index") -> Tensor:
+    return _chk(t, torch.int64, name)
+
+
+def kp(n_rbf: int) -> int:
+    return (n_rbf + 3) & ~3
+
+
+# ------------------------------------------------------------------------------------------------------------ graph
+class EdgeGraph:
+    """Receiver-grouped (CSR) and sender-grouped views of an (idx_i, idx_j) edge list, built on device."""
+
+    __slots__ = ("n_atoms", "n_edges", "rowptr", "slot_j", "slot_eid", "sptr", "pos_slot", "pos_i", "status",
+                 "_ref_i", "_ref_j", "_ver", "__weakref__")
+
+    def __init__(self, idx_i: Tensor, idx_j: Tensor, n_atoms: int):
+        i64(idx_i, "_idx_i")
+        i64(idx_j, "_idx_j")
+        if idx_i.shape != idx_j.shape or idx_i.dim() != 1:
+            raise ValueError("idx_i / idx_j must be 1-D and of equal length")
+        dev = idx_i.device
+        E = idx_i.shape[0]
+        self.n_atoms, self.n_edges = int(n_atoms), int(E)
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.rowptr = torch.empty(n_atoms + 1, **i32)
+        self.sptr = torch.empty(n_atoms + 1, **i32)
+        self.slot_j = torch.empty(max(E, 1), **i32)
+        self.slot_eid = torch.empty(max(E, 1), **i32)
+        self.pos_slot = torch.empty(max(E, 1), **i32)
+        self.pos_i = torch.empty(max(E, 1), **i32)
+        self.status = torch.empty(4, **i32)
+        nbytes = _lib.lib().spk_graph_workspace_bytes(n_atoms, E)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _lib.call("spk_graph_build", _p(idx_i), _p(idx_j), n_atoms, E, _p(self.rowptr), _p(self.slot_j),
+                  _p(self.slot_eid), _p(self.sptr), _p(self.pos_slot), _p(self.pos_i), _p(self.status), _p(ws),
+                  nbytes, _stream())
+        self._ref_i = weakref.ref(idx_i)
+        self._ref_j = weakref.ref(idx_j)
+        self._ver = (idx_i._version, idx_j._version)
+
+    def matches(self, idx_i: Tensor, idx_j: Tensor, n_atoms: int) -> bool:
+        return (self._ref_i() is idx_i and self._ref_j() is idx_j and self.n_atoms == n_atoms
+                and self._ver == (idx_i._version, idx_j._version))
+
+    def validate(self):
+        """Host-synchronising check of the device status word (bad indices) -- used by tests / debug only."""
+        st = self.status.tolist()
+        if st[1] != 0:
+            raise IndexError(f"{st[1]} neighbour indices out of range [0, {self.n_atoms})")
+        return dict(sorted=bool(st[0]), max_in_degree=st[2], max_out_degree=st[3])
+
+
+_GRAPH_CACHE: "dict[int, EdgeGraph]" = {}
+_GRAPH_CACHE_MAX = 8
+
+
+def get_graph(idx_i: Tensor, idx_j: Tensor, n_atoms: int) -> EdgeGraph:
+    """Graph for this exact pair of index tensors (identity + version checked), rebuilt when they change."""
+    key = id(idx_i)
+    g = _GRAPH_CACHE.get(key)
+    if g is not None and g.matches(idx_i, idx_j, n_atoms):
+        return g
+    g = EdgeGraph(idx_i, idx_j, n_atoms)
+    if len(_GRAPH_CACHE) >= _GRAPH_CACHE_MAX:
+        _GRAPH_CACHE.pop(next(iter(_GRAPH_CACHE)))
+    _GRAPH_CACHE[key] = g
+    return g
+
+
+def segment_ptr(idx_m: Tensor, n_mol: int) -> Tensor:
+    i64(idx_m, "_idx_m")
+    out = torch.empty(n_mol + 1, dtype=torch.int32, device=idx_m.device)
+    _lib.call("spk_segment_ptr", _p(idx_m), idx_m.shape[0], n_mol, _p(out), _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------ geometry
+def pairwise_fwd(R: Tensor, idx_i: Tensor, idx_j: Tensor, offsets: Optional[Tensor]) -> Tensor:
+    f32(R, "_positions")
+    E = idx_i.shape[0]
+    out = torch.empty((E, 3), dtype=torch.float32, device=R.device)
+    _lib.call("spk_pairwise_fwd", _p(R), _p(i64(idx_i)), _p(i64(idx_j)),
+              _p(f32(offsets, "_offsets")) if offsets is not None else None, E, _p(out), _stream())
+    return out
+
+
+def pairwise_bwd(g_rij: Tensor, graph: EdgeGraph, sign: float = 1.0) -> Tensor:
+    f32(g_rij, "g_rij")
+    out = torch.empty((graph.n_atoms, 3), dtype=torch.float32, device=g_rij.device)
+    _lib.call("spk_pairwise_bwd", _p(g_rij), _p(graph.rowptr), _p(graph.slot_eid), _p(graph.sptr), _p(graph.pos_slot),
+              graph.n_atoms, float(sign), _p(out), _stream())
+    return out
+
+
+def edge_geometry(r_ij: Tensor, graph: Optional[EdgeGraph], rbf_kind: int, n_rbf: int, p0: Tensor, p1: Optional[Tensor],
+                  cutoff: float, need_grad: bool = True):
+    f32(r_ij, "_Rij")
+    E = r_ij.shape[0]
+    KP = kp(n_rbf)
+    dev = r_ij.device
+    phi = torch.empty((E, KP), dtype=torch.float32, device=dev)
+    dphi = torch.empty((E, KP), dtype=torch.float32, device=dev) if need_grad else None
+    geo = torch.empty((E, GEO_STRIDE), dtype=torch.float32, device=dev)
+    _lib.call("spk_edge_geometry", _p(r_ij), _p(graph.slot_eid) if graph is not None else None, E, rbf_kind, n_rbf,
+              _p(f32(p0)), _p(f32(p1)) if p1 is not None else None, float(cutoff), _p(phi), _p(dphi), _p(geo),
+              _stream())
+    return phi, dphi, geo
+
+
+def rbf(d: Tensor, rbf_kind: int, p0: Tensor, p1: Optional[Tensor], need_grad: bool = False):
+    f32(d, "d")
+    n_rbf = p0.shape[0]
+    out = torch.empty(tuple(d.shape) + (n_rbf,), dtype=torch.float32, device=d.device)
+    dout = torch.empty_like(out) if need_grad else None
+    _lib.call("spk_rbf_fwd", _p(d), d.numel(), rbf_kind, n_rbf, _p(f32(p0)), _p(f32(p1)) if p1 is not None else None,
+              _p(out), _p(dout), _stream())
+    return out, dout
+
+
+def cosine_cutoff(d: Tensor, cutoff: float, need_grad: bool = False):
+    f32(d, "d")
+    out = torch.empty_like(d)
+    dout = torch.empty_like(d) if need_grad else None
+    _lib.call("spk_cosine_cutoff_fwd", _p(d), d.numel(), float(cutoff), _p(out), _p(dout), _stream())
+    return out, dout
+
+
+def activation(x: Tensor, act: int, need_grad: bool = False):
+    f32(x, "x")
+    y = torch.empty_like(x)
+    dy = torch.empty_like(x) if need_grad else None
+    _lib.call("spk_act_fwd", _p(x), x.numel(), act, _p(y), _p(dy), _stream())
+    return y, dy
+
+
+def embedding(table: Tensor, Z: Tensor) -> Tensor:
+    f32(table, "embedding.weight")
+    i64(Z, "_atomic_numbers")
+    out = torch.empty((Z.shape[0], table.shape[1]), dtype=torch.float32, device=table.device)
+    _lib.call("spk_embedding", _p(table), _p(Z), Z.shape[0], table.shape[1], table.shape[0], _p(out), _stream())
+    return out
+
+
+def segment_sum(x: Tensor, rowptr: Tensor, slot_eid: Optional[Tensor], n_out: int) -> Tensor:
+    f32(x, "x")
+    C = 1
+    for d in x.shape[1:]:
+        C *= int(d)
+    out = torch.empty((n_out,) + tuple(x.shape[1:]), dtype=torch.float32, device=x.device)
+    _lib.call("spk_segment_sum", _p(x), _p(rowptr), _p(slot_eid), n_out, max(C, 1), _p(out), _stream())
+    return out
+
+
+def add(a: Tensor, b: Optional[Tensor], out: Optional[Tensor] = None) -> Tensor:
+    f32(a)
+    if out is None:
+        out = torch.empty_like(a)
+    _lib.call("spk_add", _p(a), _p(b), a.numel(), _p(out), _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------ dense
+def dense(A: Tensor, B: Tensor, bias: Optional[Tensor] = None, act: int = ACT_NONE, a_pre: Optional[Tensor] = None,
+          a_act: int = ACT_NONE, addend: Optional[Tensor] = None, save_pre: bool = False, k: Optional[int] = None,
+          out: Optional[Tensor] = None):
+    """Y = act((A .* act'(a_pre)) @ B + bias) + addend ; A [M,lda] (first k columns used), B [K,N] contiguous.
+    ``out`` [M, ldy>=N] may be given (padded outputs).  Returns Y or (Y, pre)."""
+    f32(A, "A")
+    f32(B, "B")
+    M, lda = A.shape
+    K = lda if k is None else int(k)
+    K2, N = B.shape
+    if K2 != K:
+        raise ValueError(f"dense: inner dimensions differ ({K} vs {K2})")
+    if out is None:
+        Y = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    else:
+        Y = f32(out, "out")
+        if Y.shape[0] != M or Y.shape[1] < N:
+            raise ValueError("dense: bad output buffer")
+    ldy = Y.shape[1]
+    pre = torch.empty_like(Y) if save_pre else None
+    if addend is not None and (addend.shape[0] != M or addend.shape[1] != N):
+        raise ValueError("dense: addend shape mismatch")
+    _lib.call("spk_dense", _p(A), M, K, lda, _p(a_pre), a_act, _p(B), N, _p(bias), act, _p(addend), N, _p(Y), ldy,
+              _p(pre), _stream())
+    return (Y, pre) if save_pre else Y
+
+
+def dense_strided(A: Tensor, k: int, B: Tensor, **kw):
+    return dense(A, B, k=k, **kw)
+
+
+def dense_into(A: Tensor, B: Tensor, out: Tensor, ldy: int, **kw):
+    assert out.shape[1] == ldy
+    return dense(A, B, out=out, **kw)
+
+
+# ------------------------------------------------------------------------------------------------------------ PaiNN
+def painn_edge_fwd(x, mu, q, phi, geo, graph: EdgeGraph, wf, bf, F: int, n_rbf: int):
+    N = graph.n_atoms
+    q_out = torch.empty((N, F), dtype=torch.float32, device=x.device)
+    mu_out = torch.empty((N, 3, F), dtype=torch.float32, device=x.device)
+    _lib.call("spk_painn_edge_fwd", _p(x), _p(mu), _p(q), _p(phi), _p(geo), _p(graph.rowptr), _p(graph.slot_j),
+              _p(wf), _p(bf), N, graph.n_edges, F, n_rbf, _p(q_out), _p(mu_out), _stream())
+    return q_out, mu_out
+
+
+def painn_edge_bwd(x, mu, g_q, g_mu, phi, dphi, geo, graph: EdgeGraph, wf, bf, F: int, n_rbf: int, g_rij: Tensor,
+                   accumulate: bool):
+    N = graph.n_atoms
+    g_x = torch.empty((N, 3 * F), dtype=torch.float32, device=x.device)
+    g_mu_in = torch.empty((N, 3, F), dtype=torch.float32, device=x.device) if mu is not None else None
+    _lib.call("spk_painn_edge_bwd", _p(x), _p(mu), _p(g_q), _p(g_mu), _p(phi), _p(dphi), _p(geo), _p(graph.sptr),
+              _p(graph.pos_slot), _p(graph.pos_i), _p(graph.slot_eid), _p(wf), _p(bf), N, graph.n_edges, F, n_rbf,
+              _p(g_x), _p(g_mu_in), _p(g_rij), 1 if accumulate else 0, _stream())
+    return g_x, g_mu_in
+
+
+def painn_mix_ctx(q, VW, F: int, eps: float):
+    N = q.shape[0]
+    ctx = torch.empty((N, 2 * F), dtype=torch.float32, device=q.device)
+    _lib.call("spk_painn_mix_ctx", _p(q), _p(VW), N, F, float(eps), _p(ctx), _stream())
+    return ctx
+
+
+def painn_mix_update(q, mu, s, VW, F: int):
+    N = q.shape[0]
+    q_out = torch.empty_like(q)
+    mu_out = torch.empty_like(mu)
+    _lib.call("spk_painn_mix_update", _p(q), _p(mu), _p(s), _p(VW), N, F, _p(q_out), _p(mu_out), _stream())
+    return q_out, mu_out
+
+
+def painn_mix_update_bwd(g_q, g_mu, s, VW, F: int):
+    N = g_q.shape[0]
+    g_s = torch.empty((N, 3 * F), dtype=torch.float32, device=g_q.device)
+    g_VW = torch.empty((N, 3, 2 * F), dtype=torch.float32, device=g_q.device)
+    _lib.call("spk_painn_mix_update_bwd", _p(g_q), _p(g_mu), _p(s), _p(VW), N, F, _p(g_s), _p(g_VW), _stream())
+    return g_s, g_VW
+
+
+def painn_mix_ctx_bwd(g_ctx, g_q, VW, g_VW, F: int, eps: float):
+    N = g_q.shape[0]
+    g_q_out = torch.empty_like(g_q)
+    _lib.call("spk_painn_mix_ctx_bwd", _p(g_ctx), _p(g_q), _p(VW), N, F, float(eps), _p(g_q_out), _p(g_VW), _stream())
+    return g_q_out
+
+
+# ------------------------------------------------------------------------------------------------------------ SchNet
+def cfconv_fwd(h, w_raw, geo, graph: EdgeGraph, F: int):
+    N = graph.n_atoms
+    m = torch.empty((N, F), dtype=torch.float32, device=h.device)
+    _lib.call("spk_cfconv_fwd", _p(h), _p(w_raw), _p(geo), _p(graph.rowptr), _p(graph.slot_j), N, graph.n_edges, F,
+              _p(m), _stream())
+    return m
+
+
+def cfconv_bwd(h, w_raw, geo, g_m, graph: EdgeGraph, F: int):
+    N, E = graph.n_atoms, graph.n_edges
+    g_h = torch.empty((N, F), dtype=torch.float32, device=h.device)
+    g_wraw = torch.empty((E, F), dtype=torch.float32, device=h.device)
+    g_fc = torch.empty((E,), dtype=torch.float32, device=h.device)
+    _lib.call("spk_cfconv_bwd", _p(h), _p(w_raw), _p(geo), _p(g_m), _p(graph.sptr), _p(graph.pos_slot),
+              _p(graph.pos_i), N, E, F, _p(g_h), _p(g_wraw), _p(g_fc), _stream())
+    return g_h, g_wraw, g_fc
+
+
+def radial_bwd(g_phi, g_fc, dphi, geo, graph: Optional[EdgeGraph], n_rbf: int, g_rij: Tensor, accumulate: bool):
+    E = geo.shape[0]
+    _lib.call("spk_radial_bwd", _p(g_phi), _p(g_fc), _p(dphi), _p(geo),
+              _p(graph.slot_eid) if graph is not None else None, E, n_rbf, _p(g_rij), 1 if accumulate else 0,
+              _stream())
+    return g_rij
+
+
+# ------------------------------------------------------------------------------------------------------------ head
+def atomwise_out(hid, w1, b1, mol_ptr: Optional[Tensor], n_mol: int):
+    N, H = hid.shape
+    y = torch.empty((N,), dtype=torch.float32, device=hid.device)
+    energy = torch.empty((n_mol,), dtype=torch.float32, device=hid.device) if mol_ptr is not None else None
+    _lib.call("spk_atomwise_out", _p(hid), _p(w1), _p(b1), _p(mol_ptr), N, n_mol if mol_ptr is not None else 0, H,
+              _p(y), _p(energy), _stream())
+    return y, energy
+
+
+def atomwise_out_bwd(g_energy: Optional[Tensor], idx_m: Optional[Tensor], w1, n_atoms: int, H: int):
+    g_hid = torch.empty((n_atoms, H), dtype=torch.float32, device=w1.device)
+    _lib.call("spk_atomwise_out_bwd", _p(g_energy), _p(idx_m), _p(w1), n_atoms, H, _p(g_hid), _stream())
+    return g_hid
