@@ -63,8 +63,7 @@ class Atomwise(nn.Module):
         sig = K.ParamPack.signature(params)
         if self._sig != sig:
             l0, l1 = self.outnet[0], self.outnet[1]
-            self._pk = dict(w0_t=l0.weight.detach().t().contiguous(), w0=l0.weight.detach().contiguous(),
-                            b0=l0.bias.detach().contiguous() if l0.bias is not None else None,
+            self._pk = dict(l0=ops.Lin(l0.weight, l0.bias),
                             w1=l1.weight.detach().reshape(-1).contiguous(),
                             b1=l1.bias.detach().contiguous() if l1.bias is not None else None)
             self._sig = sig

@@ -19,6 +19,18 @@ static inline int64_t spk_cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 constexpr int SPK_NUM_SMS = 148;  // B200: 2 dies x 74 SMs
 
+// SM count of the current device (148 on B200); queried once.
+static inline int spk_num_sms() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = SPK_NUM_SMS;
+    }
+    return n;
+}
+
 __host__ __device__ __forceinline__ int spk_kp(int n_rbf) { return (n_rbf + 3) & ~3; }
 
 // ---- activations (match torch fp32 semantics) --------------------------------------------------------------------

@@ -434,8 +434,16 @@ template <int NW, int NRB>
 int launch_edge_fwd(const float* x, const float* mu, const float* q, const float* phi, const float* geo,
                     const int* rowptr, const int* slot_j, const float* wf, const float* bf, int n_atoms, int n_edges,
                     int n_rbf, float* q_out, float* mu_out, cudaStream_t st) {
-    // ~96 edges per CTA, at least one CTA, at most one CTA per atom
-    int64_t nb = spk_cdiv((int64_t)n_edges, 96);
+    // exactly one resident wave of CTAs (no tail), >= 32 edges per CTA, at most one CTA per atom
+    static int occ_mu = 0, occ_nomu = 0;
+    if (!occ_mu) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_mu, k_painn_edge_fwd<NW, NRB, true>, NW * 32, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_nomu, k_painn_edge_fwd<NW, NRB, false>, NW * 32, 0);
+        if (occ_mu < 1) occ_mu = 1;
+        if (occ_nomu < 1) occ_nomu = 1;
+    }
+    int64_t nb = (int64_t)spk_num_sms() * (mu ? occ_mu : occ_nomu);
+    if (nb > spk_cdiv((int64_t)n_edges, 32)) nb = spk_cdiv((int64_t)n_edges, 32);
     if (nb < 1) nb = 1;
     if (nb > n_atoms) nb = n_atoms;
     if (mu)
@@ -452,7 +460,15 @@ int launch_edge_bwd(const float* x, const float* mu, const float* g_q, const flo
                     const float* dphi, const float* geo, const int* sptr, const int* pos_slot, const int* pos_i,
                     const int* slot_eid, const float* wf, const float* bf, int n_atoms, int n_edges, int n_rbf,
                     float* g_x, float* g_mu_in, float* g_rij, int accumulate, cudaStream_t st) {
-    int64_t nb = spk_cdiv((int64_t)n_edges, 96);
+    static int occ_mu = 0, occ_nomu = 0;
+    if (!occ_mu) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_mu, k_painn_edge_bwd<NW, NRB, true>, NW * 32, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_nomu, k_painn_edge_bwd<NW, NRB, false>, NW * 32, 0);
+        if (occ_mu < 1) occ_mu = 1;
+        if (occ_nomu < 1) occ_nomu = 1;
+    }
+    int64_t nb = (int64_t)spk_num_sms() * (mu ? occ_mu : occ_nomu);
+    if (nb > spk_cdiv((int64_t)n_edges, 32)) nb = spk_cdiv((int64_t)n_edges, 32);
     if (nb < 1) nb = 1;
     if (nb > n_atoms) nb = n_atoms;
     if (mu)

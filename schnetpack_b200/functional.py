@@ -70,11 +70,8 @@ class PaiNNPack(ParamPack):
             c0, c1 = it.interatomic_context_net[0], it.interatomic_context_net[1]
             m0, m1 = mx.intraatomic_context_net[0], mx.intraatomic_context_net[1]
             self.blocks.append(dict(
-                c0_t=_ct(c0.weight), c0=_c(c0.weight), c0_b=_c(c0.bias),
-                c1_t=_ct(c1.weight), c1=_c(c1.weight), c1_b=_c(c1.bias),
-                mix_t=_ct(mx.mu_channel_mix.weight), mix=_c(mx.mu_channel_mix.weight),
-                m0_t=_ct(m0.weight), m0=_c(m0.weight), m0_b=_c(m0.bias),
-                m1_t=_ct(m1.weight), m1=_c(m1.weight), m1_b=_c(m1.bias),
+                c0=ops.Lin(c0.weight, c0.bias), c1=ops.Lin(c1.weight, c1.bias),
+                mix=ops.Lin(mx.mu_channel_mix.weight), m0=ops.Lin(m0.weight, m0.bias), m1=ops.Lin(m1.weight, m1.bias),
             ))
 
 
@@ -88,13 +85,13 @@ def painn_forward(pk: PaiNNPack, q0: Tensor, r_ij: Tensor, graph: ops.EdgeGraph,
     tape = []
     for t in range(pk.T):
         b = pk.blocks[t]
-        a, hpre = ops.dense(q, b["c0_t"], b["c0_b"], act, save_pre=True)                     # painn.py:54
-        x = ops.dense(a, b["c1_t"], b["c1_b"])
+        a, hpre = b["c0"].fwd(q, act, save_pre=True)                                         # painn.py:54
+        x = b["c1"].fwd(a)
         q1, mu1 = ops.painn_edge_fwd(x, mu, q, phi, geo, graph, pk.wf[t], pk.bf[t], F, n_rbf)   # :55-65
-        VW = ops.dense(mu1.view(3 * N, F), b["mix_t"])                                       # :103  [3N,2F]
+        VW = b["mix"].fwd(mu1.view(3 * N, F))                                                # :103  [3N,2F]
         ctx = ops.painn_mix_ctx(q1, VW, F, pk.eps)                                           # :104-107
-        c, cpre = ops.dense(ctx, b["m0_t"], b["m0_b"], act, save_pre=True)                   # :108
-        s = ops.dense(c, b["m1_t"], b["m1_b"])
+        c, cpre = b["m0"].fwd(ctx, act, save_pre=True)                                       # :108
+        s = b["m1"].fwd(c)
         q2, mu2 = ops.painn_mix_update(q1, mu1, s, VW, F)                                    # :110-116
         if need_grad:
             tape.append((hpre, x, mu, VW, cpre, s))
@@ -117,15 +114,15 @@ def painn_backward(pk: PaiNNPack, saved, graph: ops.EdgeGraph, n_rbf: int, act: 
         hpre, x, mu_in, VW, cpre, s = tape[t]
         # --- mixing (painn.py:103-116) reversed
         g_s, g_VW = ops.painn_mix_update_bwd(g_q, g_mu, s, VW, F)
-        g_c = ops.dense(g_s, b["m1"])                                                        # [N,3F]x[3F,F]
-        g_ctx = ops.dense(g_c, b["m0"], a_pre=cpre, a_act=act)                               # [N,F]x[F,2F]
+        g_c = b["m1"].bwd(g_s)                                                               # [N,3F]x[3F,F]
+        g_ctx = b["m0"].bwd(g_c, a_pre=cpre, a_act=act)                                      # [N,F]x[F,2F]
         g_q1 = ops.painn_mix_ctx_bwd(g_ctx, g_q, VW, g_VW, F, pk.eps)
-        g_mu1 = ops.dense(g_VW.view(3 * N, 2 * F), b["mix"], addend=g_mu.view(3 * N, F)).view(N, 3, F)
+        g_mu1 = b["mix"].bwd(g_VW.view(3 * N, 2 * F), addend=g_mu.view(3 * N, F)).view(N, 3, F)
         # --- interaction (painn.py:54-65) reversed
         g_x, g_mu0 = ops.painn_edge_bwd(x, mu_in, g_q1, g_mu1, phi, dphi, geo, graph, pk.wf[t], pk.bf[t], F, n_rbf,
                                         g_rij, accumulate=(t != pk.T - 1))
-        g_a = ops.dense(g_x, b["c1"])                                                        # [N,3F]x[3F,F]
-        g_q = ops.dense(g_a, b["c0"], a_pre=hpre, a_act=act, addend=g_q1)                    # [N,F]x[F,F] + residual
+        g_a = b["c1"].bwd(g_x)                                                               # [N,3F]x[3F,F]
+        g_q = b["c0"].bwd(g_a, a_pre=hpre, a_act=act, addend=g_q1)                           # [N,F]x[F,F] + residual
         g_mu = g_mu0
     return g_rij
 
@@ -168,11 +165,8 @@ class SchNetPack(ParamPack):
             f0, f1 = it.filter_network[0], it.filter_network[1]
             o0, o1 = it.f2out[0], it.f2out[1]
             self.blocks.append(dict(
-                in2f_t=_ct(it.in2f.weight), in2f=_c(it.in2f.weight),
-                f0_t=_ct(f0.weight), f0=_c(f0.weight), f0_b=_c(f0.bias),
-                f1_t=_ct(f1.weight), f1=_c(f1.weight), f1_b=_c(f1.bias),
-                o0_t=_ct(o0.weight), o0=_c(o0.weight), o0_b=_c(o0.bias),
-                o1_t=_ct(o1.weight), o1=_c(o1.weight), o1_b=_c(o1.bias),
+                in2f=ops.Lin(it.in2f.weight), f0=ops.Lin(f0.weight, f0.bias), f1=ops.Lin(f1.weight, f1.bias),
+                o0=ops.Lin(o0.weight, o0.bias), o1=ops.Lin(o1.weight, o1.bias),
             ))
 
 
@@ -184,12 +178,12 @@ def schnet_forward(pk: SchNetPack, x0: Tensor, r_ij: Tensor, graph: ops.EdgeGrap
     tape = []
     for t in range(pk.T):
         b = pk.blocks[t]
-        h = ops.dense(x, b["in2f_t"])                                                        # schnet.py:60
-        w0, w0pre = ops.dense_strided(phi, n_rbf, b["f0_t"], bias=b["f0_b"], act=act, save_pre=True)   # :61
-        w_raw = ops.dense(w0, b["f1_t"], b["f1_b"])                                          # [E,NF]
+        h = b["in2f"].fwd(x)                                                                 # schnet.py:60
+        w0, w0pre = b["f0"].fwd(phi, act, save_pre=True, k=n_rbf)                            # :61 (phi is [E,KP])
+        w_raw = b["f1"].fwd(w0)                                                              # [E,NF]
         m = ops.cfconv_fwd(h, w_raw, geo, graph, NF)                                         # :62-67
-        v0, v0pre = ops.dense(m, b["o0_t"], b["o0_b"], act, save_pre=True)                   # :69
-        x_new = ops.dense(v0, b["o1_t"], b["o1_b"], addend=x)                                # :69 + :168 residual
+        v0, v0pre = b["o0"].fwd(m, act, save_pre=True)                                       # :69
+        x_new = b["o1"].fwd(v0, addend=x)                                                    # :69 + :168 residual
         if need_grad:
             tape.append((h, w0pre, w_raw, v0pre))
         x = x_new
@@ -206,15 +200,15 @@ def schnet_backward(pk: SchNetPack, saved, graph: ops.EdgeGraph, n_rbf: int, act
     for t in reversed(range(pk.T)):
         b = pk.blocks[t]
         h, w0pre, w_raw, v0pre = tape[t]
-        g_v0 = ops.dense(g_x, b["o1"])                                                       # [N,F]x[F,F]
-        g_m = ops.dense(g_v0, b["o0"], a_pre=v0pre, a_act=act)                               # [N,F]x[F,NF]
+        g_v0 = b["o1"].bwd(g_x)                                                              # [N,F]x[F,F]
+        g_m = b["o0"].bwd(g_v0, a_pre=v0pre, a_act=act)                                      # [N,F]x[F,NF]
         g_h, g_wraw, g_fc = ops.cfconv_bwd(h, w_raw, geo, g_m, graph, NF)
-        g_w0 = ops.dense(g_wraw, b["f1"])                                                    # [E,NF]x[NF,NF]
+        g_w0 = b["f1"].bwd(g_wraw)                                                           # [E,NF]x[NF,NF]
         E = g_w0.shape[0]
         g_phi = torch.empty((E, KP), dtype=torch.float32, device=dev)
-        ops.dense_into(g_w0, b["f0"], g_phi, KP, a_pre=w0pre, a_act=act)                     # [E,NF]x[NF,n_rbf]
+        b["f0"].bwd(g_w0, a_pre=w0pre, a_act=act, out=g_phi)                                 # [E,NF]x[NF,n_rbf]
         ops.radial_bwd(g_phi, g_fc, dphi, geo, graph, n_rbf, g_rij, accumulate=(t != pk.T - 1))
-        g_x = ops.dense(g_h, b["in2f"], addend=g_x)                                          # + residual
+        g_x = b["in2f"].bwd(g_h, addend=g_x)                                                 # + residual
     return g_rij
 
 
@@ -247,7 +241,7 @@ class AtomwiseFunction(torch.autograd.Function):
     def forward(ctx, q, holder):
         pk, idx_m, n_mol, act = holder["pack"], holder["idx_m"], holder["n_mol"], holder["act"]
         qd = q.detach().contiguous()
-        hid, hpre = ops.dense(qd, pk["w0_t"], pk["b0"], act, save_pre=True)
+        hid, hpre = pk["l0"].fwd(qd, act, save_pre=True)
         mol_ptr = ops.segment_ptr(idx_m, n_mol) if idx_m is not None else None
         y, energy = ops.atomwise_out(hid, pk["w1"], pk["b1"], mol_ptr, n_mol)
         ctx.holder = dict(pk=pk, hpre=hpre, idx_m=idx_m, act=act, N=q.shape[0])
@@ -270,7 +264,7 @@ class AtomwiseFunction(torch.autograd.Function):
             g_hid = extra if g_hid is None else g_hid + extra
         if g_hid is None:
             return None, None
-        g_q = ops.dense(g_hid.contiguous(), pk["w0"], a_pre=h["hpre"], a_act=h["act"])
+        g_q = pk["l0"].bwd(g_hid.contiguous(), a_pre=h["hpre"], a_act=h["act"])
         return g_q, None
 
 

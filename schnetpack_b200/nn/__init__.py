@@ -161,14 +161,14 @@ class _DenseFn(torch.autograd.Function):
     def forward(ctx, x, weight, bias, code):
         shp = x.shape
         x2 = x.detach().reshape(-1, shp[-1]).contiguous()
-        wt = weight.detach().t().contiguous()
+        lin = ops.Lin(weight, bias)
         need = x.requires_grad
+        ctx.pre = None
         if need:
-            y, pre = ops.dense(x2, wt, bias.detach().contiguous() if bias is not None else None, code, save_pre=True)
-            ctx.pre = pre
+            y, ctx.pre = lin.fwd(x2, code, save_pre=True)
         else:
-            y = ops.dense(x2, wt, bias.detach().contiguous() if bias is not None else None, code)
-        ctx.w = weight.detach().contiguous()
+            y = lin.fwd(x2, code)
+        ctx.lin = lin
         ctx.code = code
         ctx.shp = shp
         return y.view(*shp[:-1], weight.shape[0])
@@ -177,7 +177,7 @@ class _DenseFn(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, g):
         g2 = g.reshape(-1, g.shape[-1]).contiguous()
-        gx = ops.dense(g2, ctx.w, a_pre=ctx.pre if ctx.code != ops.ACT_NONE else None, a_act=ctx.code)
+        gx = ctx.lin.bwd(g2, a_pre=ctx.pre if ctx.code != ops.ACT_NONE else None, a_act=ctx.code)
         return gx.view(*ctx.shp), None, None, None
 
 

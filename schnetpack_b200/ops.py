@@ -5,6 +5,7 @@ torch arithmetic on the hot path and no CPU fallback (non-CUDA tensors raise).
 """
 from __future__ import annotations
 
+import os
 import weakref
 from ctypes import c_void_p
 from typing import Optional
@@ -226,6 +227,68 @@ def dense(A: Tensor, B: Tensor, bias: Optional[Tensor] = None, act: int = ACT_NO
     _lib.call("spk_dense", _p(A), M, K, lda, _p(a_pre), a_act, _p(B), N, _p(bias), act, _p(addend), N, _p(Y), ldy,
               _p(pre), _stream())
     return (Y, pre) if save_pre else Y
+
+
+def dense_tc(A: Tensor, w_hi: Tensor, w_lo: Tensor, bias: Optional[Tensor] = None, act: int = ACT_NONE,
+             a_pre: Optional[Tensor] = None, a_act: int = ACT_NONE, addend: Optional[Tensor] = None,
+             save_pre: bool = False, k: Optional[int] = None, out: Optional[Tensor] = None):
+    """tcgen05 / 3xTF32 variant of ``dense``: Y = act((A .* act'(a_pre)) @ W^T + bias) + addend with W = w_hi + w_lo
+    given as [N, K] (K contiguous)."""
+    f32(A, "A")
+    M, lda = A.shape
+    K = lda if k is None else int(k)
+    N, K2 = w_hi.shape
+    if K2 != K:
+        raise ValueError(f"dense_tc: inner dimensions differ ({K} vs {K2})")
+    if out is None:
+        Y = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    else:
+        Y = f32(out, "out")
+        if Y.shape[0] != M or Y.shape[1] < N:
+            raise ValueError("dense_tc: bad output buffer")
+    ldy = Y.shape[1]
+    pre = torch.empty_like(Y) if save_pre else None
+    if addend is not None and (addend.shape[0] != M or addend.shape[1] != N):
+        raise ValueError("dense_tc: addend shape mismatch")
+    _lib.call("spk_dense_tc", _p(A), M, K, lda, _p(a_pre), a_act, _p(f32(w_hi)), _p(f32(w_lo)), N, _p(bias), act,
+              _p(addend), N, _p(Y), ldy, _p(pre), _stream())
+    return (Y, pre) if save_pre else Y
+
+
+def split_tf32(w: Tensor):
+    """hi = round-to-nearest(ties away) TF32 of w (low 13 mantissa bits cleared), lo = w - hi (exact in fp32)."""
+    bits = w.contiguous().view(torch.int32)
+    hi = ((bits + 0x1000) & -8192).view(torch.float32)
+    return hi.contiguous(), (w - hi).contiguous()
+
+
+# "tc": tcgen05 3xTF32 tensor-core kernel (default) | "ffma": fp32 CUDA-core kernel (csrc/gemm.cu)
+DENSE_IMPL = os.environ.get("SPK_B200_DENSE", "tc")
+
+
+class Lin:
+    """Kernel-ready copy of one Dense layer: W [N,K], W^T [K,N], bias, and their TF32 hi/lo splits."""
+
+    __slots__ = ("w", "wt", "b", "w_hl", "wt_hl")
+
+    def __init__(self, weight: Tensor, bias: Optional[Tensor] = None):
+        self.w = weight.detach().contiguous()
+        self.wt = weight.detach().t().contiguous()
+        self.b = bias.detach().contiguous() if bias is not None else None
+        self.w_hl = split_tf32(self.w)
+        self.wt_hl = split_tf32(self.wt)
+
+    def fwd(self, A: Tensor, act: int = ACT_NONE, **kw):
+        """act(A W^T + b) [+ addend]"""
+        if DENSE_IMPL == "tc":
+            return dense_tc(A, self.w_hl[0], self.w_hl[1], self.b, act, **kw)
+        return dense(A, self.wt, self.b, act, **kw)
+
+    def bwd(self, G: Tensor, **kw):
+        """(G .* act'(a_pre)) W [+ addend]  -- input gradient of the layer"""
+        if DENSE_IMPL == "tc":
+            return dense_tc(G, self.wt_hl[0], self.wt_hl[1], None, ACT_NONE, **kw)
+        return dense(G, self.w, None, ACT_NONE, **kw)
 
 
 def dense_strided(A: Tensor, k: int, B: Tensor, **kw):

@@ -163,6 +163,39 @@ def test_dense(M, K, N):
         assert rel(Y2, (A.double() * dact) @ B.double()) < 3e-6
 
 
+@pytest.mark.parametrize("M,K,N,lda", [(5376, 128, 384, None), (1000, 256, 128, None), (333, 20, 128, 20),
+                                        (4100, 128, 20, None), (16128, 128, 256, None), (130, 128, 64, None),
+                                        (77, 384, 128, None), (2000, 20, 128, 24), (5, 64, 128, None)])
+def test_dense_tcgen05_3xtf32(M, K, N, lda):
+    """tcgen05 tensor-core layer with 3xTF32 compensation must be fp32-grade (the reference GEMMs are true fp32)."""
+    from schnetpack_b200 import ops
+
+    torch.manual_seed(3)
+    lda = lda or K
+    Afull = torch.randn(M, lda, device=DEV)
+    A = Afull[:, :K]
+    W = torch.randn(N, K, device=DEV) / math.sqrt(K)
+    bias = torch.randn(N, device=DEV)
+    add = torch.randn(M, N, device=DEV)
+    pre_in = torch.randn(M, lda, device=DEV)
+    w_hi, w_lo = ops.split_tf32(W)
+    assert torch.equal(w_hi + w_lo, W) and int((w_hi.view(torch.int32) & 0x1FFF).abs().max()) == 0
+    ref_lin = A.double() @ W.double().t() + bias.double()
+    for act, f in ((ops.ACT_NONE, lambda v: v), (ops.ACT_SILU, torch.nn.functional.silu),
+                   (ops.ACT_SSP, lambda v: torch.nn.functional.softplus(v) - math.log(2.0))):
+        Y, pre = ops.dense_tc(Afull, w_hi, w_lo, bias, act, addend=add, save_pre=True, k=K)
+        assert rel(pre, ref_lin) < 3e-6, rel(pre, ref_lin)
+        assert rel(Y, f(ref_lin) + add.double()) < 3e-6
+        p64 = pre_in[:, :K].double().requires_grad_()
+        dact = torch.autograd.grad(f(p64).sum(), p64)[0]
+        Y2 = ops.dense_tc(Afull, w_hi, w_lo, a_pre=pre_in, a_act=act, k=K)
+        assert rel(Y2, (A.double() * dact) @ W.double().t()) < 5e-6
+    # padded output buffer (ldy > N)
+    out = torch.full((M, N + 4), -1.0, device=DEV)
+    ops.dense_tc(Afull, w_hi, w_lo, bias, k=K, out=out)
+    assert rel(out[:, :N], ref_lin) < 3e-6 and bool((out[:, N:] == -1.0).all())
+
+
 def _painn_layer_ref(x, mu, q, r, ii, jj, wf, bf, rc, p0, p1):
     d = r.norm(dim=1, keepdim=True)
     u = r / d
