@@ -317,6 +317,7 @@ def run_cuda(args, rank, world, local_rank):
         dist.barrier()
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_value = world * B * args.steps / (float(t2.item()) * 1e-3)
+    e2e_steps_ms = sorted(s.elapsed_time(e) for s, e in e2e_ev)
 
     if rank != 0:
         return
@@ -367,7 +368,8 @@ def run_cuda(args, rank, world, local_rank):
         "edge_msgs_per_s": world * E * T * args.steps / (total_ms * 1e-3),
         "wall_ms_per_step": 1e3 * t_wall / args.steps,
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step_median": e2e_steps_ms[len(e2e_steps_ms) // 2], "ms_per_step_max": e2e_steps_ms[-1]},
         "gpu_launches": launches,
         "roofline": roof, "roofline_all": roof_all, "cpu_baseline": cpu,
     }

@@ -2,15 +2,15 @@
 // Reference: nn/base.py:52-55 (Dense.forward) and its autograd input-gradient.  True-fp32 accumulation like the
 // reference's default torch matmul precision ("highest", cli.py:95-97), so 1e-5 parity holds by construction.
 //
-// Tiling: BM=128 x BN=64 output tile per 256-thread CTA, BK=16, 8x4 register micro-tile per thread, A tile stored
-// k-major in shared memory so both operand fetches are conflict-free 128-bit LDS; next k-tile is prefetched into
-// registers while the current one is multiplied.
+// Tiling: BM x 64 output tile per CTA (BM = 128 / 256 threads, or 64 / 128 threads for grids that would not fill the
+// chip), BK=16, 8x4 register micro-tile per thread computed with packed FFMA2, A tile stored k-major in shared memory
+// so both operand fetches are conflict-free 128-bit LDS; double-buffered shared memory (one barrier per k-tile) with
+// the next k-tile prefetched into registers while the current one is multiplied.
 #include "common.cuh"
 
 namespace {
 
-constexpr int BM = 128, BN = 64, BK = 16, NT = 256;
-constexpr int AS_LD = BM + 4;
+constexpr int BN = 64, BK = 16;
 
 struct GemmArgs {
     const float* A;
@@ -24,27 +24,32 @@ struct GemmArgs {
     int K, N, a_act, act;
 };
 
-__global__ void __launch_bounds__(NT) k_dense(GemmArgs g) {
-    __shared__ __align__(16) float As[BK][AS_LD];
-    __shared__ __align__(16) float Bs[BK][BN];
+// BM = 128 (256 threads) for tall problems, BM = 64 (128 threads) when the 128-row grid would not fill the 148 SMs.
+template <int BM>
+__global__ void __launch_bounds__(BM * 2) k_dense(GemmArgs g) {
+    constexpr int NT = BM * 2;
+    constexpr int AS_LD = BM + 4;
+    constexpr int A_IT = 2;                       // float4 A loads per thread per k-tile: BM*BK/4 / NT
+    __shared__ __align__(16) float As[2][BK][AS_LD];
+    __shared__ __align__(16) float Bs[2][BK][BN];
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
     const int64_t m0 = (int64_t)blockIdx.x * BM;
     const int n0 = blockIdx.y * BN;
 
     // global->register staging
-    float4 ra[2];
-    float4 rb;
-    const int a_row = tid >> 2, a_kq = (tid & 3) * 4;  // rows a_row and a_row+64, k offset a_kq
-    const int b_k = tid >> 4, b_n = (tid & 15) * 4;
+    float4 ra[A_IT];
+    float4 rb[256 / NT];
+    const int a_row = tid >> 2, a_kq = (tid & 3) * 4;  // rows a_row (+ NT/4 per pass), k offset a_kq
+    const int b_k = tid >> 4, b_n = (tid & 15) * 4;    // B rows b_k (+ NT/16 per pass)
     const bool a_vec = ((g.lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0) &&
                        (!g.a_pre || (reinterpret_cast<uintptr_t>(g.a_pre) & 15) == 0);
     const bool b_vec = ((g.N & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.B) & 15) == 0);
 
     auto load_tiles = [&](int k0) {
 #pragma unroll
-        for (int it = 0; it < 2; ++it) {
-            int64_t m = m0 + a_row + it * 64;
+        for (int it = 0; it < A_IT; ++it) {
+            int64_t m = m0 + a_row + it * (NT / 4);
             int k = k0 + a_kq;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (m < g.M) {
@@ -71,8 +76,9 @@ __global__ void __launch_bounds__(NT) k_dense(GemmArgs g) {
             }
             ra[it] = v;
         }
-        {
-            int k = k0 + b_k, n = n0 + b_n;
+#pragma unroll
+        for (int it = 0; it < 256 / NT; ++it) {
+            int k = k0 + b_k + it * (NT / 16), n = n0 + b_n;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (k < g.K) {
                 const float* p = g.B + (int64_t)k * g.N + n;
@@ -86,47 +92,63 @@ __global__ void __launch_bounds__(NT) k_dense(GemmArgs g) {
                     v = make_float4(t[0], t[1], t[2], t[3]);
                 }
             }
-            rb = v;
+            rb[it] = v;
         }
     };
-    auto store_tiles = [&]() {
+    auto store_tiles = [&](int buf) {
 #pragma unroll
-        for (int it = 0; it < 2; ++it) {
-            int r = a_row + it * 64;
-            As[a_kq + 0][r] = ra[it].x;
-            As[a_kq + 1][r] = ra[it].y;
-            As[a_kq + 2][r] = ra[it].z;
-            As[a_kq + 3][r] = ra[it].w;
+        for (int it = 0; it < A_IT; ++it) {
+            int r = a_row + it * (NT / 4);
+            As[buf][a_kq + 0][r] = ra[it].x;
+            As[buf][a_kq + 1][r] = ra[it].y;
+            As[buf][a_kq + 2][r] = ra[it].z;
+            As[buf][a_kq + 3][r] = ra[it].w;
         }
-        *reinterpret_cast<float4*>(&Bs[b_k][b_n]) = rb;
+#pragma unroll
+        for (int it = 0; it < 256 / NT; ++it)
+            *reinterpret_cast<float4*>(&Bs[buf][b_k + it * (NT / 16)][b_n]) = rb[it];
     };
 
-    float acc[8][4];
+    // 8x4 micro-tile held as 4x4 float2 accumulators paired along M: Blackwell issues scalar FFMA at half rate, the
+    // packed FFMA2 (fma.rn.f32x2, __ffma2_rn) restores the full fp32 rate with IEEE round-to-nearest per component.
+    float2 acc2[4][4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < 4; ++j) acc2[i][j] = make_float2(0.f, 0.f);
 
     const int nk = (g.K + BK - 1) / BK;
     load_tiles(0);
+    store_tiles(0);
+    __syncthreads();
     for (int kt = 0; kt < nk; ++kt) {
-        __syncthreads();
-        store_tiles();
-        __syncthreads();
-        if (kt + 1 < nk) load_tiles((kt + 1) * BK);
+        const int buf = kt & 1;
+        if (kt + 1 < nk) load_tiles((kt + 1) * BK);      // global loads in flight while this tile is multiplied
 #pragma unroll
         for (int k = 0; k < BK; ++k) {
-            float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
-            float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
-            float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-            float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-            float bb[4] = {b.x, b.y, b.z, b.w};
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8 + 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+            const float2 ap[4] = {make_float2(a0.x, a0.y), make_float2(a0.z, a0.w), make_float2(a1.x, a1.y),
+                                  make_float2(a1.z, a1.w)};
+            const float2 bd[4] = {make_float2(b.x, b.x), make_float2(b.y, b.y), make_float2(b.z, b.z),
+                                  make_float2(b.w, b.w)};
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+                for (int j = 0; j < 4; ++j) acc2[i][j] = __ffma2_rn(ap[i], bd[j], acc2[i][j]);
         }
+        if (kt + 1 < nk) store_tiles(buf ^ 1);           // the other buffer was last read before the previous barrier
+        __syncthreads();
     }
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            acc[2 * i][j] = acc2[i][j].x;
+            acc[2 * i + 1][j] = acc2[i][j].y;
+        }
 
     // epilogue
     const int n = n0 + tx * 4;
@@ -181,8 +203,14 @@ extern "C" int spk_dense(const float* A, int64_t M, int K, int64_t lda, const fl
     GemmArgs g;
     g.A = A; g.a_pre = a_pre; g.B = B; g.bias = bias; g.addend = addend; g.Y = Y; g.y_pre = y_pre;
     g.M = M; g.lda = lda; g.ld_add = ld_add; g.ldy = ldy; g.K = K; g.N = N; g.a_act = a_act; g.act = act;
-    dim3 grid((unsigned)spk_cdiv(M, BM), (unsigned)spk_cdiv(N, BN));
-    k_dense<<<grid, NT, 0, spk_st(stream)>>>(g);
+    const int64_t ctas128 = spk_cdiv(M, 128) * spk_cdiv(N, BN);
+    if (ctas128 >= 3 * (int64_t)spk_num_sms()) {
+        dim3 grid((unsigned)spk_cdiv(M, 128), (unsigned)spk_cdiv(N, BN));
+        k_dense<128><<<grid, 256, 0, spk_st(stream)>>>(g);
+    } else {
+        dim3 grid((unsigned)spk_cdiv(M, 64), (unsigned)spk_cdiv(N, BN));
+        k_dense<64><<<grid, 128, 0, spk_st(stream)>>>(g);
+    }
     SPK_LAUNCH_CHECK();
     return SPK_OK;
 }

@@ -12,11 +12,16 @@
 
 namespace {
 
-constexpr int CH = 32;  // edges staged per chunk
+constexpr int CH = 48;   // edges staged per chunk (multiple of the prefetch ring depths 3 and 4)
+constexpr int PFD = 4;   // forward gather ring depth: PFD-1 edges in flight per thread
+constexpr int PBD = 3;   // reverse gather ring depth
 
+// Filter weights of one channel as k-PAIRS (w[2m], w[2m+1]): with the radial basis read from shared memory as natural
+// (phi[2m], phi[2m+1]) pairs, one packed FFMA2 (fma.rn.f32x2 -- Blackwell's full-rate fp32 path; scalar FFMA issues at
+// half rate) advances an even-k and an odd-k partial sum at once; the two partials are added at the end.
 template <int NRB>
 struct FilterRegs {
-    float a[NRB], b[NRB], c[NRB];
+    float2 a[NRB / 2], b[NRB / 2], c[NRB / 2];
     float ba, bb, bc;
 };
 
@@ -24,11 +29,13 @@ template <int NRB>
 __device__ __forceinline__ void load_filter(FilterRegs<NRB>& w, const float* __restrict__ wf,
                                             const float* __restrict__ bf, int F, int n_rbf, int c) {
 #pragma unroll
-    for (int k = 0; k < NRB; ++k) {
-        bool ok = k < n_rbf;
-        w.a[k] = ok ? wf[(int64_t)c * n_rbf + k] : 0.f;
-        w.b[k] = ok ? wf[(int64_t)(F + c) * n_rbf + k] : 0.f;
-        w.c[k] = ok ? wf[(int64_t)(2 * F + c) * n_rbf + k] : 0.f;
+    for (int m = 0; m < NRB / 2; ++m) {
+        const int k0 = 2 * m, k1 = 2 * m + 1;
+        const bool ok0 = k0 < n_rbf, ok1 = k1 < n_rbf;
+        w.a[m] = make_float2(ok0 ? wf[(int64_t)c * n_rbf + k0] : 0.f, ok1 ? wf[(int64_t)c * n_rbf + k1] : 0.f);
+        w.b[m] = make_float2(ok0 ? wf[(int64_t)(F + c) * n_rbf + k0] : 0.f, ok1 ? wf[(int64_t)(F + c) * n_rbf + k1] : 0.f);
+        w.c[m] = make_float2(ok0 ? wf[(int64_t)(2 * F + c) * n_rbf + k0] : 0.f,
+                             ok1 ? wf[(int64_t)(2 * F + c) * n_rbf + k1] : 0.f);
     }
     w.ba = bf[c];
     w.bb = bf[F + c];
@@ -57,7 +64,6 @@ __global__ void __launch_bounds__(NW * 32) k_painn_edge_fwd(
     constexpr int NTHR = NW * 32;
     __shared__ __align__(16) float s_phi[CH * NRB];
     __shared__ __align__(16) float s_geo[CH * SPK_GEO_STRIDE];
-    __shared__ int s_j[CH];
 
     const int c = threadIdx.x;
     const int nb = gridDim.x, b = blockIdx.x;
@@ -90,68 +96,80 @@ __global__ void __launch_bounds__(NW * 32) k_painn_edge_fwd(
         dq = dm0 = dm1 = dm2 = 0.f;
     };
 
+    // Software pipeline over edges: the sender rows of edge s+PFD-1 are requested before edge s is processed, so PFD-1
+    // gathers (L2 latency ~600 cycles) are always in flight per thread; the ring lives in registers (static indices).
+    struct Gather { float xa, xb, xc, m0, m1, m2; };
+    Gather ring[PFD];
+    auto issue = [&](Gather& g, int s) {
+        const int j = __ldg(slot_j + s);
+        const float* __restrict__ xj = x + (size_t)j * (3 * F) + c;
+        g.xa = xj[0];
+        g.xb = xj[F];
+        if (HAS_MU) {
+            g.xc = xj[2 * F];
+            const float* __restrict__ mj = mu + (size_t)j * (3 * F) + c;
+            g.m0 = mj[0];
+            g.m1 = mj[F];
+            g.m2 = mj[2 * F];
+        }
+    };
+#pragma unroll
+    for (int d = 0; d < PFD - 1; ++d)
+        if (s_begin + d < s_end) issue(ring[d], s_begin + d);
+
     for (int cs = s_begin; cs < s_end; cs += CH) {
         const int n = min(CH, s_end - cs);
         __syncthreads();
         stage_rows_contig<NRB, NTHR>(s_phi, phi + (int64_t)cs * KP, n, KP);
         for (int t = threadIdx.x; t < n * 2; t += NTHR)
             reinterpret_cast<float4*>(s_geo)[t] = reinterpret_cast<const float4*>(geo + (int64_t)cs * SPK_GEO_STRIDE)[t];
-        for (int t = threadIdx.x; t < n; t += NTHR) s_j[t] = slot_j[cs + t];
         __syncthreads();
 
-#pragma unroll 2
-        for (int t = 0; t < n; ++t) {
-            const int s = cs + t;
-            if (s >= next_boundary) {
-                do {
-                    flush(i);
-                    ++i;
-                    next_boundary = rowptr[i + 1];
-                } while (s >= next_boundary);
-            }
-            const int j = s_j[t];
-            const float* __restrict__ xj = x + (int64_t)j * 3 * F + c;
-            const float xa = xj[0], xb = xj[F];
-            float xc = 0.f, m0 = 0.f, m1 = 0.f, m2 = 0.f;
-            if (HAS_MU) {
-                xc = xj[2 * F];
-                const float* __restrict__ mj = mu + (int64_t)j * 3 * F + c;
-                m0 = mj[0];
-                m1 = mj[F];
-                m2 = mj[2 * F];
-            }
-            const float4 g0 = *reinterpret_cast<const float4*>(s_geo + t * SPK_GEO_STRIDE);      // ux uy uz d
-            const float fc = s_geo[t * SPK_GEO_STRIDE + 4];
-            float pa = w.ba, pb = w.bb, pc = w.bc;
-            const float4* __restrict__ ph = reinterpret_cast<const float4*>(s_phi + t * NRB);
+        for (int t0 = 0; t0 < n; t0 += PFD) {
 #pragma unroll
-            for (int k4 = 0; k4 < NRB / 4; ++k4) {
-                const float4 p = ph[k4];
-                pa = fmaf(p.x, w.a[4 * k4 + 0], pa);
-                pa = fmaf(p.y, w.a[4 * k4 + 1], pa);
-                pa = fmaf(p.z, w.a[4 * k4 + 2], pa);
-                pa = fmaf(p.w, w.a[4 * k4 + 3], pa);
-                pb = fmaf(p.x, w.b[4 * k4 + 0], pb);
-                pb = fmaf(p.y, w.b[4 * k4 + 1], pb);
-                pb = fmaf(p.z, w.b[4 * k4 + 2], pb);
-                pb = fmaf(p.w, w.b[4 * k4 + 3], pb);
-                if (HAS_MU) {
-                    pc = fmaf(p.x, w.c[4 * k4 + 0], pc);
-                    pc = fmaf(p.y, w.c[4 * k4 + 1], pc);
-                    pc = fmaf(p.z, w.c[4 * k4 + 2], pc);
-                    pc = fmaf(p.w, w.c[4 * k4 + 3], pc);
+            for (int u = 0; u < PFD; ++u) {
+                const int t = t0 + u;
+                if (t < n) {
+                    const int s = cs + t;
+                    if (s + PFD - 1 < s_end) issue(ring[(u + PFD - 1) % PFD], s + PFD - 1);
+                    if (s >= next_boundary) {
+                        do {
+                            flush(i);
+                            ++i;
+                            next_boundary = rowptr[i + 1];
+                        } while (s >= next_boundary);
+                    }
+                    const Gather& g = ring[u];
+                    const float4 g0 = *reinterpret_cast<const float4*>(s_geo + t * SPK_GEO_STRIDE);      // ux uy uz d
+                    const float fc = s_geo[t * SPK_GEO_STRIDE + 4];
+                    float2 pa2 = make_float2(w.ba, 0.f), pb2 = make_float2(w.bb, 0.f), pc2 = make_float2(w.bc, 0.f);
+                    const float4* __restrict__ ph = reinterpret_cast<const float4*>(s_phi + t * NRB);
+#pragma unroll
+                    for (int k4 = 0; k4 < NRB / 4; ++k4) {
+                        const float4 p = ph[k4];
+                        const float2 p01 = make_float2(p.x, p.y), p23 = make_float2(p.z, p.w);
+                        pa2 = __ffma2_rn(p01, w.a[2 * k4], pa2);
+                        pb2 = __ffma2_rn(p01, w.b[2 * k4], pb2);
+                        pa2 = __ffma2_rn(p23, w.a[2 * k4 + 1], pa2);
+                        pb2 = __ffma2_rn(p23, w.b[2 * k4 + 1], pb2);
+                        if (HAS_MU) {
+                            pc2 = __ffma2_rn(p01, w.c[2 * k4], pc2);
+                            pc2 = __ffma2_rn(p23, w.c[2 * k4 + 1], pc2);
+                        }
+                    }
+                    const float pa = pa2.x + pa2.y, pb = pb2.x + pb2.y, pc = pc2.x + pc2.y;
+                    dq = fmaf(fc * pa, g.xa, dq);
+                    const float tb = fc * pb * g.xb;
+                    dm0 = fmaf(tb, g0.x, dm0);
+                    dm1 = fmaf(tb, g0.y, dm1);
+                    dm2 = fmaf(tb, g0.z, dm2);
+                    if (HAS_MU) {
+                        const float tc = fc * pc * g.xc;
+                        dm0 = fmaf(tc, g.m0, dm0);
+                        dm1 = fmaf(tc, g.m1, dm1);
+                        dm2 = fmaf(tc, g.m2, dm2);
+                    }
                 }
-            }
-            dq = fmaf(fc * pa, xa, dq);
-            const float tb = fc * pb * xb;
-            dm0 = fmaf(tb, g0.x, dm0);
-            dm1 = fmaf(tb, g0.y, dm1);
-            dm2 = fmaf(tb, g0.z, dm2);
-            if (HAS_MU) {
-                const float tc = fc * pc * xc;
-                dm0 = fmaf(tc, m0, dm0);
-                dm1 = fmaf(tc, m1, dm1);
-                dm2 = fmaf(tc, m2, dm2);
             }
         }
     }
@@ -174,7 +192,6 @@ __global__ void __launch_bounds__(NW * 32) k_painn_edge_bwd(
     __shared__ __align__(16) float s_phi[CH * NRB];
     __shared__ __align__(16) float s_dphi[CH * NRB];
     __shared__ __align__(16) float s_geo[CH * SPK_GEO_STRIDE];
-    __shared__ int s_i[CH];
     __shared__ int s_eid[CH];
     __shared__ float s_red[CH][NW][4];
 
@@ -222,6 +239,21 @@ __global__ void __launch_bounds__(NW * 32) k_painn_edge_bwd(
     };
     load_own(j);
 
+    // software pipeline: receiver-gradient rows of edge p+PBD-1 are requested before edge p is processed
+    struct Gather { float gq, g0, g1, g2; };
+    Gather ring[PBD];
+    auto issue = [&](Gather& g, int p) {
+        const int i = __ldg(pos_i + p);
+        g.gq = g_q[(size_t)i * F + c];
+        const float* __restrict__ gmi = g_mu + (size_t)i * (3 * F) + c;
+        g.g0 = gmi[0];
+        g.g1 = gmi[F];
+        g.g2 = gmi[2 * F];
+    };
+#pragma unroll
+    for (int d = 0; d < PBD - 1; ++d)
+        if (p_begin + d < p_end) issue(ring[d], p_begin + d);
+
     for (int cs = p_begin; cs < p_end; cs += CH) {
         const int n = min(CH, p_end - cs);
         __syncthreads();
@@ -242,15 +274,16 @@ __global__ void __launch_bounds__(NW * 32) k_painn_edge_bwd(
             int s = pos_slot[cs + r];
             reinterpret_cast<float4*>(s_geo)[t] = reinterpret_cast<const float4*>(geo + (int64_t)s * SPK_GEO_STRIDE)[t & 1];
         }
-        for (int t = threadIdx.x; t < n; t += NTHR) {
-            int s = pos_slot[cs + t];
-            s_i[t] = pos_i[cs + t];
-            s_eid[t] = slot_eid[s];
-        }
+        for (int t = threadIdx.x; t < n; t += NTHR) s_eid[t] = slot_eid[pos_slot[cs + t]];
         __syncthreads();
 
-        for (int t = 0; t < n; ++t) {
+        for (int t0 = 0; t0 < n; t0 += PBD) {
+#pragma unroll
+          for (int u = 0; u < PBD; ++u) {
+            const int t = t0 + u;
+            if (t >= n) continue;
             const int p = cs + t;
+            if (p + PBD - 1 < p_end) issue(ring[(u + PBD - 1) % PBD], p + PBD - 1);
             if (p >= next_boundary) {
                 do {
                     flush(j);
@@ -259,33 +292,36 @@ __global__ void __launch_bounds__(NW * 32) k_painn_edge_bwd(
                 } while (p >= next_boundary);
                 load_own(j);
             }
-            const int i = s_i[t];
-            const float gq = g_q[(int64_t)i * F + c];
-            const float* __restrict__ gmi = g_mu + (int64_t)i * 3 * F + c;
-            const float g0 = gmi[0], g1 = gmi[F], g2 = gmi[2 * F];
+            const float gq = ring[u].gq, g0 = ring[u].g0, g1 = ring[u].g1, g2 = ring[u].g2;
             const float4 ge = *reinterpret_cast<const float4*>(s_geo + t * SPK_GEO_STRIDE);   // ux uy uz d
             const float fc = s_geo[t * SPK_GEO_STRIDE + 4], dfc = s_geo[t * SPK_GEO_STRIDE + 5];
-            float pa = w.ba, pb = w.bb, pc = w.bc, da = 0.f, db = 0.f, dc = 0.f;
+            float2 pa2 = make_float2(w.ba, 0.f), pb2 = make_float2(w.bb, 0.f), pc2 = make_float2(w.bc, 0.f);
+            float2 da2 = make_float2(0.f, 0.f), db2 = da2, dc2 = da2;
             const float4* __restrict__ ph = reinterpret_cast<const float4*>(s_phi + t * NRB);
             const float4* __restrict__ dh = reinterpret_cast<const float4*>(s_dphi + t * NRB);
 #pragma unroll
             for (int k4 = 0; k4 < NRB / 4; ++k4) {
                 const float4 p4 = ph[k4];
                 const float4 d4 = dh[k4];
-                const float pv[4] = {p4.x, p4.y, p4.z, p4.w};
-                const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    pa = fmaf(pv[u], w.a[4 * k4 + u], pa);
-                    da = fmaf(dv[u], w.a[4 * k4 + u], da);
-                    pb = fmaf(pv[u], w.b[4 * k4 + u], pb);
-                    db = fmaf(dv[u], w.b[4 * k4 + u], db);
-                    if (HAS_MU) {
-                        pc = fmaf(pv[u], w.c[4 * k4 + u], pc);
-                        dc = fmaf(dv[u], w.c[4 * k4 + u], dc);
-                    }
+                const float2 p01 = make_float2(p4.x, p4.y), p23 = make_float2(p4.z, p4.w);
+                const float2 d01 = make_float2(d4.x, d4.y), d23 = make_float2(d4.z, d4.w);
+                pa2 = __ffma2_rn(p01, w.a[2 * k4], pa2);
+                da2 = __ffma2_rn(d01, w.a[2 * k4], da2);
+                pb2 = __ffma2_rn(p01, w.b[2 * k4], pb2);
+                db2 = __ffma2_rn(d01, w.b[2 * k4], db2);
+                pa2 = __ffma2_rn(p23, w.a[2 * k4 + 1], pa2);
+                da2 = __ffma2_rn(d23, w.a[2 * k4 + 1], da2);
+                pb2 = __ffma2_rn(p23, w.b[2 * k4 + 1], pb2);
+                db2 = __ffma2_rn(d23, w.b[2 * k4 + 1], db2);
+                if (HAS_MU) {
+                    pc2 = __ffma2_rn(p01, w.c[2 * k4], pc2);
+                    dc2 = __ffma2_rn(d01, w.c[2 * k4], dc2);
+                    pc2 = __ffma2_rn(p23, w.c[2 * k4 + 1], pc2);
+                    dc2 = __ffma2_rn(d23, w.c[2 * k4 + 1], dc2);
                 }
             }
+            const float pa = pa2.x + pa2.y, pb = pb2.x + pb2.y, pc = pc2.x + pc2.y;
+            const float da = da2.x + da2.y, db = db2.x + db2.y, dc = dc2.x + dc2.y;
             const float Wa = fc * pa, Wb = fc * pb;
             const float dWa = fmaf(dfc, pa, fc * da), dWb = fmaf(dfc, pb, fc * db);
             const float gu = g0 * ge.x + g1 * ge.y + g2 * ge.z;   // sum_d g_mu[i,d] u_d
@@ -315,6 +351,7 @@ __global__ void __launch_bounds__(NW * 32) k_painn_edge_bwd(
                 s_red[t][warp][2] = pu1;
                 s_red[t][warp][3] = pu2;
             }
+          }
         }
         __syncthreads();
         if (threadIdx.x < n) {
