@@ -55,7 +55,7 @@ __device__ __forceinline__ void stage_rows_contig(float* __restrict__ dst, const
 }
 
 template <int NW, int NRB, bool HAS_MU>
-__global__ void __launch_bounds__(NW * 32) k_painn_edge_fwd(
+__global__ void __launch_bounds__(NW * 32, 512 / (NW * 32)) k_painn_edge_fwd(
     const float* __restrict__ x, const float* __restrict__ mu, const float* __restrict__ q,
     const float* __restrict__ phi, const float* __restrict__ geo, const int* __restrict__ rowptr,
     const int* __restrict__ slot_j, const float* __restrict__ wf, const float* __restrict__ bf, int n_atoms,
@@ -76,32 +76,40 @@ __global__ void __launch_bounds__(NW * 32) k_painn_edge_fwd(
     const int KP = spk_kp(n_rbf);
 
     const int s_begin = rowptr[row_lo], s_end = rowptr[row_hi];
+    // Every dependent global load is issued at least one edge ahead of its use (the warp issues in order, so a load
+    // consumed right away would stall everything queued behind it): row boundaries two rows ahead, the receiver's own
+    // q/mu row at row entry, sender indices PFD edges ahead, sender rows PFD-1 edges ahead.
     int i = row_lo;
     int next_boundary = rowptr[i + 1];
+    int boundary2 = rowptr[min(i + 2, n_atoms)];
     float dq = 0.f, dm0 = 0.f, dm1 = 0.f, dm2 = 0.f;
-
-    auto flush = [&](int row) {
-        const int64_t o = (int64_t)row * F + c;
-        q_out[o] = q[o] + dq;
-        const int64_t om = (int64_t)row * 3 * F + c;
+    float rq, rm0 = 0.f, rm1 = 0.f, rm2 = 0.f;
+    auto load_res = [&](int row) {
+        rq = q[(size_t)row * F + c];
         if (HAS_MU) {
-            mu_out[om] = mu[om] + dm0;
-            mu_out[om + F] = mu[om + F] + dm1;
-            mu_out[om + 2 * F] = mu[om + 2 * F] + dm2;
-        } else {
-            mu_out[om] = dm0;
-            mu_out[om + F] = dm1;
-            mu_out[om + 2 * F] = dm2;
+            const float* __restrict__ mr = mu + (size_t)row * (3 * F) + c;
+            rm0 = mr[0];
+            rm1 = mr[F];
+            rm2 = mr[2 * F];
         }
+    };
+    load_res(i);
+    auto flush_advance = [&]() {
+        q_out[(size_t)i * F + c] = rq + dq;
+        float* __restrict__ mo = mu_out + (size_t)i * (3 * F) + c;
+        mo[0] = rm0 + dm0;
+        mo[F] = rm1 + dm1;
+        mo[2 * F] = rm2 + dm2;
         dq = dm0 = dm1 = dm2 = 0.f;
+        ++i;
+        next_boundary = boundary2;
+        boundary2 = rowptr[min(i + 2, n_atoms)];
+        if (i < row_hi) load_res(i);
     };
 
-    // Software pipeline over edges: the sender rows of edge s+PFD-1 are requested before edge s is processed, so PFD-1
-    // gathers (L2 latency ~600 cycles) are always in flight per thread; the ring lives in registers (static indices).
     struct Gather { float xa, xb, xc, m0, m1, m2; };
     Gather ring[PFD];
-    auto issue = [&](Gather& g, int s) {
-        const int j = __ldg(slot_j + s);
+    auto issue = [&](Gather& g, int j) {
         const float* __restrict__ xj = x + (size_t)j * (3 * F) + c;
         g.xa = xj[0];
         g.xb = xj[F];
@@ -115,7 +123,8 @@ __global__ void __launch_bounds__(NW * 32) k_painn_edge_fwd(
     };
 #pragma unroll
     for (int d = 0; d < PFD - 1; ++d)
-        if (s_begin + d < s_end) issue(ring[d], s_begin + d);
+        if (s_begin + d < s_end) issue(ring[d], __ldg(slot_j + s_begin + d));
+    int j_next = (s_begin + PFD - 1 < s_end) ? __ldg(slot_j + s_begin + PFD - 1) : 0;
 
     for (int cs = s_begin; cs < s_end; cs += CH) {
         const int n = min(CH, s_end - cs);
@@ -131,14 +140,9 @@ __global__ void __launch_bounds__(NW * 32) k_painn_edge_fwd(
                 const int t = t0 + u;
                 if (t < n) {
                     const int s = cs + t;
-                    if (s + PFD - 1 < s_end) issue(ring[(u + PFD - 1) % PFD], s + PFD - 1);
-                    if (s >= next_boundary) {
-                        do {
-                            flush(i);
-                            ++i;
-                            next_boundary = rowptr[i + 1];
-                        } while (s >= next_boundary);
-                    }
+                    if (s + PFD - 1 < s_end) issue(ring[(u + PFD - 1) % PFD], j_next);
+                    if (s + PFD < s_end) j_next = __ldg(slot_j + s + PFD);
+                    while (s >= next_boundary) flush_advance();
                     const Gather& g = ring[u];
                     const float4 g0 = *reinterpret_cast<const float4*>(s_geo + t * SPK_GEO_STRIDE);      // ux uy uz d
                     const float fc = s_geo[t * SPK_GEO_STRIDE + 4];
@@ -173,14 +177,14 @@ __global__ void __launch_bounds__(NW * 32) k_painn_edge_fwd(
             }
         }
     }
-    for (; i < row_hi; ++i) flush(i);
+    while (i < row_hi) flush_advance();
 }
 
 // ------------------------------------------------------------------------------------------------------------------
 // reverse pass, grouped by sender
 // ------------------------------------------------------------------------------------------------------------------
 template <int NW, int NRB, bool HAS_MU>
-__global__ void __launch_bounds__(NW * 32) k_painn_edge_bwd(
+__global__ void __launch_bounds__(NW * 32, 512 / (NW * 32)) k_painn_edge_bwd(
     const float* __restrict__ x, const float* __restrict__ mu, const float* __restrict__ g_q,
     const float* __restrict__ g_mu, const float* __restrict__ phi, const float* __restrict__ dphi,
     const float* __restrict__ geo, const int* __restrict__ sptr, const int* __restrict__ pos_slot,
@@ -210,40 +214,52 @@ __global__ void __launch_bounds__(NW * 32) k_painn_edge_bwd(
     const int p_begin = sptr[j_lo], p_end = sptr[j_hi];
     int j = j_lo;
     int next_boundary = sptr[j + 1];
-    float xa, xb, xc = 0.f, m0 = 0.f, m1 = 0.f, m2 = 0.f;
-    float gxa = 0.f, gxb = 0.f, gxc = 0.f, gm0 = 0.f, gm1 = 0.f, gm2 = 0.f;
-
-    auto load_own = [&](int row) {
-        const float* __restrict__ xr = x + (int64_t)row * 3 * F + c;
-        xa = xr[0];
-        xb = xr[F];
+    int boundary2 = sptr[min(j + 2, n_atoms)];
+    // the sender's own rows (x_j, mu_j and the residual g_mu_j) are requested at row entry, i.e. before the ~100
+    // filter instructions of the row's first edge, and consumed after them
+    struct Own { float xa, xb, xc, m0, m1, m2, r0, r1, r2; };
+    Own own;
+    auto load_own = [&](Own& o, int row) {
+        const float* __restrict__ xr = x + (size_t)row * (3 * F) + c;
+        o.xa = xr[0];
+        o.xb = xr[F];
+        o.xc = 0.f; o.m0 = 0.f; o.m1 = 0.f; o.m2 = 0.f; o.r0 = 0.f; o.r1 = 0.f; o.r2 = 0.f;
         if (HAS_MU) {
-            xc = xr[2 * F];
-            const float* __restrict__ mr = mu + (int64_t)row * 3 * F + c;
-            m0 = mr[0];
-            m1 = mr[F];
-            m2 = mr[2 * F];
+            o.xc = xr[2 * F];
+            const float* __restrict__ mr = mu + (size_t)row * (3 * F) + c;
+            o.m0 = mr[0];
+            o.m1 = mr[F];
+            o.m2 = mr[2 * F];
+            const float* __restrict__ gr = g_mu + (size_t)row * (3 * F) + c;
+            o.r0 = gr[0];
+            o.r1 = gr[F];
+            o.r2 = gr[2 * F];
         }
     };
-    auto flush = [&](int row) {
-        const int64_t o = (int64_t)row * 3 * F + c;
-        g_x[o] = gxa;
-        g_x[o + F] = gxb;
-        g_x[o + 2 * F] = gxc;
+    load_own(own, j);
+    float gxa = 0.f, gxb = 0.f, gxc = 0.f, gm0 = 0.f, gm1 = 0.f, gm2 = 0.f;
+    auto flush_advance = [&]() {
+        float* __restrict__ gx = g_x + (size_t)j * (3 * F) + c;
+        gx[0] = gxa;
+        gx[F] = gxb;
+        gx[2 * F] = gxc;
         if (HAS_MU) {
-            g_mu_in[o] = g_mu[o] + gm0;
-            g_mu_in[o + F] = g_mu[o + F] + gm1;
-            g_mu_in[o + 2 * F] = g_mu[o + 2 * F] + gm2;
+            float* __restrict__ gm = g_mu_in + (size_t)j * (3 * F) + c;
+            gm[0] = own.r0 + gm0;
+            gm[F] = own.r1 + gm1;
+            gm[2 * F] = own.r2 + gm2;
         }
         gxa = gxb = gxc = gm0 = gm1 = gm2 = 0.f;
+        ++j;
+        next_boundary = boundary2;
+        boundary2 = sptr[min(j + 2, n_atoms)];
+        if (j < j_hi) load_own(own, j);
     };
-    load_own(j);
 
     // software pipeline: receiver-gradient rows of edge p+PBD-1 are requested before edge p is processed
     struct Gather { float gq, g0, g1, g2; };
     Gather ring[PBD];
-    auto issue = [&](Gather& g, int p) {
-        const int i = __ldg(pos_i + p);
+    auto issue = [&](Gather& g, int i) {
         g.gq = g_q[(size_t)i * F + c];
         const float* __restrict__ gmi = g_mu + (size_t)i * (3 * F) + c;
         g.g0 = gmi[0];
@@ -252,7 +268,8 @@ __global__ void __launch_bounds__(NW * 32) k_painn_edge_bwd(
     };
 #pragma unroll
     for (int d = 0; d < PBD - 1; ++d)
-        if (p_begin + d < p_end) issue(ring[d], p_begin + d);
+        if (p_begin + d < p_end) issue(ring[d], __ldg(pos_i + p_begin + d));
+    int i_next = (p_begin + PBD - 1 < p_end) ? __ldg(pos_i + p_begin + PBD - 1) : 0;
 
     for (int cs = p_begin; cs < p_end; cs += CH) {
         const int n = min(CH, p_end - cs);
@@ -283,15 +300,10 @@ __global__ void __launch_bounds__(NW * 32) k_painn_edge_bwd(
             const int t = t0 + u;
             if (t >= n) continue;
             const int p = cs + t;
-            if (p + PBD - 1 < p_end) issue(ring[(u + PBD - 1) % PBD], p + PBD - 1);
-            if (p >= next_boundary) {
-                do {
-                    flush(j);
-                    ++j;
-                    next_boundary = sptr[j + 1];
-                } while (p >= next_boundary);
-                load_own(j);
-            }
+            if (p + PBD - 1 < p_end) issue(ring[(u + PBD - 1) % PBD], i_next);
+            if (p + PBD < p_end) i_next = __ldg(pos_i + p + PBD);
+            while (p >= next_boundary) flush_advance();
+            const float xa = own.xa, xb = own.xb, xc = own.xc, m0 = own.m0, m1 = own.m1, m2 = own.m2;
             const float gq = ring[u].gq, g0 = ring[u].g0, g1 = ring[u].g1, g2 = ring[u].g2;
             const float4 ge = *reinterpret_cast<const float4*>(s_geo + t * SPK_GEO_STRIDE);   // ux uy uz d
             const float fc = s_geo[t * SPK_GEO_STRIDE + 4], dfc = s_geo[t * SPK_GEO_STRIDE + 5];
@@ -381,9 +393,7 @@ __global__ void __launch_bounds__(NW * 32) k_painn_edge_bwd(
             out[2] = r2;
         }
     }
-    for (; j < j_hi; ++j) {
-        flush(j);
-    }
+    while (j < j_hi) flush_advance();
 }
 
 // ------------------------------------------------------------------------------------------------------------------
