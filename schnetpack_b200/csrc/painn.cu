@@ -8,39 +8,15 @@
 // back as warp-broadcast LDS.128, sender rows x[j], mu[j] are gathered with fully coalesced 128 B requests, and the
 // reduction over a receiver's edges is a private register accumulation (CSR order) -- no atomics, no shuffles.
 // CTAs take edge-balanced contiguous row ranges (binary search in rowptr).
-#include "common.cuh"
+#include <cstdlib>
+
+#include "painn_common.cuh"
 
 namespace {
 
 constexpr int CH = 48;   // edges staged per chunk (multiple of the prefetch ring depths 3 and 4)
 constexpr int PFD = 4;   // forward gather ring depth: PFD-1 edges in flight per thread
 constexpr int PBD = 3;   // reverse gather ring depth
-
-// Filter weights of one channel as k-PAIRS (w[2m], w[2m+1]): with the radial basis read from shared memory as natural
-// (phi[2m], phi[2m+1]) pairs, one packed FFMA2 (fma.rn.f32x2 -- Blackwell's full-rate fp32 path; scalar FFMA issues at
-// half rate) advances an even-k and an odd-k partial sum at once; the two partials are added at the end.
-template <int NRB>
-struct FilterRegs {
-    float2 a[NRB / 2], b[NRB / 2], c[NRB / 2];
-    float ba, bb, bc;
-};
-
-template <int NRB>
-__device__ __forceinline__ void load_filter(FilterRegs<NRB>& w, const float* __restrict__ wf,
-                                            const float* __restrict__ bf, int F, int n_rbf, int c) {
-#pragma unroll
-    for (int m = 0; m < NRB / 2; ++m) {
-        const int k0 = 2 * m, k1 = 2 * m + 1;
-        const bool ok0 = k0 < n_rbf, ok1 = k1 < n_rbf;
-        w.a[m] = make_float2(ok0 ? wf[(int64_t)c * n_rbf + k0] : 0.f, ok1 ? wf[(int64_t)c * n_rbf + k1] : 0.f);
-        w.b[m] = make_float2(ok0 ? wf[(int64_t)(F + c) * n_rbf + k0] : 0.f, ok1 ? wf[(int64_t)(F + c) * n_rbf + k1] : 0.f);
-        w.c[m] = make_float2(ok0 ? wf[(int64_t)(2 * F + c) * n_rbf + k0] : 0.f,
-                             ok1 ? wf[(int64_t)(2 * F + c) * n_rbf + k1] : 0.f);
-    }
-    w.ba = bf[c];
-    w.bb = bf[F + c];
-    w.bc = bf[2 * F + c];
-}
 
 // cooperative staging of contiguous per-slot records [n, KP] -> smem [n, NRB] (zero padded)
 template <int NRB, int NTHR>
@@ -529,7 +505,28 @@ int launch_edge_bwd(const float* x, const float* mu, const float* g_q, const flo
     return 0;
 }
 
+// one-time choice of the edge-kernel variant: "tma" (default; painn_tma.cu) or "ldg" (this file) via SPK_B200_EDGE
+bool use_tma_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SPK_B200_EDGE");
+        v = (e && e[0] == 'l') ? 0 : 1;
+    }
+    return v == 1;
+}
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 }  // namespace
+
+template <int NW, int NRB>
+int spk_launch_edge_fwd_tma(const float* x, const float* mu, const float* q, const float* phi, const float* geo,
+                            const int* rowptr, const int* slot_j, const float* wf, const float* bf, int n_atoms,
+                            int n_edges, int n_rbf, float* q_out, float* mu_out, cudaStream_t st);
+template <int NW, int NRB>
+int spk_launch_edge_bwd_tma(const float* x, const float* mu, const float* g_q, const float* g_mu, const float* phi,
+                            const float* dphi, const float* geo, const int* sptr, const int* pos_slot, const int* pos_i,
+                            const int* slot_eid, const float* wf, const float* bf, int n_atoms, int n_edges, int n_rbf,
+                            float* g_x, float* g_mu_in, float* g_rij, int accumulate, cudaStream_t st);
 
 #define DISPATCH_F_NRB(CALL)                                                   \
     do {                                                                       \
@@ -556,8 +553,13 @@ extern "C" int spk_painn_edge_fwd(const float* x, const float* mu, const float* 
     if (n_edges > 0 && (!phi || !geo || !slot_j)) return SPK_ERR_ARG;
     if (mu && mu == mu_out) return SPK_ERR_ARG;
     cudaStream_t st = spk_st(stream);
-#define CALL_FWD(NW, NRB) \
-    launch_edge_fwd<NW, NRB>(x, mu, q, phi, geo, rowptr, slot_j, wf, bf, (int)n_atoms, (int)n_edges, n_rbf, q_out, mu_out, st)
+    // the TMA variant needs 16 B-aligned rows (true for every torch allocation; F % 32 == 0 keeps row strides aligned)
+    const bool tma = use_tma_variant() && n_edges > 0 && aligned16(x) && aligned16(mu) && aligned16(phi) && aligned16(geo);
+#define CALL_FWD(NW, NRB)                                                                                              \
+    (tma ? spk_launch_edge_fwd_tma<NW, NRB>(x, mu, q, phi, geo, rowptr, slot_j, wf, bf, (int)n_atoms, (int)n_edges,    \
+                                            n_rbf, q_out, mu_out, st)                                                  \
+         : launch_edge_fwd<NW, NRB>(x, mu, q, phi, geo, rowptr, slot_j, wf, bf, (int)n_atoms, (int)n_edges, n_rbf,     \
+                                    q_out, mu_out, st))
     DISPATCH_F_NRB(CALL_FWD);
 #undef CALL_FWD
     SPK_LAUNCH_CHECK();
@@ -576,9 +578,13 @@ extern "C" int spk_painn_edge_bwd(const float* x, const float* mu, const float* 
     if (mu && !g_mu_in) return SPK_ERR_ARG;
     if (n_edges > 0 && (!phi || !dphi || !geo || !pos_slot || !pos_i || !slot_eid || !g_rij)) return SPK_ERR_ARG;
     cudaStream_t st = spk_st(stream);
-#define CALL_BWD(NW, NRB)                                                                                            \
-    launch_edge_bwd<NW, NRB>(x, mu, g_q, g_mu, phi, dphi, geo, sptr, pos_slot, pos_i, slot_eid, wf, bf, (int)n_atoms, \
-                             (int)n_edges, n_rbf, g_x, g_mu_in, g_rij, accumulate, st)
+    const bool tma = use_tma_variant() && n_edges > 0 && aligned16(g_q) && aligned16(g_mu) && aligned16(phi) &&
+                     aligned16(dphi) && aligned16(geo);
+#define CALL_BWD(NW, NRB)                                                                                               \
+    (tma ? spk_launch_edge_bwd_tma<NW, NRB>(x, mu, g_q, g_mu, phi, dphi, geo, sptr, pos_slot, pos_i, slot_eid, wf, bf,  \
+                                            (int)n_atoms, (int)n_edges, n_rbf, g_x, g_mu_in, g_rij, accumulate, st)     \
+         : launch_edge_bwd<NW, NRB>(x, mu, g_q, g_mu, phi, dphi, geo, sptr, pos_slot, pos_i, slot_eid, wf, bf,          \
+                                    (int)n_atoms, (int)n_edges, n_rbf, g_x, g_mu_in, g_rij, accumulate, st))
     DISPATCH_F_NRB(CALL_BWD);
 #undef CALL_BWD
     SPK_LAUNCH_CHECK();
