@@ -69,6 +69,20 @@ __device__ __forceinline__ float tf32_rn(float x) {
     return __uint_as_float(r);
 }
 
+// 32 consecutive accumulator columns of this thread's TMEM lane -> registers
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 struct TcArgs {
     const float* A;
     const float* a_pre;
@@ -102,7 +116,7 @@ __global__ void __launch_bounds__(128, 1) k_dense_tc(TcArgs g) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(TN));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(2 * TN));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -120,6 +134,28 @@ __global__ void __launch_bounds__(128, 1) k_dense_tc(TcArgs g) {
                        (!g.a_pre || (reinterpret_cast<uintptr_t>(g.a_pre) & 15) == 0);
     const bool w_vec = ((g.K & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.Wh) & 15) == 0) &&
                        ((reinterpret_cast<uintptr_t>(g.Wl) & 15) == 0);
+
+    // fp32 running sum of the per-k-tile main accumulators.  The tensor core adds into its TMEM accumulator with
+    // truncation (biased toward zero); keeping every hi*hi partial sum to ONE k-tile (3 truncating adds) and summing the
+    // tiles here with IEEE round-to-nearest keeps the layer at fp32-grade error.
+    float accr[TN];
+#pragma unroll
+    for (int i = 0; i < TN; ++i) accr[i] = 0.f;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    auto drain = [&](int tile) {
+        mbar_wait(&bar_mma[tile & 1], (tile >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int c0 = 0; c0 < TN; c0 += 32) {
+            if (c0 < BN) {
+                uint32_t r[32];
+                tmem_ld32(lane_addr + (uint32_t)c0, r);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) accr[c0 + j] += __uint_as_float(r[j]);
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    };
 
     for (int kt = 0; kt < nk; ++kt) {
         const int s = kt & 1;
@@ -191,6 +227,10 @@ __global__ void __launch_bounds__(128, 1) k_dense_tc(TcArgs g) {
         // make the generic-proxy stores visible to the tensor core (async proxy), then hand over to the issuer
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
+        if (kt >= 1) {               // main accumulator of the previous k-tile -> registers, before it is overwritten
+            drain(kt - 1);
+            __syncthreads();
+        }
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t sa = smem_u32(st);
@@ -201,35 +241,25 @@ __global__ void __launch_bounds__(128, 1) k_dense_tc(TcArgs g) {
                 const uint64_t al = make_desc(sa + OPER_BYTES + 2 * ks * PLANE);
                 const uint64_t bh = make_desc(sa + 2 * OPER_BYTES + 2 * ks * PLANE);
                 const uint64_t bl = make_desc(sa + 3 * OPER_BYTES + 2 * ks * PLANE);
-                umma_tf32(tmem_base, al, bh, idesc, (kt | ks) ? 1u : 0u);
-                umma_tf32(tmem_base, ah, bl, idesc, 1u);
-                umma_tf32(tmem_base, ah, bh, idesc, 1u);
+                umma_tf32(tmem_base + TN, al, bh, idesc, (kt | ks) ? 1u : 0u);   // small terms: own accumulator
+                umma_tf32(tmem_base + TN, ah, bl, idesc, 1u);
+                umma_tf32(tmem_base, ah, bh, idesc, ks ? 1u : 0u);               // main term: fresh every k-tile
             }
             // arrives on the stage barrier when every MMA issued so far has completed (implies before_thread_sync)
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                 smem_u32(&bar_mma[s])) : "memory");
         }
     }
-    // ---- wait for the last commit (covers all MMAs), then epilogue ------------------------------------------------
-    {
-        const int last = nk - 1;
-        mbar_wait(&bar_mma[last & 1], (last >> 1) & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    }
+    // ---- last k-tile, then the correction accumulator (lo terms of all k-tiles), then the epilogue -----------------
+    drain(nk - 1);
     const int64_t m = m0 + tid;                     // TMEM lane == output row
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+#pragma unroll
+    for (int c0 = 0; c0 < TN; c0 += 32) {
+        if (c0 >= BN) break;
         uint32_t r[32];
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-              "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-            : "r"(lane_addr + (uint32_t)c0));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        tmem_ld32(lane_addr + (uint32_t)(TN + c0), r);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(accr[c0 + j] + __uint_as_float(r[j]));
         if (m < g.M) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -268,7 +298,7 @@ __global__ void __launch_bounds__(128, 1) k_dense_tc(TcArgs g) {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TN));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * TN));
     }
 }
 
