@@ -1,34 +1,46 @@
-// Dense layer on the 5th-generation tensor cores (tcgen05, TMEM accumulator) with 3xTF32 error compensation:
+// Dense layer on the 5th-generation tensor cores (tcgen05, TMEM accumulators) with 3xTF32 error compensation:
 //
 //     Y = act( (A .* act'(a_pre)) * W^T + bias ) + addend            A [M,K] fp32, W [N,K] fp32 (K contiguous)
 //
 // The reference computes these layers with true-fp32 cuBLAS SGEMM (torch matmul precision "highest",
-// /root/reference/src/schnetpack/cli.py:95-97, nn/base.py:52-55); single-pass TF32 (10-bit mantissa) would miss the
-// 1e-5 parity bar by two orders of magnitude, so every operand is split  x = hi + lo  (hi = round-to-nearest TF32,
-// lo = x - hi, exact in fp32) and three tensor-core products  Ah*Bh + Al*Bh + Ah*Bl  are accumulated in fp32 in TMEM.
-// The dropped Al*Bl term and the TF32 rounding of lo are O(2^-22) relative.
+// /root/reference/src/schnetpack/cli.py:95-97, nn/base.py:52-55); single-pass TF32 would miss the 1e-5 parity bar by two
+// orders of magnitude.  Scheme (validated on B200):
+//   * every operand is split  x = hi + lo  (hi = round-to-nearest TF32, lo = x - hi exact in fp32); three tensor-core
+//     products Ah*Bh + Al*Bh + Ah*Bl are formed (Al*Bl is O(2^-24));
+//   * the tensor core adds into its TMEM accumulator with TRUNCATION, which biases long K-sums toward zero (measured: 8x
+//     worse end-to-end parity).  Therefore the main Ah*Bh product of each K-tile (16 floats = 2 MMA k-steps) goes into a
+//     FRESH accumulator that is drained into fp32 registers and summed there with IEEE round-to-nearest, while the small
+//     lo products accumulate over all of K in a separate TMEM accumulator (their truncation error is 2^-12 smaller).
 //
-// Structure (one 128-thread CTA per 128 x BN output tile, cta_group::1, UMMA M=128, N=BN<=128, K=8 per instruction):
-//   * all four warps stage the next K-tile (32 floats) of A and W: coalesced 128-bit global loads, optional backward
-//     prologue (x act'(a_pre)), hi/lo split in registers, st.shared into the canonical K-major no-swizzle core-matrix
-//     layout (8 rows x 16 B cores; LBO = plane stride between 16 B K-chunks, SBO = 128 B between 8-row groups);
-//   * fence.proxy.async + barrier, then ONE thread issues 12 tcgen05.mma.kind::tf32 per K-tile (4 k-steps x 3 products)
-//     and tcgen05.commit's them to the stage's mbarrier; two smem stages let the loads of tile t+1 overlap the MMAs of t;
-//   * epilogue: each warp reads its 32 TMEM lanes (= 32 output rows) with tcgen05.ld.32x32b.x32, applies
-//     bias / activation / addend, optionally saves the pre-activation, and stores 128-bit vectors.
+// Warp-specialised pipeline, one CTA (8 warps) per 128 x BN (<=128) output tile, cta_group::1, UMMA 128 x BN x 8:
+//   warps 4-6  producers: producer p owns K-tiles p, p+3, ... : coalesced 128-bit global loads of the A tile (optional backward
+//              prologue x act'(a_pre)) and of the pre-split weight tiles, hi/lo split in registers, st.shared into the
+//              canonical K-major no-swizzle core-matrix layout (8 rows x 16 B cores, LBO = plane stride between 16 B
+//              K-chunks, SBO = 128 B between 8-row groups), fence.proxy.async, arrive on full[stage];
+//   warp 7     MMA issuer (one lane): waits full[stage] and acc_empty[buf], issues 6 tcgen05.mma.kind::tf32, then
+//              tcgen05.commit -> empty[stage] and -> acc_full[buf];
+//   warps 0-3  drain + epilogue: tcgen05.ld.32x32b.x32 of the main accumulator buffer (thread = output row), fp32 add into
+//              128 register accumulators, arrive acc_empty[buf]; after the last K-tile add the correction accumulator,
+//              apply bias / activation / addend, store.
+// Six shared-memory stages (33 KB each) and two main TMEM buffers let loads, MMAs and drains of different K-tiles overlap.
 #include "common.cuh"
 
 namespace {
 
-constexpr int TM = 128;       // rows per CTA tile (UMMA M)
-constexpr int TN = 128;       // max columns per CTA tile (UMMA N)
-constexpr int TK = 32;        // floats per K-tile (4 UMMA k-steps of 8)
-constexpr int NSTAGE = 2;
-constexpr int GROUPS = TM / 8;                 // 8-row groups
+constexpr int TM = 128;                        // rows per CTA tile (UMMA M)
+constexpr int TN = 128;                        // max columns per CTA tile (UMMA N)
+constexpr int TK = 16;                         // floats per K-tile = 2 UMMA k-steps
+constexpr int NST = 6;                         // shared-memory stages
+constexpr int NPROD = 3;                       // producer warps (8 warps total keeps the 255-register budget)
+constexpr int GROUPS = TM / 8;                 // 8-row groups per operand tile
 constexpr int PLANE = GROUPS * 128 + 16;       // bytes between consecutive 16 B K-chunks (LBO), padded vs bank conflicts
-constexpr int OPER_BYTES = 8 * PLANE;          // one operand tile (8 K-chunks of 16 B per row)
-constexpr int STAGE_BYTES = 4 * OPER_BYTES;    // A_hi, A_lo, B_hi, B_lo
-constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 64;
+constexpr int OPER_BYTES = (TK / 4) * PLANE;   // one operand tile: TK/4 chunks of 16 B per row
+constexpr int STAGE_BYTES = 4 * OPER_BYTES;    // A_hi, A_lo, W_hi, W_lo
+constexpr int SMEM_BYTES = NST * STAGE_BYTES;
+constexpr int NTHREADS = (4 + NPROD + 1) * 32;    // warps 0-3 drain/epilogue, 4..4+NPROD-1 producers, last = MMA
+constexpr int W_PROD0 = 4;                     // first producer warp
+constexpr int W_MMA = 4 + NPROD;               // MMA issuer warp
+constexpr int TMEM_COLS = 512;                 // main[0] | main[1] | corr | (unused)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -46,6 +58,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "r"(smem_u32(bar)), "r"(parity)
             : "memory");
     } while (!done);
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    // arrives on `bar` when every tcgen05.mma issued so far by this thread has completed (implies before_thread_sync)
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
 }
 
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
@@ -99,9 +119,12 @@ struct TcArgs {
 // byte offset of (row r, 16 B chunk c) inside an operand tile
 __device__ __forceinline__ int tile_off(int r, int c) { return c * PLANE + (r >> 3) * 128 + (r & 7) * 16; }
 
-__global__ void __launch_bounds__(128, 1) k_dense_tc(TcArgs g) {
+__global__ void __launch_bounds__(NTHREADS, 1) k_dense_tc(TcArgs g) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint64_t bar_mma[NSTAGE];
+    __shared__ __align__(8) uint64_t full_bar[NST];
+    __shared__ __align__(8) uint64_t empty_bar[NST];
+    __shared__ __align__(8) uint64_t acc_full[2];
+    __shared__ __align__(8) uint64_t acc_empty[2];
     __shared__ uint32_t s_tmem;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -109,14 +132,23 @@ __global__ void __launch_bounds__(128, 1) k_dense_tc(TcArgs g) {
     const int n0 = blockIdx.y * TN;
     const int bn_real = min(TN, g.N - n0);            // valid columns of this tile
     const int BN = (bn_real + 15) & ~15;              // UMMA N (multiple of 16)
+    const int nk = (g.K + TK - 1) / TK;
 
     if (tid == 0) {
-        mbar_init(&bar_mma[0], 1);
-        mbar_init(&bar_mma[1], 1);
+#pragma unroll
+        for (int s = 0; s < NST; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(&acc_full[0], 1);
+        mbar_init(&acc_full[1], 1);
+        mbar_init(&acc_empty[0], 4);
+        mbar_init(&acc_empty[1], 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(2 * TN));
+    if (warp == W_MMA) {   // the MMA warp owns the TMEM allocation
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
+                     "n"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -124,181 +156,203 @@ __global__ void __launch_bounds__(128, 1) k_dense_tc(TcArgs g) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = s_tmem;
 
-    // instruction descriptor: D=F32 (1<<4), A=B=TF32 (2<<7, 2<<10), K-major both, N>>3 at [17,23), M>>4 at [24,29)
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-
-    const int nk = (g.K + TK - 1) / TK;
-    // coalesced staging map: lane -> (row sub-index = lane/8, 16 B chunk = lane%8); 8 passes cover 32 rows per warp
-    const int chunk = lane & 7, rsub = lane >> 3;
-    const bool a_vec = ((g.lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0) &&
-                       (!g.a_pre || (reinterpret_cast<uintptr_t>(g.a_pre) & 15) == 0);
-    const bool w_vec = ((g.K & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.Wh) & 15) == 0) &&
-                       ((reinterpret_cast<uintptr_t>(g.Wl) & 15) == 0);
-
-    // fp32 running sum of the per-k-tile main accumulators.  The tensor core adds into its TMEM accumulator with
-    // truncation (biased toward zero); keeping every hi*hi partial sum to ONE k-tile (3 truncating adds) and summing the
-    // tiles here with IEEE round-to-nearest keeps the layer at fp32-grade error.
-    float accr[TN];
+    if (warp >= W_PROD0 && warp < W_MMA) {
+        // =========================================== producers ===========================================
+        const int chunk = lane & 3, rsub = lane >> 2;          // 4 x 16 B chunks per row, 8 rows per pass, 16 passes
+        const bool a_vec = ((g.lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0) &&
+                           (!g.a_pre || (reinterpret_cast<uintptr_t>(g.a_pre) & 15) == 0);
+        const bool w_vec = ((g.K & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.Wh) & 15) == 0) &&
+                           ((reinterpret_cast<uintptr_t>(g.Wl) & 15) == 0);
+        for (int kt = warp - W_PROD0; kt < nk; kt += NPROD) {
+            const int s = kt % NST, use = kt / NST;
+            uint8_t* st = smem + s * STAGE_BYTES;
+            const int k = kt * TK + chunk * 4;
+            // ---- issue the global loads first (latency overlaps the wait for the stage) ----
+            float4 av[16];
 #pragma unroll
-    for (int i = 0; i < TN; ++i) accr[i] = 0.f;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
-    auto drain = [&](int tile) {
-        mbar_wait(&bar_mma[tile & 1], (tile >> 1) & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int p = 0; p < 16; ++p) {
+                const int64_t m = m0 + p * 8 + rsub;
+                float v[4] = {0.f, 0.f, 0.f, 0.f};
+                if (m < g.M && k < g.K) {
+                    const float* src = g.A + m * g.lda + k;
+                    if (a_vec && k + 3 < g.K) {
+                        const float4 t = *reinterpret_cast<const float4*>(src);
+                        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+                        if (g.a_pre) {
+                            const float4 q = *reinterpret_cast<const float4*>(g.a_pre + m * g.lda + k);
+                            v[0] *= spk_act_grad(q.x, g.a_act);
+                            v[1] *= spk_act_grad(q.y, g.a_act);
+                            v[2] *= spk_act_grad(q.z, g.a_act);
+                            v[3] *= spk_act_grad(q.w, g.a_act);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (k + i < g.K) {
+                                v[i] = src[i];
+                                if (g.a_pre) v[i] *= spk_act_grad(g.a_pre[m * g.lda + k + i], g.a_act);
+                            }
+                    }
+                }
+                av[p] = make_float4(v[0], v[1], v[2], v[3]);
+            }
+            if (use >= 1) mbar_wait(&empty_bar[s], (use - 1) & 1);      // MMAs that read this stage have retired
+#pragma unroll
+            for (int p = 0; p < 16; ++p) {
+                const float4 v = av[p];
+                float4 hi, lo;
+                hi.x = tf32_rn(v.x); hi.y = tf32_rn(v.y); hi.z = tf32_rn(v.z); hi.w = tf32_rn(v.w);
+                lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
+                const int off = tile_off(p * 8 + rsub, chunk);
+                *reinterpret_cast<float4*>(st + off) = hi;
+                *reinterpret_cast<float4*>(st + OPER_BYTES + off) = lo;
+            }
+            // ---- weight tiles (already split on the host): rows = output features n0 + r ----
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                float4 wh[8], wl[8];
+#pragma unroll
+                for (int p = 0; p < 8; ++p) {
+                    const int r = (half * 8 + p) * 8 + rsub;
+                    const int n = n0 + r;
+                    float4 hi = make_float4(0.f, 0.f, 0.f, 0.f), lo = hi;
+                    if (r < BN && n < g.N && k < g.K) {
+                        const int64_t o = (int64_t)n * g.K + k;
+                        if (w_vec && k + 3 < g.K) {
+                            hi = *reinterpret_cast<const float4*>(g.Wh + o);
+                            lo = *reinterpret_cast<const float4*>(g.Wl + o);
+                        } else {
+                            float h[4] = {0.f, 0.f, 0.f, 0.f}, l[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                if (k + i < g.K) {
+                                    h[i] = g.Wh[o + i];
+                                    l[i] = g.Wl[o + i];
+                                }
+                            hi = make_float4(h[0], h[1], h[2], h[3]);
+                            lo = make_float4(l[0], l[1], l[2], l[3]);
+                        }
+                    }
+                    wh[p] = hi;
+                    wl[p] = lo;
+                }
+#pragma unroll
+                for (int p = 0; p < 8; ++p) {
+                    const int r = (half * 8 + p) * 8 + rsub;
+                    if (r < BN) {
+                        const int off = tile_off(r, chunk);
+                        *reinterpret_cast<float4*>(st + 2 * OPER_BYTES + off) = wh[p];
+                        *reinterpret_cast<float4*>(st + 3 * OPER_BYTES + off) = wl[p];
+                    }
+                }
+            }
+            // generic-proxy stores -> visible to the tensor core (async proxy), then signal the MMA warp
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_bar[s]);
+        }
+    } else if (warp == W_MMA) {
+        // =========================================== MMA issuer ===========================================
+        if (lane == 0) {
+            // instruction descriptor: D=F32 (1<<4), A=B=TF32 (2<<7, 2<<10), K-major, N>>3 at [17,23), M>>4 at [24,29)
+            const uint32_t idesc =
+                (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+            for (int kt = 0; kt < nk; ++kt) {
+                const int s = kt % NST, buf = kt & 1;
+                mbar_wait(&full_bar[s], (kt / NST) & 1);
+                if (kt >= 2) mbar_wait(&acc_empty[buf], ((kt >> 1) - 1) & 1);   // drain warps are done with this buffer
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+                const uint32_t d_main = tmem_base + (uint32_t)(buf * TN);
+                const uint32_t d_corr = tmem_base + (uint32_t)(2 * TN);
+#pragma unroll
+                for (int ks = 0; ks < TK / 8; ++ks) {
+                    const uint64_t ah = make_desc(sa + 2 * ks * PLANE);
+                    const uint64_t al = make_desc(sa + OPER_BYTES + 2 * ks * PLANE);
+                    const uint64_t bh = make_desc(sa + 2 * OPER_BYTES + 2 * ks * PLANE);
+                    const uint64_t bl = make_desc(sa + 3 * OPER_BYTES + 2 * ks * PLANE);
+                    umma_tf32(d_corr, al, bh, idesc, (kt | ks) ? 1u : 0u);   // small terms: accumulate over all of K
+                    umma_tf32(d_corr, ah, bl, idesc, 1u);
+                    umma_tf32(d_main, ah, bh, idesc, ks ? 1u : 0u);          // main term: fresh accumulator per K-tile
+                }
+                umma_commit(&empty_bar[s]);      // stage reusable once these MMAs have read it
+                umma_commit(&acc_full[buf]);     // main buffer (and, after the last tile, the corrections) ready
+            }
+        }
+    } else {
+        // =========================================== drain + epilogue ===========================================
+        const int q = warp & 3;                          // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;                   // output row inside the tile == TMEM lane
+        const int64_t m = m0 + row;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        float accr[TN];
+#pragma unroll
+        for (int i = 0; i < TN; ++i) accr[i] = 0.f;
+        for (int kt = 0; kt < nk; ++kt) {
+            const int buf = kt & 1;
+            mbar_wait(&acc_full[buf], (kt >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int c0 = 0; c0 < TN; c0 += 32) {
+                if (c0 < BN) {
+                    uint32_t r[32];
+                    tmem_ld32(lane_addr + (uint32_t)(buf * TN + c0), r);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) accr[c0 + j] += __uint_as_float(r[j]);
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+        // the last acc_full commit also covers every correction MMA
 #pragma unroll
         for (int c0 = 0; c0 < TN; c0 += 32) {
-            if (c0 < BN) {
-                uint32_t r[32];
-                tmem_ld32(lane_addr + (uint32_t)c0, r);
+            if (c0 >= BN) break;
+            uint32_t r[32];
+            tmem_ld32(lane_addr + (uint32_t)(2 * TN + c0), r);
+            if (m < g.M) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) accr[c0 + j] += __uint_as_float(r[j]);
+                for (int j = 0; j < 32; j += 4) {
+                    const int n = n0 + c0 + j;
+                    if (n >= g.N) break;
+                    float v[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        v[i] = accr[c0 + j + i] + __uint_as_float(r[j + i]) + ((g.bias && n + i < g.N) ? g.bias[n + i] : 0.f);
+                    const bool full = (n + 3 < g.N);
+                    if (g.y_pre) {
+                        float* p = g.y_pre + m * g.ldy + n;
+                        if (full && ((g.ldy & 3) == 0)) *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+                        else
+                            for (int i = 0; i < 4; ++i)
+                                if (n + i < g.N) p[i] = v[i];
+                    }
+                    if (g.act != SPK_ACT_NONE) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) v[i] = spk_act(v[i], g.act);
+                    }
+                    if (g.addend) {
+                        const float* a = g.addend + m * g.ld_add + n;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (n + i < g.N) v[i] += a[i];
+                    }
+                    float* y = g.Y + m * g.ldy + n;
+                    if (full && ((g.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.Y) & 15) == 0))
+                        *reinterpret_cast<float4*>(y) = make_float4(v[0], v[1], v[2], v[3]);
+                    else
+                        for (int i = 0; i < 4; ++i)
+                            if (n + i < g.N) y[i] = v[i];
+                }
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    };
-
-    for (int kt = 0; kt < nk; ++kt) {
-        const int s = kt & 1;
-        uint8_t* st = smem + s * STAGE_BYTES;
-        if (kt >= NSTAGE) mbar_wait(&bar_mma[s], ((kt - NSTAGE) >> 1) & 1);   // MMAs that read this stage retired
-        const int k = kt * TK + chunk * 4;
-        // ---- A tile: rows warp*32 + p*4 + rsub ------------------------------------------------------------------
-#pragma unroll
-        for (int p = 0; p < 8; ++p) {
-            const int r = warp * 32 + p * 4 + rsub;
-            const int64_t m = m0 + r;
-            float v[4] = {0.f, 0.f, 0.f, 0.f};
-            if (m < g.M && k < g.K) {
-                const float* src = g.A + m * g.lda + k;
-                if (a_vec && k + 3 < g.K) {
-                    const float4 t = *reinterpret_cast<const float4*>(src);
-                    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-                    if (g.a_pre) {
-                        const float4 q = *reinterpret_cast<const float4*>(g.a_pre + m * g.lda + k);
-                        v[0] *= spk_act_grad(q.x, g.a_act);
-                        v[1] *= spk_act_grad(q.y, g.a_act);
-                        v[2] *= spk_act_grad(q.z, g.a_act);
-                        v[3] *= spk_act_grad(q.w, g.a_act);
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        if (k + i < g.K) {
-                            v[i] = src[i];
-                            if (g.a_pre) v[i] *= spk_act_grad(g.a_pre[m * g.lda + k + i], g.a_act);
-                        }
-                }
-            }
-            float4 hi, lo;
-            hi.x = tf32_rn(v[0]); hi.y = tf32_rn(v[1]); hi.z = tf32_rn(v[2]); hi.w = tf32_rn(v[3]);
-            lo.x = v[0] - hi.x; lo.y = v[1] - hi.y; lo.z = v[2] - hi.z; lo.w = v[3] - hi.w;
-            const int off = tile_off(r, chunk);
-            *reinterpret_cast<float4*>(st + off) = hi;
-            *reinterpret_cast<float4*>(st + OPER_BYTES + off) = lo;
-        }
-        // ---- W tile: rows (output features) n0 + r ---------------------------------------------------------------
-#pragma unroll
-        for (int p = 0; p < 8; ++p) {
-            const int r = warp * 32 + p * 4 + rsub;
-            if (r >= BN) continue;
-            const int n = n0 + r;
-            float4 hi = make_float4(0.f, 0.f, 0.f, 0.f), lo = hi;
-            if (n < g.N && k < g.K) {
-                const int64_t o = (int64_t)n * g.K + k;
-                if (w_vec && k + 3 < g.K) {
-                    hi = *reinterpret_cast<const float4*>(g.Wh + o);
-                    lo = *reinterpret_cast<const float4*>(g.Wl + o);
-                } else {
-                    float h[4] = {0.f, 0.f, 0.f, 0.f}, l[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        if (k + i < g.K) {
-                            h[i] = g.Wh[o + i];
-                            l[i] = g.Wl[o + i];
-                        }
-                    hi = make_float4(h[0], h[1], h[2], h[3]);
-                    lo = make_float4(l[0], l[1], l[2], l[3]);
-                }
-            }
-            const int off = tile_off(r, chunk);
-            *reinterpret_cast<float4*>(st + 2 * OPER_BYTES + off) = hi;
-            *reinterpret_cast<float4*>(st + 3 * OPER_BYTES + off) = lo;
-        }
-        // make the generic-proxy stores visible to the tensor core (async proxy), then hand over to the issuer
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
-        if (kt >= 1) {               // main accumulator of the previous k-tile -> registers, before it is overwritten
-            drain(kt - 1);
-            __syncthreads();
-        }
-        if (tid == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t sa = smem_u32(st);
-#pragma unroll
-            for (int ks = 0; ks < TK / 8; ++ks) {
-                // k-step ks covers 16 B chunks 2ks, 2ks+1  -> advance the start address by 2 planes
-                const uint64_t ah = make_desc(sa + 2 * ks * PLANE);
-                const uint64_t al = make_desc(sa + OPER_BYTES + 2 * ks * PLANE);
-                const uint64_t bh = make_desc(sa + 2 * OPER_BYTES + 2 * ks * PLANE);
-                const uint64_t bl = make_desc(sa + 3 * OPER_BYTES + 2 * ks * PLANE);
-                umma_tf32(tmem_base + TN, al, bh, idesc, (kt | ks) ? 1u : 0u);   // small terms: own accumulator
-                umma_tf32(tmem_base + TN, ah, bl, idesc, 1u);
-                umma_tf32(tmem_base, ah, bh, idesc, ks ? 1u : 0u);               // main term: fresh every k-tile
-            }
-            // arrives on the stage barrier when every MMA issued so far has completed (implies before_thread_sync)
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                smem_u32(&bar_mma[s])) : "memory");
-        }
     }
-    // ---- last k-tile, then the correction accumulator (lo terms of all k-tiles), then the epilogue -----------------
-    drain(nk - 1);
-    const int64_t m = m0 + tid;                     // TMEM lane == output row
-#pragma unroll
-    for (int c0 = 0; c0 < TN; c0 += 32) {
-        if (c0 >= BN) break;
-        uint32_t r[32];
-        tmem_ld32(lane_addr + (uint32_t)(TN + c0), r);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(accr[c0 + j] + __uint_as_float(r[j]));
-        if (m < g.M) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                const int n = n0 + c0 + j;
-                if (n >= g.N) break;
-                float v[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[j + i]) + ((g.bias && n + i < g.N) ? g.bias[n + i] : 0.f);
-                const bool full = (n + 3 < g.N);
-                if (g.y_pre) {
-                    float* p = g.y_pre + m * g.ldy + n;
-                    if (full && ((g.ldy & 3) == 0)) *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-                    else
-                        for (int i = 0; i < 4; ++i)
-                            if (n + i < g.N) p[i] = v[i];
-                }
-                if (g.act != SPK_ACT_NONE) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) v[i] = spk_act(v[i], g.act);
-                }
-                if (g.addend) {
-                    const float* a = g.addend + m * g.ld_add + n;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        if (n + i < g.N) v[i] += a[i];
-                }
-                float* y = g.Y + m * g.ldy + n;
-                if (full && ((g.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.Y) & 15) == 0))
-                    *reinterpret_cast<float4*>(y) = make_float4(v[0], v[1], v[2], v[3]);
-                else
-                    for (int i = 0; i < 4; ++i)
-                        if (n + i < g.N) y[i] = v[i];
-            }
-        }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * TN));
+    if (warp == W_MMA) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
     }
 }
 
@@ -322,7 +376,7 @@ extern "C" int spk_dense_tc(const float* A, int64_t M, int K, int64_t lda, const
     g.A = A; g.a_pre = a_pre; g.Wh = W_hi; g.Wl = W_lo; g.bias = bias; g.addend = addend; g.Y = Y; g.y_pre = y_pre;
     g.M = M; g.lda = lda; g.ld_add = ld_add; g.ldy = ldy; g.K = K; g.N = N; g.a_act = a_act; g.act = act;
     dim3 grid((unsigned)spk_cdiv(M, TM), (unsigned)spk_cdiv(N, TN));
-    k_dense_tc<<<grid, 128, SMEM_BYTES, spk_st(stream)>>>(g);
+    k_dense_tc<<<grid, NTHREADS, SMEM_BYTES, spk_st(stream)>>>(g);
     SPK_LAUNCH_CHECK();
     return SPK_OK;
 }

@@ -5,8 +5,8 @@ echo "tc rc=$?"; tail -4 gpurun_out/tc.log
 SPK_B200_DENSE=tc timeout 900 python -m pytest tests/test_cuda_parity.py -q -m gpu -s --timeout=600 > gpurun_out/parity_tc.log 2>&1
 echo "parity_tc rc=$?"
 grep -E "^\.?(painn|schnet|cfg)|passed|failed" gpurun_out/parity_tc.log | cut -c1-330
-SPK_B200_DENSE=tc SPK_B200_EDGE=ldg timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_tc.json 2> gpurun_out/bench_tc.err
-SPK_B200_DENSE=ffma SPK_B200_EDGE=ldg timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_ldg.json 2> gpurun_out/bench_ldg.err
+SPK_B200_DENSE=tc timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_tc.json 2> gpurun_out/bench_tc.err
+SPK_B200_DENSE=ffma timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_ldg.json 2> gpurun_out/bench_ldg.err
 python - <<'PY'
 import json
 for n in ("tc","ldg"):
