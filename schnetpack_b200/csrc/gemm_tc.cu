@@ -103,6 +103,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// activation (gradient) helpers kept out of line: the producer / epilogue loops are fully unrolled over register
+// arrays, inlining expf/log1pf 64x per loop blew the kernel up to 26k SASS instructions and it stalled on the
+// instruction cache (ncu: stall_no_inst 30 %)
+template <int ACT>
+__device__ __noinline__ float4 act_grad4(float4 q) {
+    return make_float4(spk_act_grad(q.x, ACT), spk_act_grad(q.y, ACT), spk_act_grad(q.z, ACT), spk_act_grad(q.w, ACT));
+}
+template <int ACT>
+__device__ __noinline__ float4 act4(float4 v) {
+    return make_float4(spk_act(v.x, ACT), spk_act(v.y, ACT), spk_act(v.z, ACT), spk_act(v.w, ACT));
+}
+
 struct TcArgs {
     const float* A;
     const float* a_pre;
@@ -119,6 +131,9 @@ struct TcArgs {
 // byte offset of (row r, 16 B chunk c) inside an operand tile
 __device__ __forceinline__ int tile_off(int r, int c) { return c * PLANE + (r >> 3) * 128 + (r & 7) * 16; }
 
+// Fast-path requirements (checked by the dispatcher, otherwise the fp32 kernel runs): lda, ldy, ld_add, K multiples of 4
+// and 16 B-aligned base pointers.
+template <int A_ACT, int ACT>
 __global__ void __launch_bounds__(NTHREADS, 1) k_dense_tc(TcArgs g) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t full_bar[NST];
@@ -159,42 +174,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dense_tc(TcArgs g) {
     if (warp >= W_PROD0 && warp < W_MMA) {
         // =========================================== producers ===========================================
         const int chunk = lane & 3, rsub = lane >> 2;          // 4 x 16 B chunks per row, 8 rows per pass, 16 passes
-        const bool a_vec = ((g.lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0) &&
-                           (!g.a_pre || (reinterpret_cast<uintptr_t>(g.a_pre) & 15) == 0);
-        const bool w_vec = ((g.K & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.Wh) & 15) == 0) &&
-                           ((reinterpret_cast<uintptr_t>(g.Wl) & 15) == 0);
         for (int kt = warp - W_PROD0; kt < nk; kt += NPROD) {
             const int s = kt % NST, use = kt / NST;
             uint8_t* st = smem + s * STAGE_BYTES;
             const int k = kt * TK + chunk * 4;
+            const bool k_ok = k < g.K;                         // K % 4 == 0: a 16 B chunk is entirely in or out
             // ---- issue the global loads first (latency overlaps the wait for the stage) ----
             float4 av[16];
 #pragma unroll
             for (int p = 0; p < 16; ++p) {
                 const int64_t m = m0 + p * 8 + rsub;
-                float v[4] = {0.f, 0.f, 0.f, 0.f};
-                if (m < g.M && k < g.K) {
-                    const float* src = g.A + m * g.lda + k;
-                    if (a_vec && k + 3 < g.K) {
-                        const float4 t = *reinterpret_cast<const float4*>(src);
-                        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-                        if (g.a_pre) {
-                            const float4 q = *reinterpret_cast<const float4*>(g.a_pre + m * g.lda + k);
-                            v[0] *= spk_act_grad(q.x, g.a_act);
-                            v[1] *= spk_act_grad(q.y, g.a_act);
-                            v[2] *= spk_act_grad(q.z, g.a_act);
-                            v[3] *= spk_act_grad(q.w, g.a_act);
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            if (k + i < g.K) {
-                                v[i] = src[i];
-                                if (g.a_pre) v[i] *= spk_act_grad(g.a_pre[m * g.lda + k + i], g.a_act);
-                            }
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (k_ok && m < g.M) {
+                    v = *reinterpret_cast<const float4*>(g.A + m * g.lda + k);
+                    if (A_ACT != SPK_ACT_NONE) {
+                        const float4 d = act_grad4<A_ACT>(*reinterpret_cast<const float4*>(g.a_pre + m * g.lda + k));
+                        v.x *= d.x; v.y *= d.y; v.z *= d.z; v.w *= d.w;
                     }
                 }
-                av[p] = make_float4(v[0], v[1], v[2], v[3]);
+                av[p] = v;
             }
             if (use >= 1) mbar_wait(&empty_bar[s], (use - 1) & 1);      // MMAs that read this stage have retired
 #pragma unroll
@@ -216,22 +214,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dense_tc(TcArgs g) {
                     const int r = (half * 8 + p) * 8 + rsub;
                     const int n = n0 + r;
                     float4 hi = make_float4(0.f, 0.f, 0.f, 0.f), lo = hi;
-                    if (r < BN && n < g.N && k < g.K) {
+                    if (r < BN && n < g.N && k_ok) {
                         const int64_t o = (int64_t)n * g.K + k;
-                        if (w_vec && k + 3 < g.K) {
-                            hi = *reinterpret_cast<const float4*>(g.Wh + o);
-                            lo = *reinterpret_cast<const float4*>(g.Wl + o);
-                        } else {
-                            float h[4] = {0.f, 0.f, 0.f, 0.f}, l[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                            for (int i = 0; i < 4; ++i)
-                                if (k + i < g.K) {
-                                    h[i] = g.Wh[o + i];
-                                    l[i] = g.Wl[o + i];
-                                }
-                            hi = make_float4(h[0], h[1], h[2], h[3]);
-                            lo = make_float4(l[0], l[1], l[2], l[3]);
-                        }
+                        hi = *reinterpret_cast<const float4*>(g.Wh + o);
+                        lo = *reinterpret_cast<const float4*>(g.Wl + o);
                     }
                     wh[p] = hi;
                     wl[p] = lo;
@@ -315,35 +301,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dense_tc(TcArgs g) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     const int n = n0 + c0 + j;
-                    if (n >= g.N) break;
-                    float v[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        v[i] = accr[c0 + j + i] + __uint_as_float(r[j + i]) + ((g.bias && n + i < g.N) ? g.bias[n + i] : 0.f);
-                    const bool full = (n + 3 < g.N);
-                    if (g.y_pre) {
-                        float* p = g.y_pre + m * g.ldy + n;
-                        if (full && ((g.ldy & 3) == 0)) *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-                        else
-                            for (int i = 0; i < 4; ++i)
-                                if (n + i < g.N) p[i] = v[i];
+                    if (n >= g.N) break;                      // N % 4 == 0: whole float4 groups only
+                    float4 v;
+                    v.x = accr[c0 + j + 0] + __uint_as_float(r[j + 0]);
+                    v.y = accr[c0 + j + 1] + __uint_as_float(r[j + 1]);
+                    v.z = accr[c0 + j + 2] + __uint_as_float(r[j + 2]);
+                    v.w = accr[c0 + j + 3] + __uint_as_float(r[j + 3]);
+                    if (g.bias) {
+                        const float4 bv = *reinterpret_cast<const float4*>(g.bias + n);
+                        v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
                     }
-                    if (g.act != SPK_ACT_NONE) {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) v[i] = spk_act(v[i], g.act);
-                    }
+                    if (g.y_pre) *reinterpret_cast<float4*>(g.y_pre + m * g.ldy + n) = v;
+                    if (ACT != SPK_ACT_NONE) v = act4<ACT>(v);
                     if (g.addend) {
-                        const float* a = g.addend + m * g.ld_add + n;
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            if (n + i < g.N) v[i] += a[i];
+                        const float4 a = *reinterpret_cast<const float4*>(g.addend + m * g.ld_add + n);
+                        v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
                     }
-                    float* y = g.Y + m * g.ldy + n;
-                    if (full && ((g.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.Y) & 15) == 0))
-                        *reinterpret_cast<float4*>(y) = make_float4(v[0], v[1], v[2], v[3]);
-                    else
-                        for (int i = 0; i < 4; ++i)
-                            if (n + i < g.N) y[i] = v[i];
+                    *reinterpret_cast<float4*>(g.Y + m * g.ldy + n) = v;
                 }
             }
         }
@@ -358,6 +332,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dense_tc(TcArgs g) {
 
 }  // namespace
 
+template <int A_ACT, int ACT>
+static int launch_tc(const TcArgs& g, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_dense_tc<A_ACT, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) return SPK_CUDA_ERR(e);
+        attr_set = true;
+    }
+    dim3 grid((unsigned)spk_cdiv(g.M, TM), (unsigned)spk_cdiv(g.N, TN));
+    k_dense_tc<A_ACT, ACT><<<grid, NTHREADS, SMEM_BYTES, st>>>(g);
+    return 0;
+}
+
 extern "C" int spk_dense_tc(const float* A, int64_t M, int K, int64_t lda, const float* a_pre, int a_act,
                             const float* W_hi, const float* W_lo, int N, const float* bias, int act, const float* addend,
                             int64_t ld_add, float* Y, int64_t ldy, float* y_pre, spk_stream_t stream) {
@@ -366,17 +353,23 @@ extern "C" int spk_dense_tc(const float* A, int64_t M, int K, int64_t lda, const
     if (M == 0) return SPK_OK;
     if (!A || !W_hi || !W_lo || !Y) return SPK_ERR_ARG;
     if (addend && ld_add < N) return SPK_ERR_ARG;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_dense_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        if (e != cudaSuccess) return SPK_CUDA_ERR(e);
-        attr_set = true;
-    }
+    if (!a_pre) a_act = SPK_ACT_NONE;
+    auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    const bool fast = !(K & 3) && !(N & 3) && !(lda & 3) && !(ldy & 3) && !(ld_add & 3) && al(A) && al(a_pre) &&
+                      al(W_hi) && al(W_lo) && al(bias) && al(addend) && al(Y) && al(y_pre) &&
+                      (a_act == SPK_ACT_NONE || act == SPK_ACT_NONE);
+    if (!fast) return SPK_ERR_UNSUPPORTED;   // caller falls back to spk_dense (fp32 CUDA-core kernel)
     TcArgs g;
     g.A = A; g.a_pre = a_pre; g.Wh = W_hi; g.Wl = W_lo; g.bias = bias; g.addend = addend; g.Y = Y; g.y_pre = y_pre;
     g.M = M; g.lda = lda; g.ld_add = ld_add; g.ldy = ldy; g.K = K; g.N = N; g.a_act = a_act; g.act = act;
-    dim3 grid((unsigned)spk_cdiv(M, TM), (unsigned)spk_cdiv(N, TN));
-    k_dense_tc<<<grid, NTHREADS, SMEM_BYTES, spk_st(stream)>>>(g);
+    cudaStream_t st = spk_st(stream);
+    int rc;
+    if (a_act == SPK_ACT_NONE) {
+        rc = act == SPK_ACT_NONE ? launch_tc<0, 0>(g, st) : act == SPK_ACT_SILU ? launch_tc<0, 1>(g, st) : launch_tc<0, 2>(g, st);
+    } else {
+        rc = a_act == SPK_ACT_SILU ? launch_tc<1, 0>(g, st) : launch_tc<2, 0>(g, st);
+    }
+    if (rc) return rc;
     SPK_LAUNCH_CHECK();
     return SPK_OK;
 }

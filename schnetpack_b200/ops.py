@@ -281,15 +281,24 @@ class Lin:
         self.w_hl = split_tf32(self.w)
         self.wt_hl = split_tf32(self.wt)
 
+    @staticmethod
+    def _tc_ok(A: Tensor, n_out: int, kw) -> bool:
+        """shapes the tensor-core kernel's vector fast path covers (otherwise the fp32 kernel runs)"""
+        k = kw.get("k")
+        K = A.shape[1] if k is None else int(k)
+        out = kw.get("out")
+        ldy = n_out if out is None else out.shape[1]
+        return K % 4 == 0 and n_out % 4 == 0 and A.shape[1] % 4 == 0 and ldy % 4 == 0
+
     def fwd(self, A: Tensor, act: int = ACT_NONE, **kw):
         """act(A W^T + b) [+ addend]"""
-        if DENSE_IMPL == "tc":
+        if DENSE_IMPL == "tc" and self._tc_ok(A, self.w.shape[0], kw):
             return dense_tc(A, self.w_hl[0], self.w_hl[1], self.b, act, **kw)
         return dense(A, self.wt, self.b, act, **kw)
 
     def bwd(self, G: Tensor, **kw):
         """(G .* act'(a_pre)) W [+ addend]  -- input gradient of the layer"""
-        if DENSE_IMPL == "tc":
+        if DENSE_IMPL == "tc" and self._tc_ok(G, self.wt.shape[0], kw):
             return dense_tc(G, self.wt_hl[0], self.wt_hl[1], None, ACT_NONE, **kw)
         return dense(G, self.w, None, ACT_NONE, **kw)
 
