@@ -101,12 +101,17 @@ int spk_dense(const float* A, int64_t M, int K, int64_t lda, const float* a_pre,
               const float* bias, int act, const float* addend, int64_t ld_add, float* Y, int64_t ldy, float* y_pre,
               spk_stream_t stream);
 
-/* Same layer on the tcgen05 tensor cores with 3xTF32 error compensation (fp32-equivalent results, see csrc/gemm_tc.cu).
- * W_hi / W_lo: [N, K] row-major (K contiguous) split of the weight the A rows are contracted with, i.e. the torch
- * weight itself for a forward layer and its transpose for the input-gradient:  W_hi = tf32_round(W), W_lo = W - W_hi. */
-int spk_dense_tc(const float* A, int64_t M, int K, int64_t lda, const float* a_pre, int a_act, const float* W_hi,
-                 const float* W_lo, int N, const float* bias, int act, const float* addend, int64_t ld_add, float* Y,
-                 int64_t ldy, float* y_pre, spk_stream_t stream);
+/* Same layer on the tcgen05 tensor cores with 3xTF32 error compensation (fp32-grade results: split accumulators, K-tile
+ * draining; see csrc/gemm_tc.cu).  The weight the A rows are contracted with -- the torch weight [N,K] itself for a
+ * forward layer, its transpose for the input-gradient -- is packed once by spk_tc_pack_weight into per-(64-row, 16-column)
+ * operand tiles [tf32_round(W) | W - tf32_round(W)] laid out exactly as the kernel's shared-memory UMMA operand, so one TMA
+ * bulk copy stages a tile.  Requirements: K, N, lda, ldy, ld_add multiples of 4, 16 B-aligned pointers, and at most one of
+ * (a_act, act) active; otherwise SPK_ERR_UNSUPPORTED is returned and the caller uses spk_dense. */
+size_t spk_tc_packed_floats(int N, int K);
+int spk_tc_pack_weight(const float* W, int N, int K, float* packed, spk_stream_t stream);
+int spk_dense_tc(const float* A, int64_t M, int K, int64_t lda, const float* a_pre, int a_act, const float* W_packed,
+                 int N, const float* bias, int act, const float* addend, int64_t ld_add, float* Y, int64_t ldy,
+                 float* y_pre, spk_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * PaiNN.  representation/painn.py:31-67 (PaiNNInteraction.forward) and :92-117 (PaiNNMixing.forward).

@@ -34,7 +34,9 @@ SIGNATURES = {
     "spk_embedding": [P, P, c_int64, c_int, c_int, P, P],
     "spk_segment_sum": [P, P, P, c_int64, c_int, P, P],
     "spk_dense": [P, c_int64, c_int, c_int64, P, c_int, P, c_int, P, c_int, P, c_int64, P, c_int64, P, P],
-    "spk_dense_tc": [P, c_int64, c_int, c_int64, P, c_int, P, P, c_int, P, c_int, P, c_int64, P, c_int64, P, P],
+    "spk_tc_packed_floats": [c_int, c_int],
+    "spk_tc_pack_weight": [P, c_int, c_int, P, P],
+    "spk_dense_tc": [P, c_int64, c_int, c_int64, P, c_int, P, c_int, P, c_int, P, c_int64, P, c_int64, P, P],
     "spk_painn_edge_fwd": [P, P, P, P, P, P, P, P, P, c_int64, c_int64, c_int, c_int, P, P, P],
     "spk_painn_edge_bwd": [P, P, P, P, P, P, P, P, P, P, P, P, P, c_int64, c_int64, c_int, c_int, P, P, P, c_int, P],
     "spk_painn_mix_ctx": [P, P, c_int64, c_int, c_float, P, P],
@@ -48,7 +50,7 @@ SIGNATURES = {
     "spk_atomwise_out_bwd": [P, P, P, c_int64, c_int, P, P],
     "spk_add": [P, P, c_int64, P, P],
 }
-_RESTYPE = {"spk_graph_workspace_bytes": c_size_t}
+_RESTYPE = {"spk_graph_workspace_bytes": c_size_t, "spk_tc_packed_floats": c_size_t}
 
 _lib = None
 

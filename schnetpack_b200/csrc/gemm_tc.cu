@@ -12,35 +12,40 @@
 //     FRESH accumulator that is drained into fp32 registers and summed there with IEEE round-to-nearest, while the small
 //     lo products accumulate over all of K in a separate TMEM accumulator (their truncation error is 2^-12 smaller).
 //
-// Warp-specialised pipeline, one CTA (8 warps) per 128 x BN (<=128) output tile, cta_group::1, UMMA 128 x BN x 8:
-//   warps 4-6  producers: producer p owns K-tiles p, p+3, ... : coalesced 128-bit global loads of the A tile (optional backward
-//              prologue x act'(a_pre)) and of the pre-split weight tiles, hi/lo split in registers, st.shared into the
-//              canonical K-major no-swizzle core-matrix layout (8 rows x 16 B cores, LBO = plane stride between 16 B
-//              K-chunks, SBO = 128 B between 8-row groups), fence.proxy.async, arrive on full[stage];
-//   warp 7     MMA issuer (one lane): waits full[stage] and acc_empty[buf], issues 6 tcgen05.mma.kind::tf32, then
+// Warp-specialised pipeline, one CTA (16 warps) per 128 x 64 output tile, cta_group::1, UMMA 128 x 64 x 8:
+//   warps 5-15 producers: each owns whole K-tiles (round robin).  Lane 0 arms full[stage] with the byte count of the
+//              weight tile and issues ONE TMA bulk copy (cp.async.bulk) of the pre-packed W_hi|W_lo operand tile (the
+//              weights are static, so the host packs them once in the exact shared-memory operand layout,
+//              spk_tc_pack_weight); all lanes load the A tile with coalesced 128-bit loads (optional backward prologue
+//              x act'(a_pre)), split hi/lo in registers and st.shared it in the canonical K-major no-swizzle core-matrix
+//              layout (8 rows x 16 B cores, LBO = plane stride between 16 B K-chunks, SBO = 128 B between 8-row
+//              groups); fence.proxy.async; arrive on full[stage];
+//   warp 4     MMA issuer (one lane): waits full[stage] and acc_empty[buf], issues 6 tcgen05.mma.kind::tf32, then
 //              tcgen05.commit -> empty[stage] and -> acc_full[buf];
 //   warps 0-3  drain + epilogue: tcgen05.ld.32x32b.x32 of the main accumulator buffer (thread = output row), fp32 add into
-//              128 register accumulators, arrive acc_empty[buf]; after the last K-tile add the correction accumulator,
+//              64 register accumulators, arrive acc_empty[buf]; after the last K-tile add the correction accumulator,
 //              apply bias / activation / addend, store.
-// Six shared-memory stages (33 KB each) and two main TMEM buffers let loads, MMAs and drains of different K-tiles overlap.
+// Eight shared-memory stages (24 KB each) and two main TMEM buffers let loads, MMAs and drains of different K-tiles overlap;
+// 128 x 64 tiles double the CTA count of these skinny problems (M = atoms) and keep every role under 128 registers.
 #include "common.cuh"
 
 namespace {
 
 constexpr int TM = 128;                        // rows per CTA tile (UMMA M)
-constexpr int TN = 128;                        // max columns per CTA tile (UMMA N)
+constexpr int TN = 64;                         // columns per CTA tile (UMMA N)
 constexpr int TK = 16;                         // floats per K-tile = 2 UMMA k-steps
-constexpr int NST = 6;                         // shared-memory stages
-constexpr int NPROD = 3;                       // producer warps (8 warps total keeps the 255-register budget)
-constexpr int GROUPS = TM / 8;                 // 8-row groups per operand tile
-constexpr int PLANE = GROUPS * 128 + 16;       // bytes between consecutive 16 B K-chunks (LBO), padded vs bank conflicts
-constexpr int OPER_BYTES = (TK / 4) * PLANE;   // one operand tile: TK/4 chunks of 16 B per row
-constexpr int STAGE_BYTES = 4 * OPER_BYTES;    // A_hi, A_lo, W_hi, W_lo
+constexpr int NST = 8;                         // shared-memory stages
+constexpr int NPROD = 11;                      // producer warps
+constexpr int PLANE_A = (TM / 8) * 128 + 16;   // bytes between consecutive 16 B K-chunks of the A tile (LBO), padded
+constexpr int PLANE_B = (TN / 8) * 128 + 16;   // same for the weight tile
+constexpr int OPER_A = (TK / 4) * PLANE_A;     // 8256 B
+constexpr int OPER_B = (TK / 4) * PLANE_B;     // 4160 B
+constexpr int STAGE_BYTES = 2 * OPER_A + 2 * OPER_B;   // A_hi, A_lo, W_hi, W_lo
 constexpr int SMEM_BYTES = NST * STAGE_BYTES;
-constexpr int NTHREADS = (4 + NPROD + 1) * 32;    // warps 0-3 drain/epilogue, 4..4+NPROD-1 producers, last = MMA
-constexpr int W_PROD0 = 4;                     // first producer warp
-constexpr int W_MMA = 4 + NPROD;               // MMA issuer warp
-constexpr int TMEM_COLS = 512;                 // main[0] | main[1] | corr | (unused)
+constexpr int W_MMA = 4;                       // warps 0-3 drain/epilogue, 4 MMA, 5.. producers
+constexpr int W_PROD0 = 5;
+constexpr int NTHREADS = (W_PROD0 + NPROD) * 32;
+constexpr int TMEM_COLS = 256;                 // main[0] | main[1] | corr | (unused)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -62,15 +67,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     // arrives on `bar` when every tcgen05.mma issued so far by this thread has completed (implies before_thread_sync)
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
 }
 
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t plane) {
     // K-major, SWIZZLE_NONE: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout 0 [61,64)
-    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(PLANE >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) |
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(plane >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) |
            (1ull << 46);
 }
 
@@ -118,8 +132,7 @@ __device__ __noinline__ float4 act4(float4 v) {
 struct TcArgs {
     const float* A;
     const float* a_pre;
-    const float* Wh;   // [N, K] tf32-rounded weights
-    const float* Wl;   // [N, K] residual
+    const float* Wp;   // packed weights: [ceil(N/64)][ceil(K/16)][W_hi tile | W_lo tile] in operand layout
     const float* bias;
     const float* addend;
     float* Y;
@@ -128,8 +141,27 @@ struct TcArgs {
     int K, N, a_act, act;
 };
 
-// byte offset of (row r, 16 B chunk c) inside an operand tile
-__device__ __forceinline__ int tile_off(int r, int c) { return c * PLANE + (r >> 3) * 128 + (r & 7) * 16; }
+// byte offset of (row r, 16 B chunk c) inside an operand tile with the given plane stride
+__host__ __device__ __forceinline__ int tile_off(int r, int c, int plane) { return c * plane + (r >> 3) * 128 + (r & 7) * 16; }
+
+// one-time packing of a weight matrix W [N,K] into per-(n-tile, k-tile) operand tiles [hi | lo]
+__global__ void k_pack_weight(const float* __restrict__ W, int N, int K, float* __restrict__ out) {
+    const int nkt = (K + TK - 1) / TK;
+    const int64_t total = (int64_t)((N + TN - 1) / TN) * nkt * TN * TK;
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int kk = (int)(t % TK);
+    const int r = (int)((t / TK) % TN);
+    const int kt = (int)((t / (TK * TN)) % nkt);
+    const int nt = (int)(t / ((int64_t)TK * TN * nkt));
+    const int n = nt * TN + r, k = kt * TK + kk;
+    const float w = (n < N && k < K) ? W[(int64_t)n * K + k] : 0.f;
+    const float hi = tf32_rn(w), lo = w - hi;
+    float* tile = out + ((int64_t)nt * nkt + kt) * (2 * OPER_B / 4);
+    const int off = tile_off(r, kk >> 2, PLANE_B) / 4 + (kk & 3);
+    tile[off] = hi;
+    tile[OPER_B / 4 + off] = lo;
+}
 
 // Fast-path requirements (checked by the dispatcher, otherwise the fp32 kernel runs): lda, ldy, ld_add, K multiples of 4
 // and 16 B-aligned base pointers.
@@ -146,13 +178,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dense_tc(TcArgs g) {
     const int64_t m0 = (int64_t)blockIdx.x * TM;
     const int n0 = blockIdx.y * TN;
     const int bn_real = min(TN, g.N - n0);            // valid columns of this tile
-    const int BN = (bn_real + 15) & ~15;              // UMMA N (multiple of 16)
+    const int BN = TN;                                // UMMA N (weight tiles are zero padded to 64 rows)
+    (void)bn_real;
     const int nk = (g.K + TK - 1) / TK;
 
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < NST; ++s) {
-            mbar_init(&full_bar[s], 1);
+            mbar_init(&full_bar[s], 2);      // expect_tx arrive (weight TMA) + arrive after the A tile is stored
             mbar_init(&empty_bar[s], 1);
         }
         mbar_init(&acc_full[0], 1);
@@ -171,9 +204,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dense_tc(TcArgs g) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = s_tmem;
 
-    if (warp >= W_PROD0 && warp < W_MMA) {
+    if (warp >= W_PROD0) {
         // =========================================== producers ===========================================
         const int chunk = lane & 3, rsub = lane >> 2;          // 4 x 16 B chunks per row, 8 rows per pass, 16 passes
+        const float* wp_tile0 = g.Wp + (int64_t)blockIdx.y * nk * (2 * OPER_B / 4);
         for (int kt = warp - W_PROD0; kt < nk; kt += NPROD) {
             const int s = kt % NST, use = kt / NST;
             uint8_t* st = smem + s * STAGE_BYTES;
@@ -195,42 +229,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dense_tc(TcArgs g) {
                 av[p] = v;
             }
             if (use >= 1) mbar_wait(&empty_bar[s], (use - 1) & 1);      // MMAs that read this stage have retired
+            if (lane == 0) {   // weight tile (hi|lo, already in operand layout): one TMA bulk copy
+                mbar_expect_tx(&full_bar[s], 2 * OPER_B);
+                tma_load(st + 2 * OPER_A, wp_tile0 + (int64_t)kt * (2 * OPER_B / 4), 2 * OPER_B, &full_bar[s]);
+            }
 #pragma unroll
             for (int p = 0; p < 16; ++p) {
                 const float4 v = av[p];
                 float4 hi, lo;
                 hi.x = tf32_rn(v.x); hi.y = tf32_rn(v.y); hi.z = tf32_rn(v.z); hi.w = tf32_rn(v.w);
                 lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
-                const int off = tile_off(p * 8 + rsub, chunk);
+                const int off = tile_off(p * 8 + rsub, chunk, PLANE_A);
                 *reinterpret_cast<float4*>(st + off) = hi;
-                *reinterpret_cast<float4*>(st + OPER_BYTES + off) = lo;
-            }
-            // ---- weight tiles (already split on the host): rows = output features n0 + r ----
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                float4 wh[8], wl[8];
-#pragma unroll
-                for (int p = 0; p < 8; ++p) {
-                    const int r = (half * 8 + p) * 8 + rsub;
-                    const int n = n0 + r;
-                    float4 hi = make_float4(0.f, 0.f, 0.f, 0.f), lo = hi;
-                    if (r < BN && n < g.N && k_ok) {
-                        const int64_t o = (int64_t)n * g.K + k;
-                        hi = *reinterpret_cast<const float4*>(g.Wh + o);
-                        lo = *reinterpret_cast<const float4*>(g.Wl + o);
-                    }
-                    wh[p] = hi;
-                    wl[p] = lo;
-                }
-#pragma unroll
-                for (int p = 0; p < 8; ++p) {
-                    const int r = (half * 8 + p) * 8 + rsub;
-                    if (r < BN) {
-                        const int off = tile_off(r, chunk);
-                        *reinterpret_cast<float4*>(st + 2 * OPER_BYTES + off) = wh[p];
-                        *reinterpret_cast<float4*>(st + 3 * OPER_BYTES + off) = wl[p];
-                    }
-                }
+                *reinterpret_cast<float4*>(st + OPER_A + off) = lo;
             }
             // generic-proxy stores -> visible to the tensor core (async proxy), then signal the MMA warp
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -253,10 +264,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dense_tc(TcArgs g) {
                 const uint32_t d_corr = tmem_base + (uint32_t)(2 * TN);
 #pragma unroll
                 for (int ks = 0; ks < TK / 8; ++ks) {
-                    const uint64_t ah = make_desc(sa + 2 * ks * PLANE);
-                    const uint64_t al = make_desc(sa + OPER_BYTES + 2 * ks * PLANE);
-                    const uint64_t bh = make_desc(sa + 2 * OPER_BYTES + 2 * ks * PLANE);
-                    const uint64_t bl = make_desc(sa + 3 * OPER_BYTES + 2 * ks * PLANE);
+                    const uint64_t ah = make_desc(sa + 2 * ks * PLANE_A, PLANE_A);
+                    const uint64_t al = make_desc(sa + OPER_A + 2 * ks * PLANE_A, PLANE_A);
+                    const uint64_t bh = make_desc(sa + 2 * OPER_A + 2 * ks * PLANE_B, PLANE_B);
+                    const uint64_t bl = make_desc(sa + 2 * OPER_A + OPER_B + 2 * ks * PLANE_B, PLANE_B);
                     umma_tf32(d_corr, al, bh, idesc, (kt | ks) ? 1u : 0u);   // small terms: accumulate over all of K
                     umma_tf32(d_corr, ah, bl, idesc, 1u);
                     umma_tf32(d_main, ah, bh, idesc, ks ? 1u : 0u);          // main term: fresh accumulator per K-tile
@@ -345,22 +356,36 @@ static int launch_tc(const TcArgs& g, cudaStream_t st) {
     return 0;
 }
 
+extern "C" size_t spk_tc_packed_floats(int N, int K) {
+    return (size_t)((N + TN - 1) / TN) * ((K + TK - 1) / TK) * (2 * OPER_B / 4);
+}
+
+extern "C" int spk_tc_pack_weight(const float* W, int N, int K, float* packed, spk_stream_t stream) {
+    if (N <= 0 || K <= 0 || !W || !packed) return SPK_ERR_ARG;
+    cudaError_t e = cudaMemsetAsync(packed, 0, spk_tc_packed_floats(N, K) * sizeof(float), spk_st(stream));
+    if (e != cudaSuccess) return SPK_CUDA_ERR(e);
+    const int64_t total = (int64_t)((N + TN - 1) / TN) * ((K + TK - 1) / TK) * TN * TK;
+    k_pack_weight<<<(unsigned)spk_cdiv(total, 256), 256, 0, spk_st(stream)>>>(W, N, K, packed);
+    SPK_LAUNCH_CHECK();
+    return SPK_OK;
+}
+
 extern "C" int spk_dense_tc(const float* A, int64_t M, int K, int64_t lda, const float* a_pre, int a_act,
-                            const float* W_hi, const float* W_lo, int N, const float* bias, int act, const float* addend,
+                            const float* W_packed, int N, const float* bias, int act, const float* addend,
                             int64_t ld_add, float* Y, int64_t ldy, float* y_pre, spk_stream_t stream) {
     if (M < 0 || K <= 0 || N <= 0 || lda < K || ldy < N) return SPK_ERR_ARG;
     if (act < 0 || act > 2 || a_act < 0 || a_act > 2) return SPK_ERR_ARG;
     if (M == 0) return SPK_OK;
-    if (!A || !W_hi || !W_lo || !Y) return SPK_ERR_ARG;
+    if (!A || !W_packed || !Y) return SPK_ERR_ARG;
     if (addend && ld_add < N) return SPK_ERR_ARG;
     if (!a_pre) a_act = SPK_ACT_NONE;
     auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     const bool fast = !(K & 3) && !(N & 3) && !(lda & 3) && !(ldy & 3) && !(ld_add & 3) && al(A) && al(a_pre) &&
-                      al(W_hi) && al(W_lo) && al(bias) && al(addend) && al(Y) && al(y_pre) &&
+                      al(W_packed) && al(bias) && al(addend) && al(Y) && al(y_pre) &&
                       (a_act == SPK_ACT_NONE || act == SPK_ACT_NONE);
     if (!fast) return SPK_ERR_UNSUPPORTED;   // caller falls back to spk_dense (fp32 CUDA-core kernel)
     TcArgs g;
-    g.A = A; g.a_pre = a_pre; g.Wh = W_hi; g.Wl = W_lo; g.bias = bias; g.addend = addend; g.Y = Y; g.y_pre = y_pre;
+    g.A = A; g.a_pre = a_pre; g.Wp = W_packed; g.bias = bias; g.addend = addend; g.Y = Y; g.y_pre = y_pre;
     g.M = M; g.lda = lda; g.ld_add = ld_add; g.ldy = ldy; g.K = K; g.N = N; g.a_act = a_act; g.act = act;
     cudaStream_t st = spk_st(stream);
     int rc;

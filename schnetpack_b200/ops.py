@@ -229,17 +229,24 @@ def dense(A: Tensor, B: Tensor, bias: Optional[Tensor] = None, act: int = ACT_NO
     return (Y, pre) if save_pre else Y
 
 
-def dense_tc(A: Tensor, w_hi: Tensor, w_lo: Tensor, bias: Optional[Tensor] = None, act: int = ACT_NONE,
+def tc_pack_weight(w: Tensor) -> Tensor:
+    """Pack W [N,K] into the tensor-core kernel's operand tiles (hi|lo TF32 split, shared-memory layout)."""
+    f32(w, "weight")
+    N, K = w.shape
+    out = torch.empty(_lib.lib().spk_tc_packed_floats(N, K), dtype=torch.float32, device=w.device)
+    _lib.call("spk_tc_pack_weight", _p(w), N, K, _p(out), _stream())
+    return out
+
+
+def dense_tc(A: Tensor, w_packed: Tensor, n_out: int, bias: Optional[Tensor] = None, act: int = ACT_NONE,
              a_pre: Optional[Tensor] = None, a_act: int = ACT_NONE, addend: Optional[Tensor] = None,
              save_pre: bool = False, k: Optional[int] = None, out: Optional[Tensor] = None):
-    """tcgen05 / 3xTF32 variant of ``dense``: Y = act((A .* act'(a_pre)) @ W^T + bias) + addend with W = w_hi + w_lo
-    given as [N, K] (K contiguous)."""
+    """tcgen05 / 3xTF32 variant of ``dense``: Y = act((A .* act'(a_pre)) @ W^T + bias) + addend with W [n_out, K] given
+    in packed form (``tc_pack_weight``)."""
     f32(A, "A")
     M, lda = A.shape
     K = lda if k is None else int(k)
-    N, K2 = w_hi.shape
-    if K2 != K:
-        raise ValueError(f"dense_tc: inner dimensions differ ({K} vs {K2})")
+    N = int(n_out)
     if out is None:
         Y = torch.empty((M, N), dtype=torch.float32, device=A.device)
     else:
@@ -250,8 +257,8 @@ def dense_tc(A: Tensor, w_hi: Tensor, w_lo: Tensor, bias: Optional[Tensor] = Non
     pre = torch.empty_like(Y) if save_pre else None
     if addend is not None and (addend.shape[0] != M or addend.shape[1] != N):
         raise ValueError("dense_tc: addend shape mismatch")
-    _lib.call("spk_dense_tc", _p(A), M, K, lda, _p(a_pre), a_act, _p(f32(w_hi)), _p(f32(w_lo)), N, _p(bias), act,
-              _p(addend), N, _p(Y), ldy, _p(pre), _stream())
+    _lib.call("spk_dense_tc", _p(A), M, K, lda, _p(a_pre), a_act, _p(f32(w_packed)), N, _p(bias), act, _p(addend), N,
+              _p(Y), ldy, _p(pre), _stream())
     return (Y, pre) if save_pre else Y
 
 
@@ -272,14 +279,16 @@ DENSE_IMPL = os.environ.get("SPK_B200_DENSE", "ffma")
 class Lin:
     """Kernel-ready copy of one Dense layer: W [N,K], W^T [K,N], bias, and their TF32 hi/lo splits."""
 
-    __slots__ = ("w", "wt", "b", "w_hl", "wt_hl")
+    __slots__ = ("w", "wt", "b", "w_pk", "wt_pk")
 
     def __init__(self, weight: Tensor, bias: Optional[Tensor] = None):
         self.w = weight.detach().contiguous()
         self.wt = weight.detach().t().contiguous()
         self.b = bias.detach().contiguous() if bias is not None else None
-        self.w_hl = split_tf32(self.w)
-        self.wt_hl = split_tf32(self.wt)
+        self.w_pk = self.wt_pk = None
+        if DENSE_IMPL == "tc" and self.w.is_cuda:
+            self.w_pk = tc_pack_weight(self.w)
+            self.wt_pk = tc_pack_weight(self.wt)
 
     @staticmethod
     def _tc_ok(A: Tensor, n_out: int, kw) -> bool:
@@ -292,14 +301,14 @@ class Lin:
 
     def fwd(self, A: Tensor, act: int = ACT_NONE, **kw):
         """act(A W^T + b) [+ addend]"""
-        if DENSE_IMPL == "tc" and self._tc_ok(A, self.w.shape[0], kw):
-            return dense_tc(A, self.w_hl[0], self.w_hl[1], self.b, act, **kw)
+        if self.w_pk is not None and self._tc_ok(A, self.w.shape[0], kw):
+            return dense_tc(A, self.w_pk, self.w.shape[0], self.b, act, **kw)
         return dense(A, self.wt, self.b, act, **kw)
 
     def bwd(self, G: Tensor, **kw):
         """(G .* act'(a_pre)) W [+ addend]  -- input gradient of the layer"""
-        if DENSE_IMPL == "tc" and self._tc_ok(G, self.wt.shape[0], kw):
-            return dense_tc(G, self.wt_hl[0], self.wt_hl[1], None, ACT_NONE, **kw)
+        if self.wt_pk is not None and self._tc_ok(G, self.wt.shape[0], kw):
+            return dense_tc(G, self.wt_pk, self.wt.shape[0], None, ACT_NONE, **kw)
         return dense(G, self.w, None, ACT_NONE, **kw)
 
 

@@ -180,19 +180,20 @@ def test_dense_tcgen05_3xtf32(M, K, N, lda):
     pre_in = torch.randn(M, lda, device=DEV)
     w_hi, w_lo = ops.split_tf32(W)
     assert torch.equal(w_hi + w_lo, W) and int((w_hi.view(torch.int32) & 0x1FFF).abs().max()) == 0
+    wp = ops.tc_pack_weight(W)
     ref_lin = A.double() @ W.double().t() + bias.double()
     for act, f in ((ops.ACT_NONE, lambda v: v), (ops.ACT_SILU, torch.nn.functional.silu),
                    (ops.ACT_SSP, lambda v: torch.nn.functional.softplus(v) - math.log(2.0))):
-        Y, pre = ops.dense_tc(Afull, w_hi, w_lo, bias, act, addend=add, save_pre=True, k=K)
+        Y, pre = ops.dense_tc(Afull, wp, N, bias, act, addend=add, save_pre=True, k=K)
         assert rel(pre, ref_lin) < 3e-6, rel(pre, ref_lin)
         assert rel(Y, f(ref_lin) + add.double()) < 3e-6
         p64 = pre_in[:, :K].double().requires_grad_()
         dact = torch.autograd.grad(f(p64).sum(), p64)[0]
-        Y2 = ops.dense_tc(Afull, w_hi, w_lo, a_pre=pre_in, a_act=act, k=K)
+        Y2 = ops.dense_tc(Afull, wp, N, a_pre=pre_in, a_act=act, k=K)
         assert rel(Y2, (A.double() * dact) @ W.double().t()) < 5e-6
     # padded output buffer (ldy > N)
     out = torch.full((M, N + 4), -1.0, device=DEV)
-    ops.dense_tc(Afull, w_hi, w_lo, bias, k=K, out=out)
+    ops.dense_tc(Afull, wp, N, bias, k=K, out=out)
     assert rel(out[:, :N], ref_lin) < 3e-6 and bool((out[:, N:] == -1.0).all())
 
 
