@@ -12,8 +12,8 @@
 //     FRESH accumulator that is drained into fp32 registers and summed there with IEEE round-to-nearest, while the small
 //     lo products accumulate over all of K in a separate TMEM accumulator (their truncation error is 2^-12 smaller).
 //
-// Warp-specialised pipeline, one CTA (16 warps) per 128 x 64 output tile, cta_group::1, UMMA 128 x 64 x 8:
-//   warps 5-15 producers: each owns whole K-tiles (round robin).  Lane 0 arms full[stage] with the byte count of the
+// Warp-specialised pipeline, one CTA (13 warps) per 128 x 64 output tile, cta_group::1, UMMA 128 x 64 x 8:
+//   warps 5-12 producers: producer p owns shared-memory stage p, i.e. K-tiles p, p+8, ...  Lane 0 arms full[stage] with the byte count of the
 //              weight tile and issues ONE TMA bulk copy (cp.async.bulk) of the pre-packed W_hi|W_lo operand tile (the
 //              weights are static, so the host packs them once in the exact shared-memory operand layout,
 //              spk_tc_pack_weight); all lanes load the A tile with coalesced 128-bit loads (optional backward prologue
@@ -35,7 +35,8 @@ constexpr int TM = 128;                        // rows per CTA tile (UMMA M)
 constexpr int TN = 64;                         // columns per CTA tile (UMMA N)
 constexpr int TK = 16;                         // floats per K-tile = 2 UMMA k-steps
 constexpr int NST = 8;                         // shared-memory stages
-constexpr int NPROD = 11;                      // producer warps
+constexpr int NPROD = NST;                     // producer warps: warp p owns stage p, so the uses of a stage are strictly
+                                               // ordered (a parity wait cannot tell phase u from phase u+2)
 constexpr int PLANE_A = (TM / 8) * 128 + 16;   // bytes between consecutive 16 B K-chunks of the A tile (LBO), padded
 constexpr int PLANE_B = (TN / 8) * 128 + 16;   // same for the weight tile
 constexpr int OPER_A = (TK / 4) * PLANE_A;     // 8256 B
