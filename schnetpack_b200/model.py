@@ -209,3 +209,60 @@ def batch_to_device(batch: dict, device, pin: bool = False) -> Dict[str, torch.T
             t = t.pin_memory()
         out[k] = t.to(device, non_blocking=pin)
     return out
+
+
+class GraphedPotential:
+    """CUDA-graph replay of a whole ``model(inputs)`` evaluation (energy, forces, graph-view build included) for a fixed
+    problem shape -- SURVEY.md §8 f2.  The first call with a new shape signature (tensor shapes/dtypes of the batch) runs
+    two eager warm-ups and captures the evaluation on a side stream into static buffers; later calls copy the batch into
+    those buffers (``copy_``, asynchronous from pinned host memory), replay the graph and return the static outputs.
+
+    Everything inside the model is capture-safe: the C-ABI calls only enqueue on the current stream, the receiver/sender
+    views are rebuilt by captured kernels from the *current contents* of ``_idx_i/_idx_j`` on every replay, and no host
+    synchronisation happens on the path (``_n_atoms`` supplies the number of systems).
+    """
+
+    def __init__(self, model: nn.Module, warmup: int = 2):
+        self.model = model
+        self.warmup = warmup
+        self._cache = {}
+
+    @staticmethod
+    def _signature(inputs: Dict[str, torch.Tensor]):
+        return tuple(sorted((k, tuple(v.shape), str(v.dtype)) for k, v in inputs.items()))
+
+    def _capture(self, inputs: Dict[str, torch.Tensor]):
+        from . import ops
+
+        dev = next(self.model.parameters()).device
+        static_in = {k: v.detach().to(dev, copy=True) for k, v in inputs.items()}   # host (pinned) or device batches
+
+        def run():
+            ops._GRAPH_CACHE.clear()                 # the CSR/sender-view build must be part of the captured work
+            # hand the model views of the static buffers: it marks positions as requiring grad, the buffers stay plain
+            x = {k: (v.detach() if v.is_floating_point() else v) for k, v in static_in.items()}
+            return self.model(x)
+
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(self.warmup):
+                run()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = run()
+        static_out = {k: v.detach() for k, v in out.items()}
+        return graph, static_in, static_out
+
+    def __call__(self, inputs: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        sig = self._signature(inputs)
+        entry = self._cache.get(sig)
+        if entry is None:
+            entry = self._capture(inputs)
+            self._cache[sig] = entry
+        graph, static_in, static_out = entry
+        for k, v in inputs.items():
+            static_in[k].copy_(v, non_blocking=True)
+        graph.replay()
+        return static_out

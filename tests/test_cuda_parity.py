@@ -177,3 +177,35 @@ def test_finite_difference_forces():
         ep["_positions"] = rp; em["_positions"] = rm
         fd = -(_run_cuda(spec, params, ep)["energy"].sum() - _run_cuda(spec, params, em)["energy"].sum()) / (2 * h)
         assert abs(fd - base["forces"][atom, comp]) < 2e-2 * max(1.0, abs(base["forces"][atom, comp]))
+
+
+def test_cuda_graph_replay_matches_eager_and_tracks_new_inputs():
+    """GraphedPotential: replayed results equal the eager ones, and a replay with NEW positions / a re-ordered neighbour
+    list (same shapes) gives the results of those new inputs (the CSR build is part of the captured graph)."""
+    from oracle import spk_oracle as O
+    from schnetpack_b200 import synthetic as S
+    from schnetpack_b200.model import GraphedPotential, batch_to_device, from_spec
+
+    dev = torch.device("cuda:0")
+    spec, a = S.make_config("cfg2", batch=6)
+    params = S.init_params(spec, seed=4)
+    model = from_spec(spec, params, dev)
+    gp = GraphedPotential(model)
+    xa = batch_to_device(a, dev)
+    out1 = {k: v.clone() for k, v in gp(xa).items()}
+    eager = model(batch_to_device(a, dev))
+    assert rel_err(out1["energy"].cpu().numpy(), eager["energy"].detach().cpu().numpy()) < 1e-6
+    assert rel_err(out1["forces"].cpu().numpy(), eager["forces"].detach().cpu().numpy()) < 1e-6
+    # second batch: same shapes, different geometry and a permuted (unsorted) edge list
+    _, b = S.make_config("cfg2", batch=6)
+    rng = np.random.default_rng(5)
+    b = dict(b)
+    b["_positions"] = (a["_positions"] + rng.normal(0, 0.02, a["_positions"].shape)).astype(np.float32)
+    perm = rng.permutation(a["_idx_i"].shape[0])
+    for k in ("_idx_i", "_idx_j", "_offsets"):
+        b[k] = a[k][perm]
+    out2 = {k: v.clone() for k, v in gp(batch_to_device(b, dev)).items()}
+    ref = O.energy_forces(spec, params, b, dtype=torch.float64)
+    assert rel_err(out2["energy"].cpu().numpy(), ref["energy"].numpy()) < TOL
+    assert rel_err(out2["forces"].cpu().numpy(), ref["forces"].numpy()) < TOL
+    assert len(gp._cache) == 1
