@@ -39,6 +39,8 @@ typedef void* spk_stream_t; /* cudaStream_t */
 #define SPK_RBF_BESSEL 1   /* nn/radial.py:82-110 */
 
 #define SPK_GEO_STRIDE 8 /* floats per edge in the geometry record: ux uy uz d fc dfc/dd 1/d 0 */
+#define SPK_NRB(n_rbf) ((n_rbf) <= 20 ? 20 : 32)          /* radial-basis capacity of the compiled edge kernels */
+#define SPK_REC(n_rbf) (2 * SPK_NRB(n_rbf) + SPK_GEO_STRIDE) /* floats of the combined per-slot record */
 
 int spk_version(void);
 
@@ -72,10 +74,12 @@ int spk_pairwise_fwd(const float* R, const int64_t* idx_i, const int64_t* idx_j,
 int spk_pairwise_bwd(const float* g_rij, const int32_t* rowptr, const int32_t* slot_eid, const int32_t* sptr,
                      const int32_t* pos_slot, int64_t n_atoms, float sign, float* g_R, spk_stream_t stream);
 /* per CSR slot s (edge slot_eid[s]): phi[s,0:n_rbf] radial basis (zero padded to KP), dphi = d phi/dd,
- * geo[s] = (ux, uy, uz, d, fc, dfc/dd, 1/d, 0).  rbf_p0/p1 = offsets/widths (gaussian) or freqs/NULL (bessel). */
+ * geo[s] = (ux, uy, uz, d, fc, dfc/dd, 1/d, 0).  rbf_p0/p1 = offsets/widths (gaussian) or freqs/NULL (bessel).
+ * erec (nullable): the same data as ONE record per slot, [E, SPK_REC(n_rbf)] = [phi (SPK_NRB, zero padded) | dphi | geo],
+ * so that the reverse edge kernel stages a slot with a single TMA bulk copy. */
 int spk_edge_geometry(const float* r_ij, const int32_t* slot_eid, int64_t n_edges, int rbf_kind, int n_rbf,
                       const float* rbf_p0, const float* rbf_p1, float cutoff, float* phi, float* dphi, float* geo,
-                      spk_stream_t stream);
+                      float* erec, spk_stream_t stream);
 /* standalone radial basis / cutoff / activation (nn.GaussianRBF, nn.BesselRBF, nn.CosineCutoff, shifted_softplus
  * forward + derivative, used by the nn.* module mirrors).  d: [n]; out: [n, n_rbf]; dout nullable */
 int spk_rbf_fwd(const float* d, int64_t n, int rbf_kind, int n_rbf, const float* rbf_p0, const float* rbf_p1,
@@ -131,7 +135,8 @@ int spk_painn_edge_fwd(const float* x, const float* mu, const float* q, const fl
  *   g_rij[eid] (+)= dE/dr_ij through d (phi, fc) and u                           [E,3]   (accumulate != 0 -> +=)
  * The residual dE/dq_in = g_q is the caller's (identity).  */
 int spk_painn_edge_bwd(const float* x, const float* mu, const float* g_q, const float* g_mu, const float* phi,
-                       const float* dphi, const float* geo, const int32_t* sptr, const int32_t* pos_slot,
+                       const float* dphi, const float* geo, const float* erec /* nullable, see spk_edge_geometry */,
+                       const int32_t* sptr, const int32_t* pos_slot,
                        const int32_t* pos_i, const int32_t* slot_eid, const float* wf, const float* bf,
                        int64_t n_atoms, int64_t n_edges, int F, int n_rbf, float* g_x, float* g_mu_in, float* g_rij,
                        int accumulate, spk_stream_t stream);

@@ -27,7 +27,7 @@ SIGNATURES = {
     "spk_segment_ptr": [P, c_int64, c_int64, P, P],
     "spk_pairwise_fwd": [P, P, P, P, c_int64, P, P],
     "spk_pairwise_bwd": [P, P, P, P, P, c_int64, c_float, P, P],
-    "spk_edge_geometry": [P, P, c_int64, c_int, c_int, P, P, c_float, P, P, P, P],
+    "spk_edge_geometry": [P, P, c_int64, c_int, c_int, P, P, c_float, P, P, P, P, P],
     "spk_rbf_fwd": [P, c_int64, c_int, c_int, P, P, P, P, P],
     "spk_cosine_cutoff_fwd": [P, c_int64, c_float, P, P, P],
     "spk_act_fwd": [P, c_int64, c_int, P, P, P],
@@ -38,7 +38,7 @@ SIGNATURES = {
     "spk_tc_pack_weight": [P, c_int, c_int, P, P],
     "spk_dense_tc": [P, c_int64, c_int, c_int64, P, c_int, P, c_int, P, c_int, P, c_int64, P, c_int64, P, P],
     "spk_painn_edge_fwd": [P, P, P, P, P, P, P, P, P, c_int64, c_int64, c_int, c_int, P, P, P],
-    "spk_painn_edge_bwd": [P, P, P, P, P, P, P, P, P, P, P, P, P, c_int64, c_int64, c_int, c_int, P, P, P, c_int, P],
+    "spk_painn_edge_bwd": [P, P, P, P, P, P, P, P, P, P, P, P, P, P, c_int64, c_int64, c_int, c_int, P, P, P, c_int, P],
     "spk_painn_mix_ctx": [P, P, c_int64, c_int, c_float, P, P],
     "spk_painn_mix_update": [P, P, P, P, c_int64, c_int, P, P, P],
     "spk_painn_mix_update_bwd": [P, P, P, P, c_int64, c_int, P, P, P],

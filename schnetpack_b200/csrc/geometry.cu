@@ -70,7 +70,8 @@ __global__ void k_pairwise_bwd(const float* __restrict__ g, const int* __restric
 // one thread per slot computes the geometry record, then KP threads-worth of radial values are produced by a loop
 __global__ void k_edge_geometry(const float* __restrict__ r_ij, const int* __restrict__ slot_eid, int64_t n_edges,
                                 int kind, int n_rbf, int KP, const float* __restrict__ p0, const float* __restrict__ p1,
-                                float rc, float* __restrict__ phi, float* __restrict__ dphi, float* __restrict__ geo) {
+                                float rc, float* __restrict__ phi, float* __restrict__ dphi, float* __restrict__ geo,
+                                float* __restrict__ erec, int NRB) {
     // thread (s, k): k in [0, KP)
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= n_edges * KP) return;
@@ -83,6 +84,17 @@ __global__ void k_edge_geometry(const float* __restrict__ r_ij, const int* __res
     if (k < n_rbf) rbf_eval(kind, d, p0[k], p1 ? p1[k] : 0.0f, v, dv);
     phi[t] = v;
     if (dphi) dphi[t] = dv;
+    const int REC = 2 * NRB + SPK_GEO_STRIDE;
+    if (erec) {   // combined per-slot record [phi (NRB, zero padded) | dphi (NRB) | geo (8)]
+        float* rec = erec + s * REC;
+        rec[k] = v;
+        rec[NRB + k] = dv;
+        if (k == 0)
+            for (int kk = KP; kk < NRB; ++kk) {
+                rec[kk] = 0.f;
+                rec[NRB + kk] = 0.f;
+            }
+    }
     if (k == 0) {
         float fc, dfc;
         cutoff_eval(d, rc, fc, dfc);
@@ -92,6 +104,11 @@ __global__ void k_edge_geometry(const float* __restrict__ r_ij, const int* __res
         float4* gp = reinterpret_cast<float4*>(geo + s * SPK_GEO_STRIDE);
         gp[0] = g0;
         gp[1] = g1;
+        if (erec) {
+            float4* rp = reinterpret_cast<float4*>(erec + s * REC + 2 * NRB);
+            rp[0] = g0;
+            rp[1] = g1;
+        }
     }
 }
 
@@ -184,7 +201,7 @@ extern "C" int spk_pairwise_bwd(const float* g_rij, const int32_t* rowptr, const
 
 extern "C" int spk_edge_geometry(const float* r_ij, const int32_t* slot_eid, int64_t n_edges, int rbf_kind, int n_rbf,
                                  const float* rbf_p0, const float* rbf_p1, float cutoff, float* phi, float* dphi,
-                                 float* geo, spk_stream_t stream) {
+                                 float* geo, float* erec, spk_stream_t stream) {
     if (n_edges < 0 || n_rbf <= 0) return SPK_ERR_ARG;
     if (n_rbf > 32) return SPK_ERR_UNSUPPORTED;
     if (rbf_kind != SPK_RBF_GAUSSIAN && rbf_kind != SPK_RBF_BESSEL) return SPK_ERR_ARG;
@@ -193,7 +210,7 @@ extern "C" int spk_edge_geometry(const float* r_ij, const int32_t* slot_eid, int
     if (rbf_kind == SPK_RBF_GAUSSIAN && !rbf_p1) return SPK_ERR_ARG;
     int KP = spk_kp(n_rbf);
     k_edge_geometry<<<GRID1D(n_edges * KP, 256)>>>(r_ij, slot_eid, n_edges, rbf_kind, n_rbf, KP, rbf_p0, rbf_p1,
-                                                   cutoff, phi, dphi, geo);
+                                                   cutoff, phi, dphi, geo, erec, SPK_NRB(n_rbf));
     SPK_LAUNCH_CHECK();
     return SPK_OK;
 }

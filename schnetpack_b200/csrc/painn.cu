@@ -505,12 +505,12 @@ int launch_edge_bwd(const float* x, const float* mu, const float* g_q, const flo
     return 0;
 }
 
-// one-time choice of the edge-kernel variant via SPK_B200_EDGE: "ldg" (this file; default) or "tma" (painn_tma.cu)
+// one-time choice of the edge-kernel variant via SPK_B200_EDGE: "tma" (painn_tma.cu; default) or "ldg" (this file)
 bool use_tma_variant() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("SPK_B200_EDGE");
-        v = (e && e[0] == 't') ? 1 : 0;
+        v = (e && e[0] == 'l') ? 0 : 1;
     }
     return v == 1;
 }
@@ -523,8 +523,8 @@ int spk_launch_edge_fwd_tma(const float* x, const float* mu, const float* q, con
                             const int* rowptr, const int* slot_j, const float* wf, const float* bf, int n_atoms,
                             int n_edges, int n_rbf, float* q_out, float* mu_out, cudaStream_t st);
 template <int NW, int NRB>
-int spk_launch_edge_bwd_tma(const float* x, const float* mu, const float* g_q, const float* g_mu, const float* phi,
-                            const float* dphi, const float* geo, const int* sptr, const int* pos_slot, const int* pos_i,
+int spk_launch_edge_bwd_tma(const float* x, const float* mu, const float* g_q, const float* g_mu, const float* erec,
+                            const int* sptr, const int* pos_slot, const int* pos_i,
                             const int* slot_eid, const float* wf, const float* bf, int n_atoms, int n_edges, int n_rbf,
                             float* g_x, float* g_mu_in, float* g_rij, int accumulate, cudaStream_t st);
 
@@ -554,7 +554,8 @@ extern "C" int spk_painn_edge_fwd(const float* x, const float* mu, const float* 
     if (mu && mu == mu_out) return SPK_ERR_ARG;
     cudaStream_t st = spk_st(stream);
     // the TMA variant needs 16 B-aligned rows (true for every torch allocation; F % 32 == 0 keeps row strides aligned)
-    const bool tma = use_tma_variant() && n_edges > 0 && aligned16(x) && aligned16(mu) && aligned16(phi) && aligned16(geo);
+    const bool tma = use_tma_variant() && n_edges > 0 && aligned16(x) && aligned16(mu) && aligned16(phi) && aligned16(geo) &&
+                     spk_kp(n_rbf) == SPK_NRB(n_rbf);   // chunked radial-basis rows need an unpadded [E, NRB] array
 #define CALL_FWD(NW, NRB)                                                                                              \
     (tma ? spk_launch_edge_fwd_tma<NW, NRB>(x, mu, q, phi, geo, rowptr, slot_j, wf, bf, (int)n_atoms, (int)n_edges,    \
                                             n_rbf, q_out, mu_out, st)                                                  \
@@ -567,7 +568,8 @@ extern "C" int spk_painn_edge_fwd(const float* x, const float* mu, const float* 
 }
 
 extern "C" int spk_painn_edge_bwd(const float* x, const float* mu, const float* g_q, const float* g_mu,
-                                  const float* phi, const float* dphi, const float* geo, const int32_t* sptr,
+                                  const float* phi, const float* dphi, const float* geo, const float* erec,
+                                  const int32_t* sptr,
                                   const int32_t* pos_slot, const int32_t* pos_i, const int32_t* slot_eid,
                                   const float* wf, const float* bf, int64_t n_atoms, int64_t n_edges, int F, int n_rbf,
                                   float* g_x, float* g_mu_in, float* g_rij, int accumulate, spk_stream_t stream) {
@@ -578,10 +580,9 @@ extern "C" int spk_painn_edge_bwd(const float* x, const float* mu, const float* 
     if (mu && !g_mu_in) return SPK_ERR_ARG;
     if (n_edges > 0 && (!phi || !dphi || !geo || !pos_slot || !pos_i || !slot_eid || !g_rij)) return SPK_ERR_ARG;
     cudaStream_t st = spk_st(stream);
-    const bool tma = use_tma_variant() && n_edges > 0 && aligned16(g_q) && aligned16(g_mu) && aligned16(phi) &&
-                     aligned16(dphi) && aligned16(geo);
+    const bool tma = use_tma_variant() && n_edges > 0 && erec && aligned16(g_q) && aligned16(g_mu) && aligned16(erec);
 #define CALL_BWD(NW, NRB)                                                                                               \
-    (tma ? spk_launch_edge_bwd_tma<NW, NRB>(x, mu, g_q, g_mu, phi, dphi, geo, sptr, pos_slot, pos_i, slot_eid, wf, bf,  \
+    (tma ? spk_launch_edge_bwd_tma<NW, NRB>(x, mu, g_q, g_mu, erec, sptr, pos_slot, pos_i, slot_eid, wf, bf,            \
                                             (int)n_atoms, (int)n_edges, n_rbf, g_x, g_mu_in, g_rij, accumulate, st)     \
          : launch_edge_bwd<NW, NRB>(x, mu, g_q, g_mu, phi, dphi, geo, sptr, pos_slot, pos_i, slot_eid, wf, bf,          \
                                     (int)n_atoms, (int)n_edges, n_rbf, g_x, g_mu_in, g_rij, accumulate, st))

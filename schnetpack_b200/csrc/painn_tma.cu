@@ -19,6 +19,7 @@ namespace {
 
 constexpr int DEPTH = 8;     // ring stages = edges in flight per CTA
 constexpr int RCH = 32;      // reverse kernel: edges per cross-warp reduction chunk
+constexpr int FCH = 32;      // forward kernel: slots per radial-basis/geometry chunk stage
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -56,12 +57,15 @@ __device__ __forceinline__ void consumer_bar(int nthreads) {
 // ------------------------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------------------------
-template <int F, int NRB, bool HAS_MU>
-struct FwdStage {
+template <int F, bool HAS_MU>
+struct FwdStage {                 // per-edge ring stage: the sender's rows
     float x[3 * F];
     float mu[HAS_MU ? 3 * F : 4];
-    float phi[NRB];
-    float geo[SPK_GEO_STRIDE];
+};
+template <int NRB>
+struct FwdChunk {                 // per-chunk stage: radial basis and geometry records of FCH consecutive slots
+    float phi[FCH * NRB];
+    float geo[FCH * SPK_GEO_STRIDE];
 };
 
 template <int NW, int NRB, bool HAS_MU>
@@ -71,11 +75,15 @@ __global__ void __launch_bounds__((NW + 1) * 32) k_painn_edge_fwd_tma(
     const int* __restrict__ slot_j, const float* __restrict__ wf, const float* __restrict__ bf, int n_atoms,
     int n_edges, int n_rbf, float* __restrict__ q_out, float* __restrict__ mu_out) {
     constexpr int F = NW * 32;
-    using Stage = FwdStage<F, NRB, HAS_MU>;
+    using Stage = FwdStage<F, HAS_MU>;
+    using Chunk = FwdChunk<NRB>;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     Stage* stages = reinterpret_cast<Stage*>(smem_raw);
+    Chunk* chunks = reinterpret_cast<Chunk*>(smem_raw + DEPTH * sizeof(Stage));
     __shared__ __align__(8) uint64_t full_bar[DEPTH];
     __shared__ __align__(8) uint64_t empty_bar[DEPTH];
+    __shared__ __align__(8) uint64_t cfull_bar[2];
+    __shared__ __align__(8) uint64_t cempty_bar[2];
 
     const int tid = threadIdx.x;
     const int nb = gridDim.x, b = blockIdx.x;
@@ -92,33 +100,42 @@ __global__ void __launch_bounds__((NW + 1) * 32) k_painn_edge_fwd_tma(
             mbar_init(&full_bar[d], 1);
             mbar_init(&empty_bar[d], NW);
         }
+        mbar_init(&cfull_bar[0], 1);
+        mbar_init(&cfull_bar[1], 1);
+        mbar_init(&cempty_bar[0], NW);
+        mbar_init(&cempty_bar[1], NW);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // zero the radial-basis padding once (TMA writes only the first KP floats of a row)
-    for (int t = tid; t < DEPTH * NRB; t += (NW + 1) * 32) stages[t / NRB].phi[t % NRB] = 0.f;
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
 
     if (tid >= F) {
         // ===================== producer warp =====================
+        // 2 bulk copies per edge (x[j], mu[j]) + 2 per chunk of FCH slots (phi rows, geo records; KP == NRB required)
         const int lane = tid - F;
         const uint32_t x_bytes = (HAS_MU ? 3 : 2) * F * 4;
-        const uint32_t bytes = x_bytes + (HAS_MU ? 3 * F * 4 : 0) + KP * 4 + SPK_GEO_STRIDE * 4;
+        const uint32_t e_bytes = x_bytes + (HAS_MU ? 3 * F * 4 : 0);
         for (int e0 = 0; e0 < n_e; e0 += 32) {
             const int jv = (e0 + lane < n_e) ? slot_j[s_begin + e0 + lane] : 0;
             const int cnt = min(32, n_e - e0);
             for (int l = 0; l < cnt; ++l) {
                 const int j = __shfl_sync(0xffffffffu, jv, l);
                 if (lane == 0) {
-                    const int e = e0 + l, st = e % DEPTH, k = e / DEPTH;
+                    const int e = e0 + l;
+                    if (e % FCH == 0) {   // stage the records of chunk e / FCH
+                        const int ck = e / FCH, cb = ck & 1;
+                        if (ck >= 2) mbar_wait(&cempty_bar[cb], ((ck >> 1) - 1) & 1);
+                        const int cn = min(FCH, n_e - e);
+                        const int64_t s0 = s_begin + e;
+                        mbar_expect_tx(&cfull_bar[cb], (uint32_t)cn * (NRB + SPK_GEO_STRIDE) * 4);
+                        tma_load(chunks[cb].phi, phi + s0 * KP, (uint32_t)cn * NRB * 4, &cfull_bar[cb]);
+                        tma_load(chunks[cb].geo, geo + s0 * SPK_GEO_STRIDE, (uint32_t)cn * SPK_GEO_STRIDE * 4, &cfull_bar[cb]);
+                    }
+                    const int st = e % DEPTH, k = e / DEPTH;
                     if (k >= 1) mbar_wait(&empty_bar[st], (k - 1) & 1);
                     Stage& S = stages[st];
-                    const int64_t s = s_begin + e;
-                    mbar_expect_tx(&full_bar[st], bytes);
+                    mbar_expect_tx(&full_bar[st], e_bytes);
                     tma_load(S.x, x + (size_t)j * (3 * F), x_bytes, &full_bar[st]);
                     if (HAS_MU) tma_load(S.mu, mu + (size_t)j * (3 * F), 3 * F * 4, &full_bar[st]);
-                    tma_load(S.phi, phi + s * KP, KP * 4, &full_bar[st]);
-                    tma_load(S.geo, geo + s * SPK_GEO_STRIDE, SPK_GEO_STRIDE * 4, &full_bar[st]);
                 }
             }
         }
@@ -161,9 +178,12 @@ __global__ void __launch_bounds__((NW + 1) * 32) k_painn_edge_fwd_tma(
     for (int e = 0; e < n_e; ++e) {
         const int s = s_begin + e;
         const int st = e % DEPTH;
+        const int ck = e / FCH, cb = ck & 1, t = e - ck * FCH;
         while (s >= next_boundary) flush_advance();
+        if (t == 0) mbar_wait(&cfull_bar[cb], (ck >> 1) & 1);
         mbar_wait(&full_bar[st], (e / DEPTH) & 1);
         const Stage& S = stages[st];
+        const Chunk& C = chunks[cb];
         const float xa = S.x[c], xb = S.x[F + c];
         float xc = 0.f, m0 = 0.f, m1 = 0.f, m2 = 0.f;
         if (HAS_MU) {
@@ -172,10 +192,13 @@ __global__ void __launch_bounds__((NW + 1) * 32) k_painn_edge_fwd_tma(
             m1 = S.mu[F + c];
             m2 = S.mu[2 * F + c];
         }
-        const float4 g0 = *reinterpret_cast<const float4*>(S.geo);      // ux uy uz d
-        const float fc = S.geo[4];
+        // the sender rows are in registers: hand the ring stage back to the producer
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[st]);
+        const float4 g0 = *reinterpret_cast<const float4*>(C.geo + t * SPK_GEO_STRIDE);      // ux uy uz d
+        const float fc = C.geo[t * SPK_GEO_STRIDE + 4];
         float2 pa2 = make_float2(w.ba, 0.f), pb2 = make_float2(w.bb, 0.f), pc2 = make_float2(w.bc, 0.f);
-        const float4* __restrict__ ph = reinterpret_cast<const float4*>(S.phi);
+        const float4* __restrict__ ph = reinterpret_cast<const float4*>(C.phi + t * NRB);
 #pragma unroll
         for (int k4 = 0; k4 < NRB / 4; ++k4) {
             const float4 p = ph[k4];
@@ -189,9 +212,10 @@ __global__ void __launch_bounds__((NW + 1) * 32) k_painn_edge_fwd_tma(
                 pc2 = __ffma2_rn(p23, w.c[2 * k4 + 1], pc2);
             }
         }
-        // every shared-memory read of this stage is done: hand it back to the producer
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[st]);
+        if (t == FCH - 1 || e == n_e - 1) {     // last edge of the chunk: release the chunk stage
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&cempty_bar[cb]);
+        }
         const float pa = pa2.x + pa2.y, pb = pb2.x + pb2.y, pc = pc2.x + pc2.y;
         dq = fmaf(fc * pa, xa, dq);
         const float tb = fc * pb * xb;
@@ -215,7 +239,7 @@ template <int F, int NRB>
 struct BwdStage {
     float gq[F];
     float gmu[3 * F];
-    float phi[NRB];
+    float phi[NRB];                  // the combined per-slot record [phi | dphi | geo] lands here with ONE bulk copy
     float dphi[NRB];
     float geo[SPK_GEO_STRIDE];
 };
@@ -223,12 +247,12 @@ struct BwdStage {
 template <int NW, int NRB, bool HAS_MU>
 __global__ void __launch_bounds__((NW + 1) * 32) k_painn_edge_bwd_tma(
     const float* __restrict__ x, const float* __restrict__ mu, const float* __restrict__ g_q,
-    const float* __restrict__ g_mu, const float* __restrict__ phi, const float* __restrict__ dphi,
-    const float* __restrict__ geo, const int* __restrict__ sptr, const int* __restrict__ pos_slot,
-    const int* __restrict__ pos_i, const int* __restrict__ slot_eid, const float* __restrict__ wf,
-    const float* __restrict__ bf, int n_atoms, int n_edges, int n_rbf, float* __restrict__ g_x,
-    float* __restrict__ g_mu_in, float* __restrict__ g_rij, int accumulate) {
+    const float* __restrict__ g_mu, const float* __restrict__ erec, const int* __restrict__ sptr,
+    const int* __restrict__ pos_slot, const int* __restrict__ pos_i, const int* __restrict__ slot_eid,
+    const float* __restrict__ wf, const float* __restrict__ bf, int n_atoms, int n_edges, int n_rbf,
+    float* __restrict__ g_x, float* __restrict__ g_mu_in, float* __restrict__ g_rij, int accumulate) {
     constexpr int F = NW * 32;
+    constexpr int REC = 2 * NRB + SPK_GEO_STRIDE;
     using Stage = BwdStage<F, NRB>;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     Stage* stages = reinterpret_cast<Stage*>(smem_raw);
@@ -244,7 +268,6 @@ __global__ void __launch_bounds__((NW + 1) * 32) k_painn_edge_bwd_tma(
     if (j_lo >= j_hi) return;
     const int p_begin = sptr[j_lo], p_end = sptr[j_hi];
     const int n_e = p_end - p_begin;
-    const int KP = spk_kp(n_rbf);
 
     if (tid == 0) {
 #pragma unroll
@@ -254,17 +277,12 @@ __global__ void __launch_bounds__((NW + 1) * 32) k_painn_edge_bwd_tma(
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int t = tid; t < DEPTH * NRB; t += (NW + 1) * 32) {
-        stages[t / NRB].phi[t % NRB] = 0.f;
-        stages[t / NRB].dphi[t % NRB] = 0.f;
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
 
     if (tid >= F) {
         // ===================== producer warp =====================
         const int lane = tid - F;
-        const uint32_t bytes = F * 4 + 3 * F * 4 + 2 * KP * 4 + SPK_GEO_STRIDE * 4;
+        const uint32_t bytes = F * 4 + 3 * F * 4 + REC * 4;
         for (int e0 = 0; e0 < n_e; e0 += 32) {
             const bool ok = e0 + lane < n_e;
             const int iv = ok ? pos_i[p_begin + e0 + lane] : 0;
@@ -280,9 +298,7 @@ __global__ void __launch_bounds__((NW + 1) * 32) k_painn_edge_bwd_tma(
                     mbar_expect_tx(&full_bar[st], bytes);
                     tma_load(S.gq, g_q + (size_t)i * F, F * 4, &full_bar[st]);
                     tma_load(S.gmu, g_mu + (size_t)i * (3 * F), 3 * F * 4, &full_bar[st]);
-                    tma_load(S.phi, phi + s * KP, KP * 4, &full_bar[st]);
-                    tma_load(S.dphi, dphi + s * KP, KP * 4, &full_bar[st]);
-                    tma_load(S.geo, geo + s * SPK_GEO_STRIDE, SPK_GEO_STRIDE * 4, &full_bar[st]);
+                    tma_load(S.phi, erec + s * REC, REC * 4, &full_bar[st]);
                 }
             }
         }
@@ -458,13 +474,14 @@ int spk_launch_edge_fwd_tma(const float* x, const float* mu, const float* q, con
                             int n_edges, int n_rbf, float* q_out, float* mu_out, cudaStream_t st) {
     constexpr int F = NW * 32, T = (NW + 1) * 32;
     static int occ_mu = 0, occ_nomu = 0;
+    if (spk_kp(n_rbf) != NRB) return -1;   // chunked phi rows need KP == NRB (n_rbf in 17..20 or 29..32): caller uses LDG
     if (mu) {
-        const size_t sm = DEPTH * sizeof(FwdStage<F, NRB, true>);
+        const size_t sm = DEPTH * sizeof(FwdStage<F, true>) + 2 * sizeof(FwdChunk<NRB>);
         int nb = single_wave_grid(k_painn_edge_fwd_tma<NW, NRB, true>, T, sm, n_atoms, n_edges, &occ_mu);
         k_painn_edge_fwd_tma<NW, NRB, true><<<nb, T, sm, st>>>(x, mu, q, phi, geo, rowptr, slot_j, wf, bf, n_atoms,
                                                                n_edges, n_rbf, q_out, mu_out);
     } else {
-        const size_t sm = DEPTH * sizeof(FwdStage<F, NRB, false>);
+        const size_t sm = DEPTH * sizeof(FwdStage<F, false>) + 2 * sizeof(FwdChunk<NRB>);
         int nb = single_wave_grid(k_painn_edge_fwd_tma<NW, NRB, false>, T, sm, n_atoms, n_edges, &occ_nomu);
         k_painn_edge_fwd_tma<NW, NRB, false><<<nb, T, sm, st>>>(x, mu, q, phi, geo, rowptr, slot_j, wf, bf, n_atoms,
                                                                 n_edges, n_rbf, q_out, mu_out);
@@ -473,8 +490,8 @@ int spk_launch_edge_fwd_tma(const float* x, const float* mu, const float* q, con
 }
 
 template <int NW, int NRB>
-int spk_launch_edge_bwd_tma(const float* x, const float* mu, const float* g_q, const float* g_mu, const float* phi,
-                            const float* dphi, const float* geo, const int* sptr, const int* pos_slot, const int* pos_i,
+int spk_launch_edge_bwd_tma(const float* x, const float* mu, const float* g_q, const float* g_mu, const float* erec,
+                            const int* sptr, const int* pos_slot, const int* pos_i,
                             const int* slot_eid, const float* wf, const float* bf, int n_atoms, int n_edges, int n_rbf,
                             float* g_x, float* g_mu_in, float* g_rij, int accumulate, cudaStream_t st) {
     constexpr int F = NW * 32, T = (NW + 1) * 32;
@@ -482,12 +499,12 @@ int spk_launch_edge_bwd_tma(const float* x, const float* mu, const float* g_q, c
     const size_t sm = DEPTH * sizeof(BwdStage<F, NRB>);
     if (mu) {
         int nb = single_wave_grid(k_painn_edge_bwd_tma<NW, NRB, true>, T, sm, n_atoms, n_edges, &occ_mu);
-        k_painn_edge_bwd_tma<NW, NRB, true><<<nb, T, sm, st>>>(x, mu, g_q, g_mu, phi, dphi, geo, sptr, pos_slot, pos_i,
+        k_painn_edge_bwd_tma<NW, NRB, true><<<nb, T, sm, st>>>(x, mu, g_q, g_mu, erec, sptr, pos_slot, pos_i,
                                                                slot_eid, wf, bf, n_atoms, n_edges, n_rbf, g_x, g_mu_in,
                                                                g_rij, accumulate);
     } else {
         int nb = single_wave_grid(k_painn_edge_bwd_tma<NW, NRB, false>, T, sm, n_atoms, n_edges, &occ_nomu);
-        k_painn_edge_bwd_tma<NW, NRB, false><<<nb, T, sm, st>>>(x, mu, g_q, g_mu, phi, dphi, geo, sptr, pos_slot, pos_i,
+        k_painn_edge_bwd_tma<NW, NRB, false><<<nb, T, sm, st>>>(x, mu, g_q, g_mu, erec, sptr, pos_slot, pos_i,
                                                                 slot_eid, wf, bf, n_atoms, n_edges, n_rbf, g_x, g_mu_in,
                                                                 g_rij, accumulate);
     }
@@ -500,7 +517,7 @@ int spk_launch_edge_bwd_tma(const float* x, const float* mu, const float* g_q, c
                                                   const int*, const int*, const float*, const float*, int, int, int,    \
                                                   float*, float*, cudaStream_t);                                        \
     template int spk_launch_edge_bwd_tma<NW, NRB>(const float*, const float*, const float*, const float*, const float*, \
-                                                  const float*, const float*, const int*, const int*, const int*,       \
+                                                  const int*, const int*, const int*,                                   \
                                                   const int*, const float*, const float*, int, int, int, float*, float*, \
                                                   float*, int, cudaStream_t);
 INST(1, 20) INST(2, 20) INST(4, 20) INST(8, 20) INST(1, 32) INST(2, 32) INST(4, 32) INST(8, 32)

@@ -80,7 +80,11 @@ def painn_forward(pk: PaiNNPack, q0: Tensor, r_ij: Tensor, graph: ops.EdgeGraph,
     """Returns q [N,F], mu [N,3,F] and the tape needed by painn_backward."""
     F = pk.F
     N = q0.shape[0]
-    phi, dphi, geo = ops.edge_geometry(r_ij, graph, rbf_kind, n_rbf, rbf_p0, rbf_p1, cutoff, need_grad)
+    if need_grad:
+        phi, dphi, geo, erec = ops.edge_geometry(r_ij, graph, rbf_kind, n_rbf, rbf_p0, rbf_p1, cutoff, True, want_rec=True)
+    else:
+        phi, dphi, geo = ops.edge_geometry(r_ij, graph, rbf_kind, n_rbf, rbf_p0, rbf_p1, cutoff, False)
+        erec = None
     q, mu = q0, None
     tape = []
     for t in range(pk.T):
@@ -96,14 +100,14 @@ def painn_forward(pk: PaiNNPack, q0: Tensor, r_ij: Tensor, graph: ops.EdgeGraph,
         if need_grad:
             tape.append((hpre, x, mu, VW, cpre, s))
         q, mu = q2, mu2
-    return q, mu, (phi, dphi, geo, tape)
+    return q, mu, (phi, dphi, geo, erec, tape)
 
 
 def painn_backward(pk: PaiNNPack, saved, graph: ops.EdgeGraph, n_rbf: int, act: int, g_q: Tensor,
                    g_mu: Optional[Tensor], n_edges_total: int) -> Tensor:
     """dE/dr_ij [E,3] (in the caller's edge order) from dE/dq [N,F], dE/dmu [N,3,F]."""
     F = pk.F
-    phi, dphi, geo, tape = saved
+    phi, dphi, geo, erec, tape = saved
     N = g_q.shape[0]
     dev = g_q.device
     g_rij = torch.empty((n_edges_total, 3), dtype=torch.float32, device=dev)
@@ -120,7 +124,7 @@ def painn_backward(pk: PaiNNPack, saved, graph: ops.EdgeGraph, n_rbf: int, act: 
         g_mu1 = b["mix"].bwd(g_VW.view(3 * N, 2 * F), addend=g_mu.view(3 * N, F)).view(N, 3, F)
         # --- interaction (painn.py:54-65) reversed
         g_x, g_mu0 = ops.painn_edge_bwd(x, mu_in, g_q1, g_mu1, phi, dphi, geo, graph, pk.wf[t], pk.bf[t], F, n_rbf,
-                                        g_rij, accumulate=(t != pk.T - 1))
+                                        g_rij, accumulate=(t != pk.T - 1), erec=erec)
         g_a = b["c1"].bwd(g_x)                                                               # [N,3F]x[3F,F]
         g_q = b["c0"].bwd(g_a, a_pre=hpre, a_act=act, addend=g_q1)                           # [N,F]x[F,F] + residual
         g_mu = g_mu0

@@ -134,8 +134,12 @@ def pairwise_bwd(g_rij: Tensor, graph: EdgeGraph, sign: float = 1.0) -> Tensor:
     return out
 
 
+def nrb(n_rbf: int) -> int:
+    return 20 if n_rbf <= 20 else 32
+
+
 def edge_geometry(r_ij: Tensor, graph: Optional[EdgeGraph], rbf_kind: int, n_rbf: int, p0: Tensor, p1: Optional[Tensor],
-                  cutoff: float, need_grad: bool = True):
+                  cutoff: float, need_grad: bool = True, want_rec: bool = False):
     f32(r_ij, "_Rij")
     E = r_ij.shape[0]
     KP = kp(n_rbf)
@@ -143,9 +147,12 @@ def edge_geometry(r_ij: Tensor, graph: Optional[EdgeGraph], rbf_kind: int, n_rbf
     phi = torch.empty((E, KP), dtype=torch.float32, device=dev)
     dphi = torch.empty((E, KP), dtype=torch.float32, device=dev) if need_grad else None
     geo = torch.empty((E, GEO_STRIDE), dtype=torch.float32, device=dev)
+    erec = torch.empty((E, 2 * nrb(n_rbf) + GEO_STRIDE), dtype=torch.float32, device=dev) if want_rec else None
     _lib.call("spk_edge_geometry", _p(r_ij), _p(graph.slot_eid) if graph is not None else None, E, rbf_kind, n_rbf,
               _p(f32(p0)), _p(f32(p1)) if p1 is not None else None, float(cutoff), _p(phi), _p(dphi), _p(geo),
-              _stream())
+              _p(erec), _stream())
+    if want_rec:
+        return phi, dphi, geo, erec
     return phi, dphi, geo
 
 
@@ -332,11 +339,11 @@ def painn_edge_fwd(x, mu, q, phi, geo, graph: EdgeGraph, wf, bf, F: int, n_rbf: 
 
 
 def painn_edge_bwd(x, mu, g_q, g_mu, phi, dphi, geo, graph: EdgeGraph, wf, bf, F: int, n_rbf: int, g_rij: Tensor,
-                   accumulate: bool):
+                   accumulate: bool, erec: Optional[Tensor] = None):
     N = graph.n_atoms
     g_x = torch.empty((N, 3 * F), dtype=torch.float32, device=x.device)
     g_mu_in = torch.empty((N, 3, F), dtype=torch.float32, device=x.device) if mu is not None else None
-    _lib.call("spk_painn_edge_bwd", _p(x), _p(mu), _p(g_q), _p(g_mu), _p(phi), _p(dphi), _p(geo), _p(graph.sptr),
+    _lib.call("spk_painn_edge_bwd", _p(x), _p(mu), _p(g_q), _p(g_mu), _p(phi), _p(dphi), _p(geo), _p(erec), _p(graph.sptr),
               _p(graph.pos_slot), _p(graph.pos_i), _p(graph.slot_eid), _p(wf), _p(bf), N, graph.n_edges, F, n_rbf,
               _p(g_x), _p(g_mu_in), _p(g_rij), 1 if accumulate else 0, _stream())
     return g_x, g_mu_in

@@ -230,7 +230,10 @@ def test_painn_edge_fwd_bwd(F, n_rbf, has_mu):
     q = torch.randn(N, F, device=DEV)
     wf = torch.randn(3 * F, n_rbf, device=DEV) * 0.3
     bf = torch.randn(3 * F, device=DEV) * 0.3
-    phi, dphi, geo = ops.edge_geometry(r, g, ops.RBF_GAUSSIAN, n_rbf, p0, p1, rc, True)
+    phi, dphi, geo, erec = ops.edge_geometry(r, g, ops.RBF_GAUSSIAN, n_rbf, p0, p1, rc, True, want_rec=True)
+    NRB = ops.nrb(n_rbf)
+    assert torch.equal(erec[:, :n_rbf], phi[:, :n_rbf]) and torch.equal(erec[:, NRB:NRB + n_rbf], dphi[:, :n_rbf])
+    assert torch.equal(erec[:, 2 * NRB:], geo) and float(erec[:, n_rbf:NRB].abs().max() if n_rbf < NRB else 0.0) == 0.0
     qo, muo = ops.painn_edge_fwd(x, mu, q, phi, geo, g, wf, bf, F, n_rbf)
     # fp64 reference + autograd
     x64, q64, r64 = x.double().requires_grad_(), q.double(), r.double().requires_grad_()
@@ -241,7 +244,12 @@ def test_painn_edge_fwd_bwd(F, n_rbf, has_mu):
     g_mu = torch.randn(N, 3, F, device=DEV)
     gx_r, gmu_r, gr_r = torch.autograd.grad((qr * g_q.double()).sum() + (mur * g_mu.double()).sum(), [x64, mu64, r64])
     g_rij = torch.full((r.shape[0], 3), 7.0, device=DEV)
-    g_x, g_mu_in = ops.painn_edge_bwd(x, mu, g_q, g_mu, phi, dphi, geo, g, wf, bf, F, n_rbf, g_rij, accumulate=False)
+    g_x, g_mu_in = ops.painn_edge_bwd(x, mu, g_q, g_mu, phi, dphi, geo, g, wf, bf, F, n_rbf, g_rij, accumulate=False,
+                                      erec=erec)
+    # the LDG variant (no combined record) must agree with the TMA variant
+    g_rij_b = torch.zeros_like(g_rij)
+    g_x_b, g_mu_b = ops.painn_edge_bwd(x, mu, g_q, g_mu, phi, dphi, geo, g, wf, bf, F, n_rbf, g_rij_b, accumulate=False)
+    assert rel(g_x_b, g_x) < 2e-6 and rel(g_rij_b, g_rij) < 5e-6
     if has_mu:
         assert rel(g_x, gx_r) < 5e-6
         assert rel(g_mu_in, gmu_r) < 5e-6
@@ -249,7 +257,7 @@ def test_painn_edge_fwd_bwd(F, n_rbf, has_mu):
         assert rel(g_x[:, : 2 * F], gx_r[:, : 2 * F]) < 5e-6 and float(g_x[:, 2 * F:].abs().max()) == 0.0
     assert rel(g_rij, gr_r) < 1e-5
     # accumulate=True adds on top
-    g_x2, _ = ops.painn_edge_bwd(x, mu, g_q, g_mu, phi, dphi, geo, g, wf, bf, F, n_rbf, g_rij, accumulate=True)
+    g_x2, _ = ops.painn_edge_bwd(x, mu, g_q, g_mu, phi, dphi, geo, g, wf, bf, F, n_rbf, g_rij, accumulate=True, erec=erec)
     assert rel(g_rij, 2 * gr_r) < 1e-5
 
 
