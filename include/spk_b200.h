@@ -140,6 +140,20 @@ int spk_painn_edge_bwd(const float* x, const float* mu, const float* g_q, const 
                        const int32_t* pos_i, const int32_t* slot_eid, const float* wf, const float* bf,
                        int64_t n_atoms, int64_t n_edges, int F, int n_rbf, float* g_x, float* g_mu_in, float* g_rij,
                        int accumulate, spk_stream_t stream);
+/* "System-resident" variants for batches of small systems (molecules): edges never cross systems
+ * (data/loader.py:35-46), so one CTA stages a system's sender rows in shared memory once and every gather is an LDS.
+ * mol_ptr[n_mol+1] = first atom of each system (spk_segment_ptr).  Systems larger than the shared-memory capacity chosen
+ * at launch (~1.1 x the average system size) use global gathers inside the same kernel; results are identical to the
+ * streaming kernels above. */
+int spk_painn_edge_fwd_sys(const float* x, const float* mu, const float* q, const float* phi, const float* geo,
+                           const int32_t* rowptr, const int32_t* slot_j, const float* wf, const float* bf,
+                           const int32_t* mol_ptr, int64_t n_mol, int64_t n_atoms, int64_t n_edges, int F, int n_rbf,
+                           float* q_out, float* mu_out, spk_stream_t stream);
+int spk_painn_edge_bwd_sys(const float* x, const float* mu, const float* g_q, const float* g_mu, const float* phi,
+                           const float* dphi, const float* geo, const int32_t* sptr, const int32_t* pos_slot,
+                           const int32_t* pos_i, const int32_t* slot_eid, const float* wf, const float* bf,
+                           const int32_t* mol_ptr, int64_t n_mol, int64_t n_atoms, int64_t n_edges, int F, int n_rbf,
+                           float* g_x, float* g_mu_in, float* g_rij, int accumulate, spk_stream_t stream);
 /* painn.py:104-107: ctx[a] = [ q[a] | sqrt(sum_d V[a,d]^2 + eps) ], VW = mu_channel_mix(mu) [N,3,2F] */
 int spk_painn_mix_ctx(const float* q, const float* VW, int64_t n_atoms, int F, float eps, float* ctx,
                       spk_stream_t stream);

@@ -39,6 +39,9 @@ SIGNATURES = {
     "spk_dense_tc": [P, c_int64, c_int, c_int64, P, c_int, P, c_int, P, c_int, P, c_int64, P, c_int64, P, P],
     "spk_painn_edge_fwd": [P, P, P, P, P, P, P, P, P, c_int64, c_int64, c_int, c_int, P, P, P],
     "spk_painn_edge_bwd": [P, P, P, P, P, P, P, P, P, P, P, P, P, P, c_int64, c_int64, c_int, c_int, P, P, P, c_int, P],
+    "spk_painn_edge_fwd_sys": [P, P, P, P, P, P, P, P, P, P, c_int64, c_int64, c_int64, c_int, c_int, P, P, P],
+    "spk_painn_edge_bwd_sys": [P, P, P, P, P, P, P, P, P, P, P, P, P, P, c_int64, c_int64, c_int64, c_int, c_int, P, P, P,
+                               c_int, P],
     "spk_painn_mix_ctx": [P, P, c_int64, c_int, c_float, P, P],
     "spk_painn_mix_update": [P, P, P, P, c_int64, c_int, P, P, P],
     "spk_painn_mix_update_bwd": [P, P, P, P, c_int64, c_int, P, P, P],

@@ -76,7 +76,8 @@ class PaiNNPack(ParamPack):
 
 
 def painn_forward(pk: PaiNNPack, q0: Tensor, r_ij: Tensor, graph: ops.EdgeGraph, rbf_kind: int, n_rbf: int,
-                  rbf_p0: Tensor, rbf_p1: Optional[Tensor], cutoff: float, act: int, need_grad: bool):
+                  rbf_p0: Tensor, rbf_p1: Optional[Tensor], cutoff: float, act: int, need_grad: bool,
+                  mol_ptr: Optional[Tensor] = None, n_mol: int = 0):
     """Returns q [N,F], mu [N,3,F] and the tape needed by painn_backward."""
     F = pk.F
     N = q0.shape[0]
@@ -91,7 +92,8 @@ def painn_forward(pk: PaiNNPack, q0: Tensor, r_ij: Tensor, graph: ops.EdgeGraph,
         b = pk.blocks[t]
         a, hpre = b["c0"].fwd(q, act, save_pre=True)                                         # painn.py:54
         x = b["c1"].fwd(a)
-        q1, mu1 = ops.painn_edge_fwd(x, mu, q, phi, geo, graph, pk.wf[t], pk.bf[t], F, n_rbf)   # :55-65
+        q1, mu1 = ops.painn_edge_fwd(x, mu, q, phi, geo, graph, pk.wf[t], pk.bf[t], F, n_rbf,   # :55-65
+                                     mol_ptr=mol_ptr, n_mol=n_mol)
         VW = b["mix"].fwd(mu1.view(3 * N, F))                                                # :103  [3N,2F]
         ctx = ops.painn_mix_ctx(q1, VW, F, pk.eps)                                           # :104-107
         c, cpre = b["m0"].fwd(ctx, act, save_pre=True)                                       # :108
@@ -100,14 +102,14 @@ def painn_forward(pk: PaiNNPack, q0: Tensor, r_ij: Tensor, graph: ops.EdgeGraph,
         if need_grad:
             tape.append((hpre, x, mu, VW, cpre, s))
         q, mu = q2, mu2
-    return q, mu, (phi, dphi, geo, erec, tape)
+    return q, mu, (phi, dphi, geo, erec, tape, mol_ptr, n_mol)
 
 
 def painn_backward(pk: PaiNNPack, saved, graph: ops.EdgeGraph, n_rbf: int, act: int, g_q: Tensor,
                    g_mu: Optional[Tensor], n_edges_total: int) -> Tensor:
     """dE/dr_ij [E,3] (in the caller's edge order) from dE/dq [N,F], dE/dmu [N,3,F]."""
     F = pk.F
-    phi, dphi, geo, erec, tape = saved
+    phi, dphi, geo, erec, tape, mol_ptr, n_mol = saved
     N = g_q.shape[0]
     dev = g_q.device
     g_rij = torch.empty((n_edges_total, 3), dtype=torch.float32, device=dev)
@@ -124,7 +126,7 @@ def painn_backward(pk: PaiNNPack, saved, graph: ops.EdgeGraph, n_rbf: int, act: 
         g_mu1 = b["mix"].bwd(g_VW.view(3 * N, 2 * F), addend=g_mu.view(3 * N, F)).view(N, 3, F)
         # --- interaction (painn.py:54-65) reversed
         g_x, g_mu0 = ops.painn_edge_bwd(x, mu_in, g_q1, g_mu1, phi, dphi, geo, graph, pk.wf[t], pk.bf[t], F, n_rbf,
-                                        g_rij, accumulate=(t != pk.T - 1), erec=erec)
+                                        g_rij, accumulate=(t != pk.T - 1), erec=erec, mol_ptr=mol_ptr, n_mol=n_mol)
         g_a = b["c1"].bwd(g_x)                                                               # [N,3F]x[3F,F]
         g_q = b["c0"].bwd(g_a, a_pre=hpre, a_act=act, addend=g_q1)                           # [N,F]x[F,F] + residual
         g_mu = g_mu0
@@ -140,7 +142,8 @@ class PaiNNFunction(torch.autograd.Function):
         pk = mod._pack()
         need = r_ij.requires_grad
         q, mu, saved = painn_forward(pk, q0, r_ij.detach(), graph, mod._rbf_kind, mod._n_rbf, mod._rbf_p0,
-                                     mod._rbf_p1, mod._cutoff_value, mod._act, need)
+                                     mod._rbf_p1, mod._cutoff_value, mod._act, need,
+                                     mol_ptr=holder.get("mol_ptr"), n_mol=holder.get("n_mol", 0))
         ctx.holder = dict(pk=pk, saved=saved, graph=graph, n_rbf=mod._n_rbf, act=mod._act, E=r_ij.shape[0])
         ctx.set_materialize_grads(False)
         return q, mu

@@ -329,23 +329,43 @@ def dense_into(A: Tensor, B: Tensor, out: Tensor, ldy: int, **kw):
 
 
 # ------------------------------------------------------------------------------------------------------------ PaiNN
-def painn_edge_fwd(x, mu, q, phi, geo, graph: EdgeGraph, wf, bf, F: int, n_rbf: int):
+# edge-kernel variant: "sys" (default) = system-resident kernels for batches of small systems when the caller supplies
+# mol_ptr, streaming kernels otherwise; "ldg" / "tma" force the streaming kernels (the C library reads SPK_B200_EDGE for
+# the ldg-vs-tma choice of the streaming path itself)
+EDGE_IMPL = os.environ.get("SPK_B200_EDGE", "sys")
+SYS_MAX_AVG_ATOMS = 48
+
+
+def _use_sys(n_atoms: int, mol_ptr, n_mol: int) -> bool:
+    return (EDGE_IMPL == "sys" and mol_ptr is not None and n_mol > 0 and n_atoms / n_mol <= SYS_MAX_AVG_ATOMS)
+
+
+def painn_edge_fwd(x, mu, q, phi, geo, graph: EdgeGraph, wf, bf, F: int, n_rbf: int, mol_ptr=None, n_mol: int = 0):
     N = graph.n_atoms
     q_out = torch.empty((N, F), dtype=torch.float32, device=x.device)
     mu_out = torch.empty((N, 3, F), dtype=torch.float32, device=x.device)
-    _lib.call("spk_painn_edge_fwd", _p(x), _p(mu), _p(q), _p(phi), _p(geo), _p(graph.rowptr), _p(graph.slot_j),
-              _p(wf), _p(bf), N, graph.n_edges, F, n_rbf, _p(q_out), _p(mu_out), _stream())
+    if _use_sys(N, mol_ptr, n_mol):
+        _lib.call("spk_painn_edge_fwd_sys", _p(x), _p(mu), _p(q), _p(phi), _p(geo), _p(graph.rowptr), _p(graph.slot_j),
+                  _p(wf), _p(bf), _p(mol_ptr), n_mol, N, graph.n_edges, F, n_rbf, _p(q_out), _p(mu_out), _stream())
+    else:
+        _lib.call("spk_painn_edge_fwd", _p(x), _p(mu), _p(q), _p(phi), _p(geo), _p(graph.rowptr), _p(graph.slot_j),
+                  _p(wf), _p(bf), N, graph.n_edges, F, n_rbf, _p(q_out), _p(mu_out), _stream())
     return q_out, mu_out
 
 
 def painn_edge_bwd(x, mu, g_q, g_mu, phi, dphi, geo, graph: EdgeGraph, wf, bf, F: int, n_rbf: int, g_rij: Tensor,
-                   accumulate: bool, erec: Optional[Tensor] = None):
+                   accumulate: bool, erec: Optional[Tensor] = None, mol_ptr=None, n_mol: int = 0):
     N = graph.n_atoms
     g_x = torch.empty((N, 3 * F), dtype=torch.float32, device=x.device)
     g_mu_in = torch.empty((N, 3, F), dtype=torch.float32, device=x.device) if mu is not None else None
-    _lib.call("spk_painn_edge_bwd", _p(x), _p(mu), _p(g_q), _p(g_mu), _p(phi), _p(dphi), _p(geo), _p(erec), _p(graph.sptr),
-              _p(graph.pos_slot), _p(graph.pos_i), _p(graph.slot_eid), _p(wf), _p(bf), N, graph.n_edges, F, n_rbf,
-              _p(g_x), _p(g_mu_in), _p(g_rij), 1 if accumulate else 0, _stream())
+    if _use_sys(N, mol_ptr, n_mol):
+        _lib.call("spk_painn_edge_bwd_sys", _p(x), _p(mu), _p(g_q), _p(g_mu), _p(phi), _p(dphi), _p(geo),
+                  _p(graph.sptr), _p(graph.pos_slot), _p(graph.pos_i), _p(graph.slot_eid), _p(wf), _p(bf), _p(mol_ptr),
+                  n_mol, N, graph.n_edges, F, n_rbf, _p(g_x), _p(g_mu_in), _p(g_rij), 1 if accumulate else 0, _stream())
+    else:
+        _lib.call("spk_painn_edge_bwd", _p(x), _p(mu), _p(g_q), _p(g_mu), _p(phi), _p(dphi), _p(geo), _p(erec),
+                  _p(graph.sptr), _p(graph.pos_slot), _p(graph.pos_i), _p(graph.slot_eid), _p(wf), _p(bf), N,
+                  graph.n_edges, F, n_rbf, _p(g_x), _p(g_mu_in), _p(g_rij), 1 if accumulate else 0, _stream())
     return g_x, g_mu_in
 
 

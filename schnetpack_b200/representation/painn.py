@@ -150,8 +150,14 @@ class PaiNN(nn.Module):
                 q0 = q0 + embedding(q0, inputs)
             q0 = q0.detach().contiguous()
 
-        q, mu = K.PaiNNFunction.apply(r_ij if r_ij.is_contiguous() else r_ij.contiguous(), q0,
-                                      dict(module=self, graph=graph))
+        # system boundaries (if the batch carries them) let the edge kernels keep a small system's rows in shared memory
+        holder = dict(module=self, graph=graph)
+        if properties.idx_m in inputs and properties.n_atoms in inputs:
+            n_mol = int(inputs[properties.n_atoms].shape[0])
+            if n_mol > 0 and n_atoms / n_mol <= ops.SYS_MAX_AVG_ATOMS and ops.EDGE_IMPL == "sys":
+                holder["mol_ptr"] = ops.segment_ptr(inputs[properties.idx_m], n_mol)
+                holder["n_mol"] = n_mol
+        q, mu = K.PaiNNFunction.apply(r_ij if r_ij.is_contiguous() else r_ij.contiguous(), q0, holder)
         inputs["scalar_representation"] = q
         inputs["vector_representation"] = mu
         return inputs

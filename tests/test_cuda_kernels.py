@@ -357,3 +357,42 @@ def test_atomwise_and_pairwise():
     gR = ops.pairwise_bwd(gr, g, 1.0)
     ref = torch.zeros(N, 3, device=DEV, dtype=torch.float64).index_add(0, tj, gr.double()).index_add(0, ti, -gr.double())
     assert rel(gR, ref) < 2e-6
+
+
+@pytest.mark.parametrize("gen", ["aspirin", "qm9like"])
+def test_painn_edge_system_resident_matches_streaming(gen):
+    """System-resident edge kernels (rows of a small system staged in shared memory) == streaming kernels; the qm9like
+    batch has systems above the shared-memory capacity chosen at launch, which exercises the in-kernel global fallback."""
+    from schnetpack_b200 import ops
+    from schnetpack_b200 import synthetic as S
+
+    b = S.aspirin_batch(7, seed=11) if gen == "aspirin" else S.qm9like_batch(40, seed=12)
+    ti, tj = torch.as_tensor(b["_idx_i"], device=DEV), torch.as_tensor(b["_idx_j"], device=DEV)
+    N, B = b["_atomic_numbers"].shape[0], b["_n_atoms"].shape[0]
+    g = ops.EdgeGraph(ti, tj, N)
+    mol_ptr = ops.segment_ptr(torch.as_tensor(b["_idx_m"], device=DEV), B)
+    assert mol_ptr.tolist() == np.concatenate([[0], np.cumsum(b["_n_atoms"])]).tolist()
+    torch.manual_seed(13)
+    F, n_rbf, rc = 128, 20, 5.0
+    R = torch.as_tensor(b["_positions"], device=DEV)
+    r = (R[tj] - R[ti]).contiguous()
+    p0 = torch.linspace(0, rc, n_rbf, device=DEV)
+    p1 = torch.full((n_rbf,), float(p0[1] - p0[0]), device=DEV)
+    phi, dphi, geo, erec = ops.edge_geometry(r, g, ops.RBF_GAUSSIAN, n_rbf, p0, p1, rc, True, want_rec=True)
+    x = torch.randn(N, 3 * F, device=DEV)
+    q = torch.randn(N, F, device=DEV)
+    wf = torch.randn(3 * F, n_rbf, device=DEV) * 0.3
+    bf = torch.randn(3 * F, device=DEV) * 0.3
+    g_q = torch.randn(N, F, device=DEV)
+    g_mu = torch.randn(N, 3, F, device=DEV)
+    for mu in (torch.randn(N, 3, F, device=DEV), None):
+        qa, ma = ops.painn_edge_fwd(x, mu, q, phi, geo, g, wf, bf, F, n_rbf)
+        qb, mb = ops.painn_edge_fwd(x, mu, q, phi, geo, g, wf, bf, F, n_rbf, mol_ptr=mol_ptr, n_mol=B)
+        assert rel(qb, qa) < 1e-6 and rel(mb, ma) < 1e-6
+        ra, rb = torch.zeros(r.shape[0], 3, device=DEV), torch.zeros(r.shape[0], 3, device=DEV)
+        gxa, gma = ops.painn_edge_bwd(x, mu, g_q, g_mu, phi, dphi, geo, g, wf, bf, F, n_rbf, ra, False, erec=erec)
+        gxb, gmb = ops.painn_edge_bwd(x, mu, g_q, g_mu, phi, dphi, geo, g, wf, bf, F, n_rbf, rb, False, erec=erec,
+                                      mol_ptr=mol_ptr, n_mol=B)
+        assert rel(gxb, gxa) < 2e-6 and rel(rb, ra) < 5e-6
+        if mu is not None:
+            assert rel(gmb, gma) < 2e-6
