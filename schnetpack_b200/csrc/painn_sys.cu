@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(NW * 32) k_painn_edge_bwd_sys(
 // raise the kernel's dynamic shared-memory limit when needed (remembered per kernel: no API call on the steady path)
 template <typename Kern>
 static int set_smem(Kern k, size_t bytes) {
-    static size_t cur = 48 * 1024;
+    static size_t cur = 0;   // (the default 48 KB limit counts static + dynamic shared memory: always opt in)
     if (bytes <= cur) return 0;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return SPK_CUDA_ERR(e);
