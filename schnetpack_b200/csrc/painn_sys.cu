@@ -377,13 +377,14 @@ __global__ void __launch_bounds__(NW * 32) k_painn_edge_bwd_sys(
 }
 
 // raise the kernel's dynamic shared-memory limit when needed (remembered per kernel: no API call on the steady path)
+// (`cur` is the caller's per-kernel-instantiation cache; the default 48 KB limit counts static + dynamic shared memory,
+// so the attribute is always raised at least once)
 template <typename Kern>
-static int set_smem(Kern k, size_t bytes) {
-    static size_t cur = 0;   // (the default 48 KB limit counts static + dynamic shared memory: always opt in)
-    if (bytes <= cur) return 0;
+static int set_smem(Kern k, size_t bytes, size_t* cur) {
+    if (bytes <= *cur) return 0;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return SPK_CUDA_ERR(e);
-    cur = bytes;
+    *cur = bytes;
     return 0;
 }
 
@@ -393,13 +394,14 @@ int launch_fwd_sys(const float* x, const float* mu, const float* q, const float*
                    int n_mol, int parts, int cap, int n_rbf, float* q_out, float* mu_out, cudaStream_t st) {
     constexpr int F = NW * 32;
     const size_t sm = (size_t)cap * 3 * F * 4 * (mu ? 2 : 1);
+    static size_t cur_mu = 0, cur_nomu = 0;
     int rc;
     if (mu) {
-        if ((rc = set_smem(k_painn_edge_fwd_sys<NW, NRB, true>, sm))) return rc;
+        if ((rc = set_smem(k_painn_edge_fwd_sys<NW, NRB, true>, sm, &cur_mu))) return rc;
         k_painn_edge_fwd_sys<NW, NRB, true><<<n_mol * parts, NW * 32, sm, st>>>(x, mu, q, phi, geo, rowptr, slot_j, wf, bf,
                                                                               mol_ptr, parts, cap, n_rbf, q_out, mu_out);
     } else {
-        if ((rc = set_smem(k_painn_edge_fwd_sys<NW, NRB, false>, sm))) return rc;
+        if ((rc = set_smem(k_painn_edge_fwd_sys<NW, NRB, false>, sm, &cur_nomu))) return rc;
         k_painn_edge_fwd_sys<NW, NRB, false><<<n_mol * parts, NW * 32, sm, st>>>(x, mu, q, phi, geo, rowptr, slot_j, wf,
                                                                                bf, mol_ptr, parts, cap, n_rbf, q_out, mu_out);
     }
@@ -413,14 +415,15 @@ int launch_bwd_sys(const float* x, const float* mu, const float* g_q, const floa
                    int cap, int n_rbf, float* g_x, float* g_mu_in, float* g_rij, int accumulate, cudaStream_t st) {
     constexpr int F = NW * 32;
     const size_t sm = (size_t)cap * 4 * F * 4;
+    static size_t cur_mu = 0, cur_nomu = 0;
     int rc;
     if (mu) {
-        if ((rc = set_smem(k_painn_edge_bwd_sys<NW, NRB, true>, sm))) return rc;
+        if ((rc = set_smem(k_painn_edge_bwd_sys<NW, NRB, true>, sm, &cur_mu))) return rc;
         k_painn_edge_bwd_sys<NW, NRB, true><<<n_mol * parts, NW * 32, sm, st>>>(
             x, mu, g_q, g_mu, phi, dphi, geo, sptr, pos_slot, pos_i, slot_eid, wf, bf, mol_ptr, parts, cap, n_rbf, g_x,
             g_mu_in, g_rij, accumulate);
     } else {
-        if ((rc = set_smem(k_painn_edge_bwd_sys<NW, NRB, false>, sm))) return rc;
+        if ((rc = set_smem(k_painn_edge_bwd_sys<NW, NRB, false>, sm, &cur_nomu))) return rc;
         k_painn_edge_bwd_sys<NW, NRB, false><<<n_mol * parts, NW * 32, sm, st>>>(
             x, mu, g_q, g_mu, phi, dphi, geo, sptr, pos_slot, pos_i, slot_eid, wf, bf, mol_ptr, parts, cap, n_rbf, g_x,
             g_mu_in, g_rij, accumulate);
