@@ -203,13 +203,19 @@ extern "C" int spk_dense(const float* A, int64_t M, int K, int64_t lda, const fl
     GemmArgs g;
     g.A = A; g.a_pre = a_pre; g.B = B; g.bias = bias; g.addend = addend; g.Y = Y; g.y_pre = y_pre;
     g.M = M; g.lda = lda; g.ld_add = ld_add; g.ldy = ldy; g.K = K; g.N = N; g.a_act = a_act; g.act = act;
-    const int64_t ctas128 = spk_cdiv(M, 128) * spk_cdiv(N, BN);
-    if (ctas128 >= 3 * (int64_t)spk_num_sms()) {
-        dim3 grid((unsigned)spk_cdiv(M, 128), (unsigned)spk_cdiv(N, BN));
+    // these layers are skinny (M = atoms): pick the largest row tile that still gives every SM several CTAs, because a
+    // CTA's k-loop is a chain of global-load -> shared -> barrier latencies that only co-resident CTAs can hide
+    const int64_t want = 3 * (int64_t)spk_num_sms();
+    const int64_t nt = spk_cdiv(N, BN);
+    if (spk_cdiv(M, 128) * nt >= want) {
+        dim3 grid((unsigned)spk_cdiv(M, 128), (unsigned)nt);
         k_dense<128><<<grid, 256, 0, spk_st(stream)>>>(g);
-    } else {
-        dim3 grid((unsigned)spk_cdiv(M, 64), (unsigned)spk_cdiv(N, BN));
+    } else if (spk_cdiv(M, 64) * nt >= want) {
+        dim3 grid((unsigned)spk_cdiv(M, 64), (unsigned)nt);
         k_dense<64><<<grid, 128, 0, spk_st(stream)>>>(g);
+    } else {
+        dim3 grid((unsigned)spk_cdiv(M, 32), (unsigned)nt);
+        k_dense<32><<<grid, 64, 0, spk_st(stream)>>>(g);
     }
     SPK_LAUNCH_CHECK();
     return SPK_OK;

@@ -505,12 +505,12 @@ int launch_edge_bwd(const float* x, const float* mu, const float* g_q, const flo
     return 0;
 }
 
-// one-time choice of the edge-kernel variant via SPK_B200_EDGE: "tma" (painn_tma.cu; default) or "ldg" (this file)
+// one-time choice of the streaming edge-kernel variant via SPK_B200_EDGE: "ldg" (this file; default, fastest in r1) or "tma"
 bool use_tma_variant() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("SPK_B200_EDGE");
-        v = (e && e[0] == 'l') ? 0 : 1;
+        v = (e && e[0] == 't') ? 1 : 0;
     }
     return v == 1;
 }

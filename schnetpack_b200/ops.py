@@ -329,10 +329,12 @@ def dense_into(A: Tensor, B: Tensor, out: Tensor, ldy: int, **kw):
 
 
 # ------------------------------------------------------------------------------------------------------------ PaiNN
-# edge-kernel variant: "sys" (default) = system-resident kernels for batches of small systems when the caller supplies
-# mol_ptr, streaming kernels otherwise; "ldg" / "tma" force the streaming kernels (the C library reads SPK_B200_EDGE for
-# the ldg-vs-tma choice of the streaming path itself)
-EDGE_IMPL = os.environ.get("SPK_B200_EDGE", "sys")
+# edge-kernel variant (r1 measurements on cfg2, fwd/bwd us per launch: ldg 59/115, tma 71/145, sys 80/170):
+#   "ldg" (default) streaming kernels with coalesced global gathers (csrc/painn.cu);
+#   "tma"           streaming kernels with a TMA bulk-copy + mbarrier producer/consumer ring (csrc/painn_tma.cu);
+#   "sys"           system-resident kernels for batches of small systems when the caller supplies mol_ptr
+#                   (csrc/painn_sys.cu).  The C library reads SPK_B200_EDGE for the ldg-vs-tma choice.
+EDGE_IMPL = os.environ.get("SPK_B200_EDGE", "ldg")
 SYS_MAX_AVG_ATOMS = 48
 
 

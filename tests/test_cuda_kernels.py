@@ -366,6 +366,18 @@ def test_painn_edge_system_resident_matches_streaming(gen):
     from schnetpack_b200 import ops
     from schnetpack_b200 import synthetic as S
 
+    monkey_impl = ops.EDGE_IMPL
+    ops.EDGE_IMPL = "sys"          # opt in to the system-resident dispatch for this comparison
+    try:
+        _sys_vs_streaming(gen)
+    finally:
+        ops.EDGE_IMPL = monkey_impl
+
+
+def _sys_vs_streaming(gen):
+    from schnetpack_b200 import ops
+    from schnetpack_b200 import synthetic as S
+
     b = S.aspirin_batch(7, seed=11) if gen == "aspirin" else S.qm9like_batch(40, seed=12)
     ti, tj = torch.as_tensor(b["_idx_i"], device=DEV), torch.as_tensor(b["_idx_j"], device=DEV)
     N, B = b["_atomic_numbers"].shape[0], b["_n_atoms"].shape[0]
@@ -386,7 +398,7 @@ def test_painn_edge_system_resident_matches_streaming(gen):
     g_q = torch.randn(N, F, device=DEV)
     g_mu = torch.randn(N, 3, F, device=DEV)
     for mu in (torch.randn(N, 3, F, device=DEV), None):
-        qa, ma = ops.painn_edge_fwd(x, mu, q, phi, geo, g, wf, bf, F, n_rbf)
+        qa, ma = ops.painn_edge_fwd(x, mu, q, phi, geo, g, wf, bf, F, n_rbf)          # streaming (no mol_ptr)
         qb, mb = ops.painn_edge_fwd(x, mu, q, phi, geo, g, wf, bf, F, n_rbf, mol_ptr=mol_ptr, n_mol=B)
         assert rel(qb, qa) < 1e-6 and rel(mb, ma) < 1e-6
         ra, rb = torch.zeros(r.shape[0], 3, device=DEV), torch.zeros(r.shape[0], 3, device=DEV)
