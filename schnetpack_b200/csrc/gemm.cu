@@ -24,8 +24,16 @@ struct GemmArgs {
     int K, N, a_act, act;
 };
 
-// BM = 128 (256 threads) for tall problems, BM = 64 (128 threads) when the 128-row grid would not fill the 148 SMs.
-template <int BM>
+// activation helpers kept out of line and selected at compile time: inlining the runtime-switched expf/log1pf code into
+// the unrolled load / epilogue loops made the kernel 6.3k SASS instructions long and 22 % of its stalls were
+// instruction-cache misses (profiles/r1_ncu_dense.txt)
+template <int ACT>
+__device__ __noinline__ float act_grad1(float q) { return spk_act_grad(q, ACT); }
+template <int ACT>
+__device__ __noinline__ float act1(float v) { return spk_act(v, ACT); }
+
+// BM = 128 (256 threads) for tall problems, BM = 64 / 32 when the 128-row grid would not fill the 148 SMs.
+template <int BM, int A_ACT, int ACT>
 __global__ void __launch_bounds__(BM * 2) k_dense(GemmArgs g) {
     constexpr int NT = BM * 2;
     constexpr int AS_LD = BM + 4;
@@ -56,12 +64,12 @@ __global__ void __launch_bounds__(BM * 2) k_dense(GemmArgs g) {
                 const float* p = g.A + m * g.lda + k;
                 if (a_vec && k + 3 < g.K) {
                     v = *reinterpret_cast<const float4*>(p);
-                    if (g.a_pre) {
+                    if (A_ACT != SPK_ACT_NONE) {
                         float4 q = *reinterpret_cast<const float4*>(g.a_pre + m * g.lda + k);
-                        v.x *= spk_act_grad(q.x, g.a_act);
-                        v.y *= spk_act_grad(q.y, g.a_act);
-                        v.z *= spk_act_grad(q.z, g.a_act);
-                        v.w *= spk_act_grad(q.w, g.a_act);
+                        v.x *= act_grad1<A_ACT>(q.x);
+                        v.y *= act_grad1<A_ACT>(q.y);
+                        v.z *= act_grad1<A_ACT>(q.z);
+                        v.w *= act_grad1<A_ACT>(q.w);
                     }
                 } else {
                     float t[4] = {0.f, 0.f, 0.f, 0.f};
@@ -69,7 +77,7 @@ __global__ void __launch_bounds__(BM * 2) k_dense(GemmArgs g) {
                     for (int i = 0; i < 4; ++i)
                         if (k + i < g.K) {
                             t[i] = p[i];
-                            if (g.a_pre) t[i] *= spk_act_grad(g.a_pre[m * g.lda + k + i], g.a_act);
+                            if (A_ACT != SPK_ACT_NONE) t[i] *= act_grad1<A_ACT>(g.a_pre[m * g.lda + k + i]);
                         }
                     v = make_float4(t[0], t[1], t[2], t[3]);
                 }
@@ -171,9 +179,9 @@ __global__ void __launch_bounds__(BM * 2) k_dense(GemmArgs g) {
             for (int j = 0; j < 4; ++j)
                 if (n + j < g.N) g.y_pre[m * g.ldy + n + j] = v[j];
         }
-        if (g.act != SPK_ACT_NONE) {
+        if (ACT != SPK_ACT_NONE) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] = spk_act(v[j], g.act);
+            for (int j = 0; j < 4; ++j) v[j] = act1<ACT>(v[j]);
         }
         if (g.addend) {
 #pragma unroll
@@ -203,20 +211,32 @@ extern "C" int spk_dense(const float* A, int64_t M, int K, int64_t lda, const fl
     GemmArgs g;
     g.A = A; g.a_pre = a_pre; g.B = B; g.bias = bias; g.addend = addend; g.Y = Y; g.y_pre = y_pre;
     g.M = M; g.lda = lda; g.ld_add = ld_add; g.ldy = ldy; g.K = K; g.N = N; g.a_act = a_act; g.act = act;
+    if (!a_pre) a_act = SPK_ACT_NONE;
+    g.a_act = a_act;
     // these layers are skinny (M = atoms): pick the largest row tile that still gives every SM several CTAs, because a
     // CTA's k-loop is a chain of global-load -> shared -> barrier latencies that only co-resident CTAs can hide
     const int64_t want = 3 * (int64_t)spk_num_sms();
     const int64_t nt = spk_cdiv(N, BN);
-    if (spk_cdiv(M, 128) * nt >= want) {
-        dim3 grid((unsigned)spk_cdiv(M, 128), (unsigned)nt);
-        k_dense<128><<<grid, 256, 0, spk_st(stream)>>>(g);
-    } else if (spk_cdiv(M, 64) * nt >= want) {
-        dim3 grid((unsigned)spk_cdiv(M, 64), (unsigned)nt);
-        k_dense<64><<<grid, 128, 0, spk_st(stream)>>>(g);
-    } else {
-        dim3 grid((unsigned)spk_cdiv(M, 32), (unsigned)nt);
-        k_dense<32><<<grid, 64, 0, spk_st(stream)>>>(g);
+    const int bm = (spk_cdiv(M, 128) * nt >= want) ? 128 : (spk_cdiv(M, 64) * nt >= want) ? 64 : 32;
+    dim3 grid((unsigned)spk_cdiv(M, bm), (unsigned)nt);
+    cudaStream_t st = spk_st(stream);
+#define LAUNCH_BM(AA, AC)                                                        \
+    do {                                                                         \
+        if (bm == 128) k_dense<128, AA, AC><<<grid, 256, 0, st>>>(g);            \
+        else if (bm == 64) k_dense<64, AA, AC><<<grid, 128, 0, st>>>(g);         \
+        else k_dense<32, AA, AC><<<grid, 64, 0, st>>>(g);                        \
+    } while (0)
+    if (a_act == SPK_ACT_NONE) {
+        if (act == SPK_ACT_NONE) LAUNCH_BM(0, 0); else if (act == SPK_ACT_SILU) LAUNCH_BM(0, 1); else LAUNCH_BM(0, 2);
+    } else if (act == SPK_ACT_NONE) {
+        if (a_act == SPK_ACT_SILU) LAUNCH_BM(1, 0); else LAUNCH_BM(2, 0);
+    } else {   // both a backward prologue and a forward activation: rare, compiled for SiLU/ssp pairs of the same kind
+        if (a_act == SPK_ACT_SILU && act == SPK_ACT_SILU) LAUNCH_BM(1, 1);
+        else if (a_act == SPK_ACT_SSP && act == SPK_ACT_SSP) LAUNCH_BM(2, 2);
+        else if (a_act == SPK_ACT_SILU) LAUNCH_BM(1, 2);
+        else LAUNCH_BM(2, 1);
     }
+#undef LAUNCH_BM
     SPK_LAUNCH_CHECK();
     return SPK_OK;
 }
