@@ -366,6 +366,29 @@ def run_cuda(args, rank, world, local_rank):
                          f"ATen op sequence) on {cores} threads (fastest of 8/16/32/64/{os.cpu_count()} probed on this "
                          f"host); mean {1e3 * float(np.mean(ts)):.0f} ms"}
 
+    # ---- the reference's eager single-GPU path (oracle port = same ATen op sequence) on this B200, for the >=5x target ----
+    eager = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            from oracle import spk_oracle as O
+
+            p_dev = O.to_torch(params, torch.float32, dev)
+            x_dev = O.to_torch(data, torch.float32, dev)
+            for _ in range(3):
+                O.energy_forces(spec, p_dev, x_dev, device=dev)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            n_it = 10
+            for _ in range(n_it):
+                O.energy_forces(spec, p_dev, x_dev, device=dev)
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / n_it
+            eager = {"value": B / dt, "unit": UNIT, "ms_per_step": 1e3 * dt,
+                     "kind": "port: oracle/spk_oracle.py (the reference modules' eager ATen op sequence, cuBLAS SGEMM, "
+                             "index_select / index_add_ atomics, autograd backward) on the same B200, inputs resident"}
+        except Exception as exc:  # pragma: no cover
+            eager = {"error": repr(exc)[:200]}
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -381,7 +404,8 @@ def run_cuda(args, rank, world, local_rank):
                 "api": "eager model(inputs)" if graphed is None else "GraphedPotential(model)(host_batch): CUDA-graph replay",
                 "ms_per_step_median": e2e_steps_ms[len(e2e_steps_ms) // 2], "ms_per_step_max": e2e_steps_ms[-1]},
         "gpu_launches": launches,
-        "roofline": roof, "roofline_all": roof_all, "cpu_baseline": cpu,
+        "roofline": roof, "roofline_all": roof_all, "cpu_baseline": cpu, "eager_gpu_baseline": eager,
+        "impl_switches": {"dense": ops.DENSE_IMPL, "edge": ops.EDGE_IMPL},
     }
     print(json.dumps(line), flush=True)
 

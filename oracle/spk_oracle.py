@@ -60,7 +60,7 @@ def dense(x: Tensor, w: Tensor, b: Optional[Tensor] = None, act=None) -> Tensor:
 
 def scatter_add(x: Tensor, idx: Tensor, dim_size: int) -> Tensor:
     """nn/scatter.py:26-34 -- zeros(dim_size, ...).index_add(0, idx, x)."""
-    out = torch.zeros((dim_size,) + tuple(x.shape[1:]), dtype=x.dtype)
+    out = torch.zeros((dim_size,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
     return out.index_add(0, idx, x)
 
 
@@ -112,7 +112,7 @@ def painn_representation(spec: dict, p: Dict[str, Tensor], Z: Tensor, r_ij: Tens
     filters = dense(phi, p["representation.filter_net.weight"], p["representation.filter_net.bias"])
     filters = filters * fcut[..., None]                                  # :232  [E,1,T*3F]
     q = p["representation.embedding.weight"][Z][:, None, :]             # :239,:242  [N,1,F]
-    mu = torch.zeros((n, 3, Fd), dtype=q.dtype)                          # :246
+    mu = torch.zeros((n, 3, Fd), dtype=q.dtype, device=q.device)         # :246
     for t in range(spec["n_interactions"]):
         tt = 0 if spec["shared_interactions"] else t
         w_t = filters if spec["shared_filters"] else filters[..., t * 3 * Fd:(t + 1) * 3 * Fd]   # :233-236
@@ -152,17 +152,20 @@ def atomwise(p: Dict[str, Tensor], q: Tensor, idx_m: Tensor, n_mol: int, prefix:
 
 
 # ----------------------------------------------------------------------------------------------------- whole model
-def to_torch(d: dict, dtype=torch.float32) -> Dict[str, Tensor]:
+def to_torch(d: dict, dtype=torch.float32, device=None) -> Dict[str, Tensor]:
     out = {}
     for k, v in d.items():
         t = torch.as_tensor(v)
         if t.is_floating_point():
             t = t.to(dtype)
+        if device is not None:
+            t = t.to(device)
         out[k] = t
     return out
 
 
-def energy_forces(spec: dict, params: dict, inputs: dict, dtype=torch.float32, need_repr: bool = False):
+def energy_forces(spec: dict, params: dict, inputs: dict, dtype=torch.float32, need_repr: bool = False, device=None,
+                  n_mol: Optional[int] = None):
     """model/base.py:174-190 (NeuralNetworkPotential.forward) for the modules
     [PairwiseDistances] -> {SchNet|PaiNN} -> [Atomwise, Forces]; forces = -dE/dR (atomistic/response.py:59-76).
 
@@ -170,10 +173,11 @@ def energy_forces(spec: dict, params: dict, inputs: dict, dtype=torch.float32, n
     are taken w.r.t. it pushed back through R only when ``_positions``/``_offsets`` are given.
     Returns dict(energy [B], forces [N,3] or None, scalar_representation, vector_representation?).
     """
-    p = to_torch(params, dtype)
-    x = to_torch(inputs, dtype)
+    p = params if device is not None and all(torch.is_tensor(v) for v in params.values()) else to_torch(params, dtype, device)
+    x = inputs if device is not None and all(torch.is_tensor(v) for v in inputs.values()) else to_torch(inputs, dtype, device)
     Z, idx_i, idx_j, idx_m = x["_atomic_numbers"], x["_idx_i"], x["_idx_j"], x["_idx_m"]
-    n_mol = int(idx_m[-1]) + 1                                           # atomwise.py:80
+    if n_mol is None:
+        n_mol = int(idx_m[-1]) + 1                                       # atomwise.py:80 (host sync, as in the reference)
     want_f = bool(spec.get("forces", True))
     direct_rij = "_Rij" in x
     if direct_rij:
