@@ -14,9 +14,7 @@
 
 namespace {
 
-constexpr int CH = 48;   // edges staged per chunk (multiple of the prefetch ring depths 3 and 4)
-constexpr int PFD = 4;   // forward gather ring depth: PFD-1 edges in flight per thread
-constexpr int PBD = 3;   // reverse gather ring depth
+constexpr int CH = 32;   // edges staged per chunk (multiple of the 4-edge reduction groups of the reverse kernel)
 
 // cooperative staging of contiguous per-slot records [n, KP] -> smem [n, NRB] (zero padded)
 template <int NRB, int NTHR>
@@ -40,6 +38,7 @@ __global__ void __launch_bounds__(NW * 32, 512 / (NW * 32)) k_painn_edge_fwd(
     constexpr int NTHR = NW * 32;
     __shared__ __align__(16) float s_phi[CH * NRB];
     __shared__ __align__(16) float s_geo[CH * SPK_GEO_STRIDE];
+    __shared__ int s_j[CH];
 
     const int c = threadIdx.x;
     const int nb = gridDim.x, b = blockIdx.x;
@@ -52,55 +51,25 @@ __global__ void __launch_bounds__(NW * 32, 512 / (NW * 32)) k_painn_edge_fwd(
     const int KP = spk_kp(n_rbf);
 
     const int s_begin = rowptr[row_lo], s_end = rowptr[row_hi];
-    // Every dependent global load is issued at least one edge ahead of its use (the warp issues in order, so a load
-    // consumed right away would stall everything queued behind it): row boundaries two rows ahead, the receiver's own
-    // q/mu row at row entry, sender indices PFD edges ahead, sender rows PFD-1 edges ahead.
     int i = row_lo;
     int next_boundary = rowptr[i + 1];
-    int boundary2 = rowptr[min(i + 2, n_atoms)];
     float dq = 0.f, dm0 = 0.f, dm1 = 0.f, dm2 = 0.f;
-    float rq, rm0 = 0.f, rm1 = 0.f, rm2 = 0.f;
-    auto load_res = [&](int row) {
-        rq = q[(size_t)row * F + c];
-        if (HAS_MU) {
-            const float* __restrict__ mr = mu + (size_t)row * (3 * F) + c;
-            rm0 = mr[0];
-            rm1 = mr[F];
-            rm2 = mr[2 * F];
-        }
-    };
-    load_res(i);
-    auto flush_advance = [&]() {
-        q_out[(size_t)i * F + c] = rq + dq;
-        float* __restrict__ mo = mu_out + (size_t)i * (3 * F) + c;
-        mo[0] = rm0 + dm0;
-        mo[F] = rm1 + dm1;
-        mo[2 * F] = rm2 + dm2;
-        dq = dm0 = dm1 = dm2 = 0.f;
-        ++i;
-        next_boundary = boundary2;
-        boundary2 = rowptr[min(i + 2, n_atoms)];
-        if (i < row_hi) load_res(i);
-    };
 
-    struct Gather { float xa, xb, xc, m0, m1, m2; };
-    Gather ring[PFD];
-    auto issue = [&](Gather& g, int j) {
-        const float* __restrict__ xj = x + (size_t)j * (3 * F) + c;
-        g.xa = xj[0];
-        g.xb = xj[F];
+    auto flush = [&](int row) {
+        const size_t o = (size_t)row * F + c;
+        q_out[o] = q[o] + dq;
+        const size_t om = (size_t)row * 3 * F + c;
         if (HAS_MU) {
-            g.xc = xj[2 * F];
-            const float* __restrict__ mj = mu + (size_t)j * (3 * F) + c;
-            g.m0 = mj[0];
-            g.m1 = mj[F];
-            g.m2 = mj[2 * F];
+            mu_out[om] = mu[om] + dm0;
+            mu_out[om + F] = mu[om + F] + dm1;
+            mu_out[om + 2 * F] = mu[om + 2 * F] + dm2;
+        } else {
+            mu_out[om] = dm0;
+            mu_out[om + F] = dm1;
+            mu_out[om + 2 * F] = dm2;
         }
+        dq = dm0 = dm1 = dm2 = 0.f;
     };
-#pragma unroll
-    for (int d = 0; d < PFD - 1; ++d)
-        if (s_begin + d < s_end) issue(ring[d], __ldg(slot_j + s_begin + d));
-    int j_next = (s_begin + PFD - 1 < s_end) ? __ldg(slot_j + s_begin + PFD - 1) : 0;
 
     for (int cs = s_begin; cs < s_end; cs += CH) {
         const int n = min(CH, s_end - cs);
@@ -108,57 +77,98 @@ __global__ void __launch_bounds__(NW * 32, 512 / (NW * 32)) k_painn_edge_fwd(
         stage_rows_contig<NRB, NTHR>(s_phi, phi + (int64_t)cs * KP, n, KP);
         for (int t = threadIdx.x; t < n * 2; t += NTHR)
             reinterpret_cast<float4*>(s_geo)[t] = reinterpret_cast<const float4*>(geo + (int64_t)cs * SPK_GEO_STRIDE)[t];
+        for (int t = threadIdx.x; t < n; t += NTHR) s_j[t] = slot_j[cs + t];
         __syncthreads();
 
-        for (int t0 = 0; t0 < n; t0 += PFD) {
+#pragma unroll 2
+        for (int t = 0; t < n; ++t) {
+            const int s = cs + t;
+            while (s >= next_boundary) {
+                flush(i);
+                ++i;
+                next_boundary = rowptr[i + 1];
+            }
+            const int j = s_j[t];
+            const float* __restrict__ xj = x + (size_t)j * (3 * F) + c;
+            const float xa = xj[0], xb = xj[F];
+            float xc = 0.f, m0 = 0.f, m1 = 0.f, m2 = 0.f;
+            if (HAS_MU) {
+                xc = xj[2 * F];
+                const float* __restrict__ mj = mu + (size_t)j * (3 * F) + c;
+                m0 = mj[0];
+                m1 = mj[F];
+                m2 = mj[2 * F];
+            }
+            const float4 g0 = *reinterpret_cast<const float4*>(s_geo + t * SPK_GEO_STRIDE);      // ux uy uz d
+            const float fc = s_geo[t * SPK_GEO_STRIDE + 4];
+            float2 pa2 = make_float2(w.ba, 0.f), pb2 = make_float2(w.bb, 0.f), pc2 = make_float2(w.bc, 0.f);
+            const float4* __restrict__ ph = reinterpret_cast<const float4*>(s_phi + t * NRB);
 #pragma unroll
-            for (int u = 0; u < PFD; ++u) {
-                const int t = t0 + u;
-                if (t < n) {
-                    const int s = cs + t;
-                    if (s + PFD - 1 < s_end) issue(ring[(u + PFD - 1) % PFD], j_next);
-                    if (s + PFD < s_end) j_next = __ldg(slot_j + s + PFD);
-                    while (s >= next_boundary) flush_advance();
-                    const Gather& g = ring[u];
-                    const float4 g0 = *reinterpret_cast<const float4*>(s_geo + t * SPK_GEO_STRIDE);      // ux uy uz d
-                    const float fc = s_geo[t * SPK_GEO_STRIDE + 4];
-                    float2 pa2 = make_float2(w.ba, 0.f), pb2 = make_float2(w.bb, 0.f), pc2 = make_float2(w.bc, 0.f);
-                    const float4* __restrict__ ph = reinterpret_cast<const float4*>(s_phi + t * NRB);
-#pragma unroll
-                    for (int k4 = 0; k4 < NRB / 4; ++k4) {
-                        const float4 p = ph[k4];
-                        const float2 p01 = make_float2(p.x, p.y), p23 = make_float2(p.z, p.w);
-                        pa2 = __ffma2_rn(p01, w.a[2 * k4], pa2);
-                        pb2 = __ffma2_rn(p01, w.b[2 * k4], pb2);
-                        pa2 = __ffma2_rn(p23, w.a[2 * k4 + 1], pa2);
-                        pb2 = __ffma2_rn(p23, w.b[2 * k4 + 1], pb2);
-                        if (HAS_MU) {
-                            pc2 = __ffma2_rn(p01, w.c[2 * k4], pc2);
-                            pc2 = __ffma2_rn(p23, w.c[2 * k4 + 1], pc2);
-                        }
-                    }
-                    const float pa = pa2.x + pa2.y, pb = pb2.x + pb2.y, pc = pc2.x + pc2.y;
-                    dq = fmaf(fc * pa, g.xa, dq);
-                    const float tb = fc * pb * g.xb;
-                    dm0 = fmaf(tb, g0.x, dm0);
-                    dm1 = fmaf(tb, g0.y, dm1);
-                    dm2 = fmaf(tb, g0.z, dm2);
-                    if (HAS_MU) {
-                        const float tc = fc * pc * g.xc;
-                        dm0 = fmaf(tc, g.m0, dm0);
-                        dm1 = fmaf(tc, g.m1, dm1);
-                        dm2 = fmaf(tc, g.m2, dm2);
-                    }
+            for (int k4 = 0; k4 < NRB / 4; ++k4) {
+                const float4 p = ph[k4];
+                const float2 p01 = make_float2(p.x, p.y), p23 = make_float2(p.z, p.w);
+                pa2 = __ffma2_rn(p01, w.a[2 * k4], pa2);
+                pb2 = __ffma2_rn(p01, w.b[2 * k4], pb2);
+                pa2 = __ffma2_rn(p23, w.a[2 * k4 + 1], pa2);
+                pb2 = __ffma2_rn(p23, w.b[2 * k4 + 1], pb2);
+                if (HAS_MU) {
+                    pc2 = __ffma2_rn(p01, w.c[2 * k4], pc2);
+                    pc2 = __ffma2_rn(p23, w.c[2 * k4 + 1], pc2);
                 }
+            }
+            const float pa = pa2.x + pa2.y, pb = pb2.x + pb2.y, pc = pc2.x + pc2.y;
+            dq = fmaf(fc * pa, xa, dq);
+            const float tb = fc * pb * xb;
+            dm0 = fmaf(tb, g0.x, dm0);
+            dm1 = fmaf(tb, g0.y, dm1);
+            dm2 = fmaf(tb, g0.z, dm2);
+            if (HAS_MU) {
+                const float tc = fc * pc * xc;
+                dm0 = fmaf(tc, m0, dm0);
+                dm1 = fmaf(tc, m1, dm1);
+                dm2 = fmaf(tc, m2, dm2);
             }
         }
     }
-    while (i < row_hi) flush_advance();
+    for (; i < row_hi; ++i) flush(i);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
 // reverse pass, grouped by sender
 // ------------------------------------------------------------------------------------------------------------------
+// Sum over the 32 lanes of 16 values per lane (4 edges x 4 scalars) with a transposing butterfly: 16 shuffles instead of
+// 80.  Afterwards lane l holds the complete sum of value index 8*bit4 + 4*bit3 + 2*bit2 + bit1 (both lanes of a pair).
+__device__ __forceinline__ float butterfly16(float (&v)[16], int lane) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const bool up = lane & 16;
+        const float send = up ? v[i] : v[i + 8];
+        const float keep = up ? v[i + 8] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const bool up = lane & 8;
+        const float send = up ? v[i] : v[i + 4];
+        const float keep = up ? v[i + 4] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const bool up = lane & 4;
+        const float send = up ? v[i] : v[i + 2];
+        const float keep = up ? v[i + 2] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    {
+        const bool up = lane & 2;
+        const float send = up ? v[0] : v[1];
+        const float keep = up ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
 template <int NW, int NRB, bool HAS_MU>
 __global__ void __launch_bounds__(NW * 32, 512 / (NW * 32)) k_painn_edge_bwd(
     const float* __restrict__ x, const float* __restrict__ mu, const float* __restrict__ g_q,
@@ -172,6 +182,7 @@ __global__ void __launch_bounds__(NW * 32, 512 / (NW * 32)) k_painn_edge_bwd(
     __shared__ __align__(16) float s_phi[CH * NRB];
     __shared__ __align__(16) float s_dphi[CH * NRB];
     __shared__ __align__(16) float s_geo[CH * SPK_GEO_STRIDE];
+    __shared__ int s_i[CH];
     __shared__ int s_eid[CH];
     __shared__ float s_red[CH][NW][4];
 
@@ -190,62 +201,36 @@ __global__ void __launch_bounds__(NW * 32, 512 / (NW * 32)) k_painn_edge_bwd(
     const int p_begin = sptr[j_lo], p_end = sptr[j_hi];
     int j = j_lo;
     int next_boundary = sptr[j + 1];
-    int boundary2 = sptr[min(j + 2, n_atoms)];
-    // the sender's own rows (x_j, mu_j and the residual g_mu_j) are requested at row entry, i.e. before the ~100
-    // filter instructions of the row's first edge, and consumed after them
-    struct Own { float xa, xb, xc, m0, m1, m2, r0, r1, r2; };
-    Own own;
-    auto load_own = [&](Own& o, int row) {
+    float xa, xb, xc = 0.f, m0 = 0.f, m1 = 0.f, m2 = 0.f;
+    float gxa = 0.f, gxb = 0.f, gxc = 0.f, gm0 = 0.f, gm1 = 0.f, gm2 = 0.f;
+
+    auto load_own = [&](int row) {
         const float* __restrict__ xr = x + (size_t)row * (3 * F) + c;
-        o.xa = xr[0];
-        o.xb = xr[F];
-        o.xc = 0.f; o.m0 = 0.f; o.m1 = 0.f; o.m2 = 0.f; o.r0 = 0.f; o.r1 = 0.f; o.r2 = 0.f;
+        xa = xr[0];
+        xb = xr[F];
         if (HAS_MU) {
-            o.xc = xr[2 * F];
+            xc = xr[2 * F];
             const float* __restrict__ mr = mu + (size_t)row * (3 * F) + c;
-            o.m0 = mr[0];
-            o.m1 = mr[F];
-            o.m2 = mr[2 * F];
-            const float* __restrict__ gr = g_mu + (size_t)row * (3 * F) + c;
-            o.r0 = gr[0];
-            o.r1 = gr[F];
-            o.r2 = gr[2 * F];
+            m0 = mr[0];
+            m1 = mr[F];
+            m2 = mr[2 * F];
         }
     };
-    load_own(own, j);
-    float gxa = 0.f, gxb = 0.f, gxc = 0.f, gm0 = 0.f, gm1 = 0.f, gm2 = 0.f;
-    auto flush_advance = [&]() {
-        float* __restrict__ gx = g_x + (size_t)j * (3 * F) + c;
-        gx[0] = gxa;
-        gx[F] = gxb;
-        gx[2 * F] = gxc;
+    auto flush = [&](int row) {
+        const size_t o = (size_t)row * 3 * F + c;
+        g_x[o] = gxa;
+        g_x[o + F] = gxb;
+        g_x[o + 2 * F] = gxc;
         if (HAS_MU) {
-            float* __restrict__ gm = g_mu_in + (size_t)j * (3 * F) + c;
-            gm[0] = own.r0 + gm0;
-            gm[F] = own.r1 + gm1;
-            gm[2 * F] = own.r2 + gm2;
+            g_mu_in[o] = g_mu[o] + gm0;
+            g_mu_in[o + F] = g_mu[o + F] + gm1;
+            g_mu_in[o + 2 * F] = g_mu[o + 2 * F] + gm2;
         }
         gxa = gxb = gxc = gm0 = gm1 = gm2 = 0.f;
-        ++j;
-        next_boundary = boundary2;
-        boundary2 = sptr[min(j + 2, n_atoms)];
-        if (j < j_hi) load_own(own, j);
     };
-
-    // software pipeline: receiver-gradient rows of edge p+PBD-1 are requested before edge p is processed
-    struct Gather { float gq, g0, g1, g2; };
-    Gather ring[PBD];
-    auto issue = [&](Gather& g, int i) {
-        g.gq = g_q[(size_t)i * F + c];
-        const float* __restrict__ gmi = g_mu + (size_t)i * (3 * F) + c;
-        g.g0 = gmi[0];
-        g.g1 = gmi[F];
-        g.g2 = gmi[2 * F];
-    };
-#pragma unroll
-    for (int d = 0; d < PBD - 1; ++d)
-        if (p_begin + d < p_end) issue(ring[d], __ldg(pos_i + p_begin + d));
-    int i_next = (p_begin + PBD - 1 < p_end) ? __ldg(pos_i + p_begin + PBD - 1) : 0;
+    load_own(j);
+    // value index held by this lane after the butterfly: edge (idx >> 2) of the group, scalar (idx & 3)
+    const int my_idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
 
     for (int cs = p_begin; cs < p_end; cs += CH) {
         const int n = min(CH, p_end - cs);
@@ -267,79 +252,91 @@ __global__ void __launch_bounds__(NW * 32, 512 / (NW * 32)) k_painn_edge_bwd(
             int s = pos_slot[cs + r];
             reinterpret_cast<float4*>(s_geo)[t] = reinterpret_cast<const float4*>(geo + (int64_t)s * SPK_GEO_STRIDE)[t & 1];
         }
-        for (int t = threadIdx.x; t < n; t += NTHR) s_eid[t] = slot_eid[pos_slot[cs + t]];
+        for (int t = threadIdx.x; t < n; t += NTHR) {
+            s_i[t] = pos_i[cs + t];
+            s_eid[t] = slot_eid[pos_slot[cs + t]];
+        }
         __syncthreads();
 
-        for (int t0 = 0; t0 < n; t0 += PBD) {
+        for (int t0 = 0; t0 < n; t0 += 4) {
+            float red[16];
 #pragma unroll
-          for (int u = 0; u < PBD; ++u) {
-            const int t = t0 + u;
-            if (t >= n) continue;
-            const int p = cs + t;
-            if (p + PBD - 1 < p_end) issue(ring[(u + PBD - 1) % PBD], i_next);
-            if (p + PBD < p_end) i_next = __ldg(pos_i + p + PBD);
-            while (p >= next_boundary) flush_advance();
-            const float xa = own.xa, xb = own.xb, xc = own.xc, m0 = own.m0, m1 = own.m1, m2 = own.m2;
-            const float gq = ring[u].gq, g0 = ring[u].g0, g1 = ring[u].g1, g2 = ring[u].g2;
-            const float4 ge = *reinterpret_cast<const float4*>(s_geo + t * SPK_GEO_STRIDE);   // ux uy uz d
-            const float fc = s_geo[t * SPK_GEO_STRIDE + 4], dfc = s_geo[t * SPK_GEO_STRIDE + 5];
-            float2 pa2 = make_float2(w.ba, 0.f), pb2 = make_float2(w.bb, 0.f), pc2 = make_float2(w.bc, 0.f);
-            float2 da2 = make_float2(0.f, 0.f), db2 = da2, dc2 = da2;
-            const float4* __restrict__ ph = reinterpret_cast<const float4*>(s_phi + t * NRB);
-            const float4* __restrict__ dh = reinterpret_cast<const float4*>(s_dphi + t * NRB);
+            for (int u = 0; u < 4; ++u) {
+                const int t = t0 + u;
+                float part_d = 0.f, pu0 = 0.f, pu1 = 0.f, pu2 = 0.f;
+                if (t < n) {
+                    const int p = cs + t;
+                    if (p >= next_boundary) {
+                        do {
+                            flush(j);
+                            ++j;
+                            next_boundary = sptr[j + 1];
+                        } while (p >= next_boundary);
+                        load_own(j);
+                    }
+                    const int i = s_i[t];
+                    const float gq = g_q[(size_t)i * F + c];
+                    const float* __restrict__ gmi = g_mu + (size_t)i * (3 * F) + c;
+                    const float g0 = gmi[0], g1 = gmi[F], g2 = gmi[2 * F];
+                    const float4 ge = *reinterpret_cast<const float4*>(s_geo + t * SPK_GEO_STRIDE);   // ux uy uz d
+                    const float fc = s_geo[t * SPK_GEO_STRIDE + 4], dfc = s_geo[t * SPK_GEO_STRIDE + 5];
+                    float2 pa2 = make_float2(w.ba, 0.f), pb2 = make_float2(w.bb, 0.f), pc2 = make_float2(w.bc, 0.f);
+                    float2 da2 = make_float2(0.f, 0.f), db2 = da2, dc2 = da2;
+                    const float4* __restrict__ ph = reinterpret_cast<const float4*>(s_phi + t * NRB);
+                    const float4* __restrict__ dh = reinterpret_cast<const float4*>(s_dphi + t * NRB);
 #pragma unroll
-            for (int k4 = 0; k4 < NRB / 4; ++k4) {
-                const float4 p4 = ph[k4];
-                const float4 d4 = dh[k4];
-                const float2 p01 = make_float2(p4.x, p4.y), p23 = make_float2(p4.z, p4.w);
-                const float2 d01 = make_float2(d4.x, d4.y), d23 = make_float2(d4.z, d4.w);
-                pa2 = __ffma2_rn(p01, w.a[2 * k4], pa2);
-                da2 = __ffma2_rn(d01, w.a[2 * k4], da2);
-                pb2 = __ffma2_rn(p01, w.b[2 * k4], pb2);
-                db2 = __ffma2_rn(d01, w.b[2 * k4], db2);
-                pa2 = __ffma2_rn(p23, w.a[2 * k4 + 1], pa2);
-                da2 = __ffma2_rn(d23, w.a[2 * k4 + 1], da2);
-                pb2 = __ffma2_rn(p23, w.b[2 * k4 + 1], pb2);
-                db2 = __ffma2_rn(d23, w.b[2 * k4 + 1], db2);
-                if (HAS_MU) {
-                    pc2 = __ffma2_rn(p01, w.c[2 * k4], pc2);
-                    dc2 = __ffma2_rn(d01, w.c[2 * k4], dc2);
-                    pc2 = __ffma2_rn(p23, w.c[2 * k4 + 1], pc2);
-                    dc2 = __ffma2_rn(d23, w.c[2 * k4 + 1], dc2);
+                    for (int k4 = 0; k4 < NRB / 4; ++k4) {
+                        const float4 p4 = ph[k4];
+                        const float4 d4 = dh[k4];
+                        const float2 p01 = make_float2(p4.x, p4.y), p23 = make_float2(p4.z, p4.w);
+                        const float2 d01 = make_float2(d4.x, d4.y), d23 = make_float2(d4.z, d4.w);
+                        pa2 = __ffma2_rn(p01, w.a[2 * k4], pa2);
+                        da2 = __ffma2_rn(d01, w.a[2 * k4], da2);
+                        pb2 = __ffma2_rn(p01, w.b[2 * k4], pb2);
+                        db2 = __ffma2_rn(d01, w.b[2 * k4], db2);
+                        pa2 = __ffma2_rn(p23, w.a[2 * k4 + 1], pa2);
+                        da2 = __ffma2_rn(d23, w.a[2 * k4 + 1], da2);
+                        pb2 = __ffma2_rn(p23, w.b[2 * k4 + 1], pb2);
+                        db2 = __ffma2_rn(d23, w.b[2 * k4 + 1], db2);
+                        if (HAS_MU) {
+                            pc2 = __ffma2_rn(p01, w.c[2 * k4], pc2);
+                            dc2 = __ffma2_rn(d01, w.c[2 * k4], dc2);
+                            pc2 = __ffma2_rn(p23, w.c[2 * k4 + 1], pc2);
+                            dc2 = __ffma2_rn(d23, w.c[2 * k4 + 1], dc2);
+                        }
+                    }
+                    const float pa = pa2.x + pa2.y, pb = pb2.x + pb2.y, pc = pc2.x + pc2.y;
+                    const float da = da2.x + da2.y, db = db2.x + db2.y, dc = dc2.x + dc2.y;
+                    const float Wa = fc * pa, Wb = fc * pb;
+                    const float dWa = fmaf(dfc, pa, fc * da), dWb = fmaf(dfc, pb, fc * db);
+                    const float gu = g0 * ge.x + g1 * ge.y + g2 * ge.z;   // sum_d g_mu[i,d] u_d
+                    gxa = fmaf(Wa, gq, gxa);
+                    gxb = fmaf(Wb, gu, gxb);
+                    part_d = gq * xa * dWa + gu * xb * dWb;
+                    const float wbx = Wb * xb;
+                    pu0 = g0 * wbx;
+                    pu1 = g1 * wbx;
+                    pu2 = g2 * wbx;
+                    if (HAS_MU) {
+                        const float Wc = fc * pc;
+                        const float dWc = fmaf(dfc, pc, fc * dc);
+                        const float gm = g0 * m0 + g1 * m1 + g2 * m2;     // sum_d g_mu[i,d] mu[j,d]
+                        gxc = fmaf(Wc, gm, gxc);
+                        const float wcx = Wc * xc;
+                        gm0 = fmaf(wcx, g0, gm0);
+                        gm1 = fmaf(wcx, g1, gm1);
+                        gm2 = fmaf(wcx, g2, gm2);
+                        part_d = fmaf(gm * xc, dWc, part_d);
+                    }
                 }
+                red[4 * u + 0] = part_d;
+                red[4 * u + 1] = pu0;
+                red[4 * u + 2] = pu1;
+                red[4 * u + 3] = pu2;
             }
-            const float pa = pa2.x + pa2.y, pb = pb2.x + pb2.y, pc = pc2.x + pc2.y;
-            const float da = da2.x + da2.y, db = db2.x + db2.y, dc = dc2.x + dc2.y;
-            const float Wa = fc * pa, Wb = fc * pb;
-            const float dWa = fmaf(dfc, pa, fc * da), dWb = fmaf(dfc, pb, fc * db);
-            const float gu = g0 * ge.x + g1 * ge.y + g2 * ge.z;   // sum_d g_mu[i,d] u_d
-            gxa = fmaf(Wa, gq, gxa);
-            gxb = fmaf(Wb, gu, gxb);
-            float part_d = gq * xa * dWa + gu * xb * dWb;
-            const float wbx = Wb * xb;
-            float pu0 = g0 * wbx, pu1 = g1 * wbx, pu2 = g2 * wbx;
-            if (HAS_MU) {
-                const float Wc = fc * pc;
-                const float dWc = fmaf(dfc, pc, fc * dc);
-                const float gm = g0 * m0 + g1 * m1 + g2 * m2;     // sum_d g_mu[i,d] mu[j,d]
-                gxc = fmaf(Wc, gm, gxc);
-                const float wcx = Wc * xc;
-                gm0 = fmaf(wcx, g0, gm0);
-                gm1 = fmaf(wcx, g1, gm1);
-                gm2 = fmaf(wcx, g2, gm2);
-                part_d = fmaf(gm * xc, dWc, part_d);
-            }
-            part_d = spk_warp_sum(part_d);
-            pu0 = spk_warp_sum(pu0);
-            pu1 = spk_warp_sum(pu1);
-            pu2 = spk_warp_sum(pu2);
-            if (lane == 0) {
-                s_red[t][warp][0] = part_d;
-                s_red[t][warp][1] = pu0;
-                s_red[t][warp][2] = pu1;
-                s_red[t][warp][3] = pu2;
-            }
-          }
+            const float tot = butterfly16(red, lane);
+            const int te = t0 + (my_idx >> 2);
+            if (!(lane & 1) && te < n) s_red[te][warp][my_idx & 3] = tot;
         }
         __syncthreads();
         if (threadIdx.x < n) {
@@ -369,7 +366,7 @@ __global__ void __launch_bounds__(NW * 32, 512 / (NW * 32)) k_painn_edge_bwd(
             out[2] = r2;
         }
     }
-    while (j < j_hi) flush_advance();
+    for (; j < j_hi; ++j) flush(j);
 }
 
 // ------------------------------------------------------------------------------------------------------------------

@@ -127,6 +127,8 @@ def painn_backward(pk: PaiNNPack, saved, graph: ops.EdgeGraph, n_rbf: int, act: 
         # --- interaction (painn.py:54-65) reversed
         g_x, g_mu0 = ops.painn_edge_bwd(x, mu_in, g_q1, g_mu1, phi, dphi, geo, graph, pk.wf[t], pk.bf[t], F, n_rbf,
                                         g_rij, accumulate=(t != pk.T - 1), erec=erec, mol_ptr=mol_ptr, n_mol=n_mol)
+        if t == 0:
+            break   # dE/dq0 would only reach the (position-independent) embedding: the first context net is not reversed
         g_a = b["c1"].bwd(g_x)                                                               # [N,3F]x[3F,F]
         g_q = b["c0"].bwd(g_a, a_pre=hpre, a_act=act, addend=g_q1)                           # [N,F]x[F,F] + residual
         g_mu = g_mu0
@@ -215,6 +217,8 @@ def schnet_backward(pk: SchNetPack, saved, graph: ops.EdgeGraph, n_rbf: int, act
         g_phi = torch.empty((E, KP), dtype=torch.float32, device=dev)
         b["f0"].bwd(g_w0, a_pre=w0pre, a_act=act, out=g_phi)                                 # [E,NF]x[NF,n_rbf]
         ops.radial_bwd(g_phi, g_fc, dphi, geo, graph, n_rbf, g_rij, accumulate=(t != pk.T - 1))
+        if t == 0:
+            break   # the gradient w.r.t. the embedding output is not needed for forces
         g_x = b["in2f"].bwd(g_h, addend=g_x)                                                 # + residual
     return g_rij
 
