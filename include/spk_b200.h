@@ -34,6 +34,9 @@ typedef void* spk_stream_t; /* cudaStream_t */
 #define SPK_ACT_NONE 0
 #define SPK_ACT_SILU 1 /* torch.nn.functional.silu            (PaiNN, Atomwise)  */
 #define SPK_ACT_SSP 2  /* nn/activations.py:9-22 shifted_softplus (SchNet)        */
+#define SPK_ACT_GIVEN 3      /* a_act only: a_pre already holds act'(pre) (saved by the forward layer, see below)  */
+#define SPK_SAVE_DERIV 0x10  /* OR-ed into `act`: y_pre receives act'(pre) instead of the pre-activation, so the input-
+                              * gradient layer multiplies by it without re-evaluating exp() (a_act = SPK_ACT_GIVEN)  */
 
 #define SPK_RBF_GAUSSIAN 0 /* nn/radial.py:11-48  */
 #define SPK_RBF_BESSEL 1   /* nn/radial.py:82-110 */

@@ -13,7 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libspk_b200.so")
 
 SPK_OK = 0
-ACT_NONE, ACT_SILU, ACT_SSP = 0, 1, 2
+ACT_NONE, ACT_SILU, ACT_SSP, ACT_GIVEN = 0, 1, 2, 3
+SAVE_DERIV = 0x10
 RBF_GAUSSIAN, RBF_BESSEL = 0, 1
 GEO_STRIDE = 8
 

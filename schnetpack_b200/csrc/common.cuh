@@ -58,6 +58,21 @@ __device__ __forceinline__ float spk_act_grad(float x, int act) {
     return 1.0f;
 }
 
+// activation value and derivative sharing one exp()
+__device__ __forceinline__ void spk_act_both(float x, int act, float& y, float& dy) {
+    if (act == SPK_ACT_SILU) {
+        const float s = 1.0f / (1.0f + expf(-x));
+        y = x * s;
+        dy = s * (1.0f + x * (1.0f - s));
+    } else if (act == SPK_ACT_SSP) {
+        y = spk_ssp(x);
+        dy = spk_ssp_grad(x);
+    } else {
+        y = x;
+        dy = 1.0f;
+    }
+}
+
 __device__ __forceinline__ float spk_warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

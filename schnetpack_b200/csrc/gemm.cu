@@ -21,16 +21,22 @@ struct GemmArgs {
     float* Y;
     float* y_pre;
     int64_t M, lda, ld_add, ldy;
-    int K, N, a_act, act;
+    int K, N, a_act, act, save_deriv;
 };
 
 // activation helpers kept out of line and selected at compile time: inlining the runtime-switched expf/log1pf code into
 // the unrolled load / epilogue loops made the kernel 6.3k SASS instructions long and 22 % of its stalls were
 // instruction-cache misses (profiles/r1_ncu_dense.txt)
 template <int ACT>
-__device__ __noinline__ float act_grad1(float q) { return spk_act_grad(q, ACT); }
+__device__ __noinline__ float act_grad1(float q) { return ACT == SPK_ACT_GIVEN ? q : spk_act_grad(q, ACT); }
 template <int ACT>
 __device__ __noinline__ float act1(float v) { return spk_act(v, ACT); }
+template <int ACT>
+__device__ __noinline__ float2 act_both1(float v) {
+    float y, dy;
+    spk_act_both(v, ACT, y, dy);
+    return make_float2(y, dy);
+}
 
 // BM = 128 (256 threads) for tall problems, BM = 64 / 32 when the 128-row grid would not fill the 148 SMs.
 template <int BM, int A_ACT, int ACT>
@@ -174,14 +180,23 @@ __global__ void __launch_bounds__(BM * 2) k_dense(GemmArgs g) {
         float v[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) v[j] = acc[i][j] + bv[j];
-        if (g.y_pre) {
+        if (g.y_pre && g.save_deriv && ACT != SPK_ACT_NONE) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (n + j < g.N) g.y_pre[m * g.ldy + n + j] = v[j];
-        }
-        if (ACT != SPK_ACT_NONE) {
+            for (int j = 0; j < 4; ++j) {
+                const float2 yd = act_both1<ACT>(v[j]);
+                v[j] = yd.x;
+                if (n + j < g.N) g.y_pre[m * g.ldy + n + j] = yd.y;
+            }
+        } else {
+            if (g.y_pre) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] = act1<ACT>(v[j]);
+                for (int j = 0; j < 4; ++j)
+                    if (n + j < g.N) g.y_pre[m * g.ldy + n + j] = (g.save_deriv ? 1.0f : v[j]);
+            }
+            if (ACT != SPK_ACT_NONE) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] = act1<ACT>(v[j]);
+            }
         }
         if (g.addend) {
 #pragma unroll
@@ -204,13 +219,15 @@ extern "C" int spk_dense(const float* A, int64_t M, int K, int64_t lda, const fl
                          int N, const float* bias, int act, const float* addend, int64_t ld_add, float* Y, int64_t ldy,
                          float* y_pre, spk_stream_t stream) {
     if (M < 0 || K <= 0 || N <= 0 || lda < K || ldy < N) return SPK_ERR_ARG;
-    if (act < 0 || act > 2 || a_act < 0 || a_act > 2) return SPK_ERR_ARG;
+    const int save_deriv = (act & SPK_SAVE_DERIV) ? 1 : 0;
+    act &= ~SPK_SAVE_DERIV;
+    if (act < 0 || act > 2 || a_act < 0 || a_act > 3) return SPK_ERR_ARG;
     if (M == 0) return SPK_OK;
     if (!A || !B || !Y) return SPK_ERR_ARG;
     if (addend && ld_add < N) return SPK_ERR_ARG;
     GemmArgs g;
     g.A = A; g.a_pre = a_pre; g.B = B; g.bias = bias; g.addend = addend; g.Y = Y; g.y_pre = y_pre;
-    g.M = M; g.lda = lda; g.ld_add = ld_add; g.ldy = ldy; g.K = K; g.N = N; g.a_act = a_act; g.act = act;
+    g.M = M; g.lda = lda; g.ld_add = ld_add; g.ldy = ldy; g.K = K; g.N = N; g.a_act = a_act; g.act = act; g.save_deriv = save_deriv;
     if (!a_pre) a_act = SPK_ACT_NONE;
     g.a_act = a_act;
     // these layers are skinny (M = atoms): pick the largest row tile that still gives every SM several CTAs, because a
@@ -229,7 +246,9 @@ extern "C" int spk_dense(const float* A, int64_t M, int K, int64_t lda, const fl
     if (a_act == SPK_ACT_NONE) {
         if (act == SPK_ACT_NONE) LAUNCH_BM(0, 0); else if (act == SPK_ACT_SILU) LAUNCH_BM(0, 1); else LAUNCH_BM(0, 2);
     } else if (act == SPK_ACT_NONE) {
-        if (a_act == SPK_ACT_SILU) LAUNCH_BM(1, 0); else LAUNCH_BM(2, 0);
+        if (a_act == SPK_ACT_SILU) LAUNCH_BM(1, 0); else if (a_act == SPK_ACT_SSP) LAUNCH_BM(2, 0); else LAUNCH_BM(3, 0);
+    } else if (a_act == SPK_ACT_GIVEN) {
+        if (act == SPK_ACT_SILU) LAUNCH_BM(3, 1); else LAUNCH_BM(3, 2);
     } else {   // both a backward prologue and a forward activation: rare, compiled for SiLU/ssp pairs of the same kind
         if (a_act == SPK_ACT_SILU && act == SPK_ACT_SILU) LAUNCH_BM(1, 1);
         else if (a_act == SPK_ACT_SSP && act == SPK_ACT_SSP) LAUNCH_BM(2, 2);

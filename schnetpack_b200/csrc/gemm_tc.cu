@@ -126,6 +126,13 @@ __device__ __noinline__ float4 act_grad4(float4 q) {
     return make_float4(spk_act_grad(q.x, ACT), spk_act_grad(q.y, ACT), spk_act_grad(q.z, ACT), spk_act_grad(q.w, ACT));
 }
 template <int ACT>
+__device__ __noinline__ void act_both4(float4& v, float4& d) {
+    spk_act_both(v.x, ACT, v.x, d.x);
+    spk_act_both(v.y, ACT, v.y, d.y);
+    spk_act_both(v.z, ACT, v.z, d.z);
+    spk_act_both(v.w, ACT, v.w, d.w);
+}
+template <int ACT>
 __device__ __noinline__ float4 act4(float4 v) {
     return make_float4(spk_act(v.x, ACT), spk_act(v.y, ACT), spk_act(v.z, ACT), spk_act(v.w, ACT));
 }
@@ -139,7 +146,7 @@ struct TcArgs {
     float* Y;
     float* y_pre;
     int64_t M, lda, ld_add, ldy;
-    int K, N, a_act, act;
+    int K, N, a_act, act, save_deriv;
 };
 
 // byte offset of (row r, 16 B chunk c) inside an operand tile with the given plane stride
@@ -222,7 +229,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dense_tc(TcArgs g) {
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (k_ok && m < g.M) {
                     v = *reinterpret_cast<const float4*>(g.A + m * g.lda + k);
-                    if (A_ACT != SPK_ACT_NONE) {
+                    if (A_ACT == SPK_ACT_GIVEN) {          // a_pre holds act'(pre) saved by the forward layer
+                        const float4 d = *reinterpret_cast<const float4*>(g.a_pre + m * g.lda + k);
+                        v.x *= d.x; v.y *= d.y; v.z *= d.z; v.w *= d.w;
+                    } else if (A_ACT != SPK_ACT_NONE) {
                         const float4 d = act_grad4<A_ACT>(*reinterpret_cast<const float4*>(g.a_pre + m * g.lda + k));
                         v.x *= d.x; v.y *= d.y; v.z *= d.z; v.w *= d.w;
                     }
@@ -323,8 +333,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dense_tc(TcArgs g) {
                         const float4 bv = *reinterpret_cast<const float4*>(g.bias + n);
                         v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
                     }
-                    if (g.y_pre) *reinterpret_cast<float4*>(g.y_pre + m * g.ldy + n) = v;
-                    if (ACT != SPK_ACT_NONE) v = act4<ACT>(v);
+                    if (g.y_pre && g.save_deriv && ACT != SPK_ACT_NONE) {
+                        float4 d;
+                        act_both4<ACT>(v, d);
+                        *reinterpret_cast<float4*>(g.y_pre + m * g.ldy + n) = d;
+                    } else {
+                        if (g.y_pre)
+                            *reinterpret_cast<float4*>(g.y_pre + m * g.ldy + n) =
+                                g.save_deriv ? make_float4(1.f, 1.f, 1.f, 1.f) : v;
+                        if (ACT != SPK_ACT_NONE) v = act4<ACT>(v);
+                    }
                     if (g.addend) {
                         const float4 a = *reinterpret_cast<const float4*>(g.addend + m * g.ld_add + n);
                         v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
@@ -375,7 +393,9 @@ extern "C" int spk_dense_tc(const float* A, int64_t M, int K, int64_t lda, const
                             const float* W_packed, int N, const float* bias, int act, const float* addend,
                             int64_t ld_add, float* Y, int64_t ldy, float* y_pre, spk_stream_t stream) {
     if (M < 0 || K <= 0 || N <= 0 || lda < K || ldy < N) return SPK_ERR_ARG;
-    if (act < 0 || act > 2 || a_act < 0 || a_act > 2) return SPK_ERR_ARG;
+    const int save_deriv = (act & SPK_SAVE_DERIV) ? 1 : 0;
+    act &= ~SPK_SAVE_DERIV;
+    if (act < 0 || act > 2 || a_act < 0 || a_act > 3) return SPK_ERR_ARG;
     if (M == 0) return SPK_OK;
     if (!A || !W_packed || !Y) return SPK_ERR_ARG;
     if (addend && ld_add < N) return SPK_ERR_ARG;
@@ -387,13 +407,14 @@ extern "C" int spk_dense_tc(const float* A, int64_t M, int K, int64_t lda, const
     if (!fast) return SPK_ERR_UNSUPPORTED;   // caller falls back to spk_dense (fp32 CUDA-core kernel)
     TcArgs g;
     g.A = A; g.a_pre = a_pre; g.Wp = W_packed; g.bias = bias; g.addend = addend; g.Y = Y; g.y_pre = y_pre;
-    g.M = M; g.lda = lda; g.ld_add = ld_add; g.ldy = ldy; g.K = K; g.N = N; g.a_act = a_act; g.act = act;
+    g.M = M; g.lda = lda; g.ld_add = ld_add; g.ldy = ldy; g.K = K; g.N = N; g.a_act = a_act; g.act = act; g.save_deriv = save_deriv;
     cudaStream_t st = spk_st(stream);
     int rc;
     if (a_act == SPK_ACT_NONE) {
         rc = act == SPK_ACT_NONE ? launch_tc<0, 0>(g, st) : act == SPK_ACT_SILU ? launch_tc<0, 1>(g, st) : launch_tc<0, 2>(g, st);
     } else {
-        rc = a_act == SPK_ACT_SILU ? launch_tc<1, 0>(g, st) : launch_tc<2, 0>(g, st);
+        rc = a_act == SPK_ACT_SILU ? launch_tc<1, 0>(g, st)
+             : a_act == SPK_ACT_SSP ? launch_tc<2, 0>(g, st) : launch_tc<3, 0>(g, st);
     }
     if (rc) return rc;
     SPK_LAUNCH_CHECK();

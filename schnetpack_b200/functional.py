@@ -90,13 +90,13 @@ def painn_forward(pk: PaiNNPack, q0: Tensor, r_ij: Tensor, graph: ops.EdgeGraph,
     tape = []
     for t in range(pk.T):
         b = pk.blocks[t]
-        a, hpre = b["c0"].fwd(q, act, save_pre=True)                                         # painn.py:54
+        a, hpre = b["c0"].fwd(q, act, save_deriv=True)                                         # painn.py:54
         x = b["c1"].fwd(a)
         q1, mu1 = ops.painn_edge_fwd(x, mu, q, phi, geo, graph, pk.wf[t], pk.bf[t], F, n_rbf,   # :55-65
                                      mol_ptr=mol_ptr, n_mol=n_mol)
         VW = b["mix"].fwd(mu1.view(3 * N, F))                                                # :103  [3N,2F]
         ctx = ops.painn_mix_ctx(q1, VW, F, pk.eps)                                           # :104-107
-        c, cpre = b["m0"].fwd(ctx, act, save_pre=True)                                       # :108
+        c, cpre = b["m0"].fwd(ctx, act, save_deriv=True)                                       # :108
         s = b["m1"].fwd(c)
         q2, mu2 = ops.painn_mix_update(q1, mu1, s, VW, F)                                    # :110-116
         if need_grad:
@@ -121,7 +121,7 @@ def painn_backward(pk: PaiNNPack, saved, graph: ops.EdgeGraph, n_rbf: int, act: 
         # --- mixing (painn.py:103-116) reversed
         g_s, g_VW = ops.painn_mix_update_bwd(g_q, g_mu, s, VW, F)
         g_c = b["m1"].bwd(g_s)                                                               # [N,3F]x[3F,F]
-        g_ctx = b["m0"].bwd(g_c, a_pre=cpre, a_act=act)                                      # [N,F]x[F,2F]
+        g_ctx = b["m0"].bwd(g_c, a_pre=cpre, a_act=ops.ACT_GIVEN)                                      # [N,F]x[F,2F]
         g_q1 = ops.painn_mix_ctx_bwd(g_ctx, g_q, VW, g_VW, F, pk.eps)
         g_mu1 = b["mix"].bwd(g_VW.view(3 * N, 2 * F), addend=g_mu.view(3 * N, F)).view(N, 3, F)
         # --- interaction (painn.py:54-65) reversed
@@ -130,7 +130,7 @@ def painn_backward(pk: PaiNNPack, saved, graph: ops.EdgeGraph, n_rbf: int, act: 
         if t == 0:
             break   # dE/dq0 would only reach the (position-independent) embedding: the first context net is not reversed
         g_a = b["c1"].bwd(g_x)                                                               # [N,3F]x[3F,F]
-        g_q = b["c0"].bwd(g_a, a_pre=hpre, a_act=act, addend=g_q1)                           # [N,F]x[F,F] + residual
+        g_q = b["c0"].bwd(g_a, a_pre=hpre, a_act=ops.ACT_GIVEN, addend=g_q1)                           # [N,F]x[F,F] + residual
         g_mu = g_mu0
     return g_rij
 
@@ -188,10 +188,10 @@ def schnet_forward(pk: SchNetPack, x0: Tensor, r_ij: Tensor, graph: ops.EdgeGrap
     for t in range(pk.T):
         b = pk.blocks[t]
         h = b["in2f"].fwd(x)                                                                 # schnet.py:60
-        w0, w0pre = b["f0"].fwd(phi, act, save_pre=True, k=n_rbf)                            # :61 (phi is [E,KP])
+        w0, w0pre = b["f0"].fwd(phi, act, save_deriv=True, k=n_rbf)                            # :61 (phi is [E,KP])
         w_raw = b["f1"].fwd(w0)                                                              # [E,NF]
         m = ops.cfconv_fwd(h, w_raw, geo, graph, NF)                                         # :62-67
-        v0, v0pre = b["o0"].fwd(m, act, save_pre=True)                                       # :69
+        v0, v0pre = b["o0"].fwd(m, act, save_deriv=True)                                       # :69
         x_new = b["o1"].fwd(v0, addend=x)                                                    # :69 + :168 residual
         if need_grad:
             tape.append((h, w0pre, w_raw, v0pre))
@@ -210,12 +210,12 @@ def schnet_backward(pk: SchNetPack, saved, graph: ops.EdgeGraph, n_rbf: int, act
         b = pk.blocks[t]
         h, w0pre, w_raw, v0pre = tape[t]
         g_v0 = b["o1"].bwd(g_x)                                                              # [N,F]x[F,F]
-        g_m = b["o0"].bwd(g_v0, a_pre=v0pre, a_act=act)                                      # [N,F]x[F,NF]
+        g_m = b["o0"].bwd(g_v0, a_pre=v0pre, a_act=ops.ACT_GIVEN)                                      # [N,F]x[F,NF]
         g_h, g_wraw, g_fc = ops.cfconv_bwd(h, w_raw, geo, g_m, graph, NF)
         g_w0 = b["f1"].bwd(g_wraw)                                                           # [E,NF]x[NF,NF]
         E = g_w0.shape[0]
         g_phi = torch.empty((E, KP), dtype=torch.float32, device=dev)
-        b["f0"].bwd(g_w0, a_pre=w0pre, a_act=act, out=g_phi)                                 # [E,NF]x[NF,n_rbf]
+        b["f0"].bwd(g_w0, a_pre=w0pre, a_act=ops.ACT_GIVEN, out=g_phi)                                 # [E,NF]x[NF,n_rbf]
         ops.radial_bwd(g_phi, g_fc, dphi, geo, graph, n_rbf, g_rij, accumulate=(t != pk.T - 1))
         if t == 0:
             break   # the gradient w.r.t. the embedding output is not needed for forces
@@ -252,7 +252,7 @@ class AtomwiseFunction(torch.autograd.Function):
     def forward(ctx, q, holder):
         pk, idx_m, n_mol, act = holder["pack"], holder["idx_m"], holder["n_mol"], holder["act"]
         qd = q.detach().contiguous()
-        hid, hpre = pk["l0"].fwd(qd, act, save_pre=True)
+        hid, hpre = pk["l0"].fwd(qd, act, save_deriv=True)
         mol_ptr = ops.segment_ptr(idx_m, n_mol) if idx_m is not None else None
         y, energy = ops.atomwise_out(hid, pk["w1"], pk["b1"], mol_ptr, n_mol)
         ctx.holder = dict(pk=pk, hpre=hpre, idx_m=idx_m, act=act, N=q.shape[0])
@@ -275,7 +275,7 @@ class AtomwiseFunction(torch.autograd.Function):
             g_hid = extra if g_hid is None else g_hid + extra
         if g_hid is None:
             return None, None
-        g_q = pk["l0"].bwd(g_hid.contiguous(), a_pre=h["hpre"], a_act=h["act"])
+        g_q = pk["l0"].bwd(g_hid.contiguous(), a_pre=h["hpre"], a_act=ops.ACT_GIVEN)
         return g_q, None
 
 

@@ -165,7 +165,7 @@ class _DenseFn(torch.autograd.Function):
         need = x.requires_grad
         ctx.pre = None
         if need:
-            y, ctx.pre = lin.fwd(x2, code, save_pre=True)
+            y, ctx.pre = lin.fwd(x2, code, save_deriv=True)
         else:
             y = lin.fwd(x2, code)
         ctx.lin = lin
@@ -177,7 +177,7 @@ class _DenseFn(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, g):
         g2 = g.reshape(-1, g.shape[-1]).contiguous()
-        gx = ctx.lin.bwd(g2, a_pre=ctx.pre if ctx.code != ops.ACT_NONE else None, a_act=ctx.code)
+        gx = ctx.lin.bwd(g2, a_pre=ctx.pre if ctx.code != ops.ACT_NONE else None, a_act=ops.ACT_GIVEN)
         return gx.view(*ctx.shp), None, None, None
 
 

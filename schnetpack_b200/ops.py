@@ -13,7 +13,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import ACT_NONE, ACT_SILU, ACT_SSP, GEO_STRIDE, RBF_BESSEL, RBF_GAUSSIAN  # noqa: F401
+from ._lib import ACT_GIVEN, ACT_NONE, ACT_SILU, ACT_SSP, GEO_STRIDE, RBF_BESSEL, RBF_GAUSSIAN, SAVE_DERIV  # noqa: F401
 
 Tensor = torch.Tensor
 
@@ -306,8 +306,12 @@ class Lin:
         ldy = n_out if out is None else out.shape[1]
         return K % 4 == 0 and n_out % 4 == 0 and A.shape[1] % 4 == 0 and ldy % 4 == 0
 
-    def fwd(self, A: Tensor, act: int = ACT_NONE, **kw):
-        """act(A W^T + b) [+ addend]"""
+    def fwd(self, A: Tensor, act: int = ACT_NONE, save_deriv: bool = False, **kw):
+        """act(A W^T + b) [+ addend].  ``save_deriv=True`` returns (Y, act'(pre)): the tensor the input-gradient layer
+        multiplies by (``bwd(G, a_pre=deriv, a_act=ACT_GIVEN)``) without re-evaluating the activation."""
+        if save_deriv:
+            kw["save_pre"] = True
+            act = act | SAVE_DERIV
         if self.w_pk is not None and self._tc_ok(A, self.w.shape[0], kw):
             return dense_tc(A, self.w_pk, self.w.shape[0], self.b, act, **kw)
         return dense(A, self.wt, self.b, act, **kw)

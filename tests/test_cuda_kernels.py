@@ -408,3 +408,35 @@ def _sys_vs_streaming(gen):
         assert rel(gxb, gxa) < 2e-6 and rel(rb, ra) < 5e-6
         if mu is not None:
             assert rel(gmb, gma) < 2e-6
+
+
+@pytest.mark.parametrize("impl", ["tc", "ffma"])
+def test_lin_saved_derivative_backward(impl):
+    """Lin.fwd(save_deriv=True) stores act'(pre) (SPK_SAVE_DERIV); Lin.bwd(a_act=ACT_GIVEN) multiplies by it: together they
+    are the input gradient of act(x W^T + b)."""
+    from schnetpack_b200 import ops
+
+    old = ops.DENSE_IMPL
+    ops.DENSE_IMPL = impl
+    try:
+        torch.manual_seed(5)
+        M, K, N = 700, 128, 256
+        X = torch.randn(M, K, device=DEV)
+        W = torch.randn(N, K, device=DEV) / math.sqrt(K)
+        b = torch.randn(N, device=DEV)
+        G = torch.randn(M, N, device=DEV)
+        lin = ops.Lin(W, b)
+        for act, f in ((ops.ACT_SILU, torch.nn.functional.silu),
+                       (ops.ACT_SSP, lambda v: torch.nn.functional.softplus(v) - math.log(2.0))):
+            Y, d = lin.fwd(X, act, save_deriv=True)
+            x64 = X.double().requires_grad_()
+            pre = x64 @ W.double().t() + b.double()
+            y64 = f(pre)
+            assert rel(Y, y64) < 3e-6
+            dref = torch.autograd.grad(y64.sum(), pre, retain_graph=True)[0]
+            assert rel(d, dref) < 3e-6
+            gx_ref = torch.autograd.grad((y64 * G.double()).sum(), x64)[0]
+            gx = lin.bwd(G, a_pre=d, a_act=ops.ACT_GIVEN)
+            assert rel(gx, gx_ref) < 5e-6
+    finally:
+        ops.DENSE_IMPL = old
