@@ -12,41 +12,64 @@
 //     FRESH accumulator that is drained into fp32 registers and summed there with IEEE round-to-nearest, while the small
 //     lo products accumulate over all of K in a separate TMEM accumulator (their truncation error is 2^-12 smaller).
 //
-// Warp-specialised pipeline, one CTA (13 warps) per 128 x 64 output tile, cta_group::1, UMMA 128 x 64 x 8:
-//   warps 5-12 producers: producer p owns shared-memory stage p, i.e. K-tiles p, p+8, ...  Lane 0 arms full[stage] with the byte count of the
-//              weight tile and issues ONE TMA bulk copy (cp.async.bulk) of the pre-packed W_hi|W_lo operand tile (the
-//              weights are static, so the host packs them once in the exact shared-memory operand layout,
-//              spk_tc_pack_weight); all lanes load the A tile with coalesced 128-bit loads (optional backward prologue
-//              x act'(a_pre)), split hi/lo in registers and st.shared it in the canonical K-major no-swizzle core-matrix
-//              layout (8 rows x 16 B cores, LBO = plane stride between 16 B K-chunks, SBO = 128 B between 8-row
-//              groups); fence.proxy.async; arrive on full[stage];
-//   warp 4     MMA issuer (one lane): waits full[stage] and acc_empty[buf], issues 6 tcgen05.mma.kind::tf32, then
+// Measured on B200 (tools/tc_trace.cu, clock64 phase stamps): one tcgen05.mma.kind::tf32 with M = 128 takes ~130 cycles for
+// every N <= 256, from shared memory or from TMEM alike, so a CTA's K-loop is a serial chain of 3 * K/8 MMAs and the
+// tensor-pipe work of a GEMM is proportional to the NUMBER of MMAs.  Hence the widest tile that still fills the GPU:
+// TN = 128 columns when N >= 256, 64 otherwise.
+//
+// Warp-specialised pipeline, one CTA per 128 x TN output tile, cta_group::1, UMMA 128 x TN x 8:
+//   warps 9..  producers: K-tile kt belongs to warp kt % NPROD and stage kt % NST (NPROD divides NST).  Lane 0 arms
+//              full[stage] with the byte count of the weight tile and issues ONE TMA bulk copy (cp.async.bulk) of the
+//              pre-packed W_hi|W_lo operand tile (the weights are static, so the host packs them once in the exact
+//              shared-memory operand layout, spk_tc_pack_weight); all lanes load the A tile with coalesced 128-bit loads
+//              (optional backward prologue x act'(a_pre)), split hi/lo in registers and st.shared it K-major with the
+//              64-byte swizzle (row = 64 B, 8-row atoms of 512 B, 16 B chunk index XOR row bits [1,3));
+//              fence.proxy.async; arrive on full[stage];
+//   warp 8     MMA issuer (one lane): waits full[stage] and acc_empty[buf], issues 6 tcgen05.mma.kind::tf32, then
 //              tcgen05.commit -> empty[stage] and -> acc_full[buf];
-//   warps 0-3  drain + epilogue: tcgen05.ld.32x32b.x32 of the main accumulator buffer (thread = output row), fp32 add into
-//              64 register accumulators, arrive acc_empty[buf]; after the last K-tile add the correction accumulator,
-//              apply bias / activation / addend, store.
-// Eight shared-memory stages (24 KB each) and two main TMEM buffers let loads, MMAs and drains of different K-tiles overlap;
-// 128 x 64 tiles double the CTA count of these skinny problems (M = atoms) and keep every role under 128 registers.
+//   warps 0-7  drain: warp w reads TMEM lane quarter w % 4 (thread = output row), column half w / 4, with
+//              tcgen05.ld.32x32b.x32, adds into fp32 registers, arrives acc_empty[buf]; after the last K-tile adds the
+//              correction accumulator and stages the raw tile in shared memory (the pipeline stages are free by then);
+//   all warps  epilogue: bias / activation (+ saved derivative) / addend / stores, 16 B per thread, whole 128 B lines
+//              per row segment (a thread-per-row epilogue kept only 4 warps busy and cost up to 60 % of the kernel).
 #include "common.cuh"
 
 namespace {
 
 constexpr int TM = 128;                        // rows per CTA tile (UMMA M)
-constexpr int TN = 64;                         // columns per CTA tile (UMMA N)
 constexpr int TK = 16;                         // floats per K-tile = 2 UMMA k-steps
-constexpr int NST = 8;                         // shared-memory stages
-constexpr int NPROD = NST;                     // producer warps: warp p owns stage p, so the uses of a stage are strictly
-                                               // ordered (a parity wait cannot tell phase u from phase u+2)
-constexpr int PLANE_A = (TM / 8) * 128 + 16;   // bytes between consecutive 16 B K-chunks of the A tile (LBO), padded
-constexpr int PLANE_B = (TN / 8) * 128 + 16;   // same for the weight tile
-constexpr int OPER_A = (TK / 4) * PLANE_A;     // 8256 B
-constexpr int OPER_B = (TK / 4) * PLANE_B;     // 4160 B
-constexpr int STAGE_BYTES = 2 * OPER_A + 2 * OPER_B;   // A_hi, A_lo, W_hi, W_lo
-constexpr int SMEM_BYTES = NST * STAGE_BYTES;
-constexpr int W_MMA = 4;                       // warps 0-3 drain/epilogue, 4 MMA, 5.. producers
-constexpr int W_PROD0 = 5;
-constexpr int NTHREADS = (W_PROD0 + NPROD) * 32;
-constexpr int TMEM_COLS = 256;                 // main[0] | main[1] | corr | (unused)
+constexpr int N_DRAIN = 8;                     // drain warps 0-7
+constexpr int W_MMA = 8;
+constexpr int W_PROD0 = 9;
+constexpr int OPER_A = TM * TK * 4;            // 8192 B: A tile, K-major, SWIZZLE_64B
+constexpr int SBO_BYTES = 8 * TK * 4;          // 512 B between consecutive 8-row groups
+
+template <int TN>
+struct Cfg {
+    static constexpr int NST = TN == 64 ? 7 : 6;           // shared-memory stages (16 / 15 warps: 128 registers each)
+    static constexpr int NPROD = NST;                       // producer warps; NPROD divides NST, so all uses of a stage belong
+                                                            // to ONE warp and are strictly ordered (a parity wait cannot
+                                                            // tell phase u from phase u+2)
+    static constexpr int OPER_B = TN * TK * 4;              // weight tile, same layout as the A tile
+    static constexpr int STAGE_BYTES = 2 * OPER_A + 2 * OPER_B;   // A_hi, A_lo, W_hi, W_lo
+    static constexpr int EP_LD = TN + 4;                    // padded row of the epilogue staging tile (floats)
+    static constexpr int SMEM_BYTES = NST * STAGE_BYTES + 1024;   // + slack to align the stages to 1024 B
+    static constexpr int NTHREADS = (W_PROD0 + NPROD) * 32;
+    static constexpr int TMEM_COLS = TN == 64 ? 256 : 512;  // main[0] | main[1] | corr | (unused)
+    static constexpr int CW = TN / 2;                       // columns drained by one warp
+    static_assert(NST * STAGE_BYTES >= TM * EP_LD * 4, "epilogue staging tile reuses the pipeline stages");
+    static_assert(NST % NPROD == 0, "a stage must be owned by exactly one producer warp");
+};
+
+#ifdef SPK_TC_TRACE
+#define TRACE(slot)                                                                                     \
+    do {                                                                                                \
+        if (g.dbg && (threadIdx.x & 31) == 0)                                                           \
+            g.dbg[((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * 128 + (slot)] = clock64();           \
+    } while (0)
+#else
+#define TRACE(slot) do { } while (0)
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -83,10 +106,10 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                  : "memory");
 }
 
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t plane) {
-    // K-major, SWIZZLE_NONE: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout 0 [61,64)
-    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(plane >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) |
-           (1ull << 46);
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    // K-major, SWIZZLE_64B: start>>4 [0,14) | LBO (unused, 1) [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout 4 [61,64)
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(SBO_BYTES >> 4) << 32) | (1ull << 46) |
+           (4ull << 61);
 }
 
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
@@ -118,42 +141,46 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// activation (gradient) helpers kept out of line: the producer / epilogue loops are fully unrolled over register
-// arrays, inlining expf/log1pf 64x per loop blew the kernel up to 26k SASS instructions and it stalled on the
-// instruction cache (ncu: stall_no_inst 30 %)
+// activation-gradient helper kept out of line: the producer loop is fully unrolled over a register array, inlining
+// expf/log1pf 16x blew the kernel up and it stalled on the instruction cache (ncu: stall_no_inst 30 %)
 template <int ACT>
 __device__ __noinline__ float4 act_grad4(float4 q) {
     return make_float4(spk_act_grad(q.x, ACT), spk_act_grad(q.y, ACT), spk_act_grad(q.z, ACT), spk_act_grad(q.w, ACT));
-}
-template <int ACT>
-__device__ __noinline__ void act_both4(float4& v, float4& d) {
-    spk_act_both(v.x, ACT, v.x, d.x);
-    spk_act_both(v.y, ACT, v.y, d.y);
-    spk_act_both(v.z, ACT, v.z, d.z);
-    spk_act_both(v.w, ACT, v.w, d.w);
-}
-template <int ACT>
-__device__ __noinline__ float4 act4(float4 v) {
-    return make_float4(spk_act(v.x, ACT), spk_act(v.y, ACT), spk_act(v.z, ACT), spk_act(v.w, ACT));
 }
 
 struct TcArgs {
     const float* A;
     const float* a_pre;
-    const float* Wp;   // packed weights: [ceil(N/64)][ceil(K/16)][W_hi tile | W_lo tile] in operand layout
+    const float* Wp;   // packed weights: [ceil(N/TN)][ceil(K/16)][W_hi tile | W_lo tile] in operand layout
     const float* bias;
     const float* addend;
     float* Y;
     float* y_pre;
     int64_t M, lda, ld_add, ldy;
     int K, N, a_act, act, save_deriv;
+#ifdef SPK_TC_TRACE
+    long long* dbg;
+#endif
 };
 
-// byte offset of (row r, 16 B chunk c) inside an operand tile with the given plane stride
-__host__ __device__ __forceinline__ int tile_off(int r, int c, int plane) { return c * plane + (r >> 3) * 128 + (r & 7) * 16; }
+// byte offset of (row r, 16 B K-chunk c in 0..3) inside an operand tile: rows are 64 B, groups of 8 rows are 512 B atoms and
+// the chunk index is XOR-swizzled with bits [1,3) of the row (Swizzle<2,4,3>, the pattern the tensor core applies to the
+// byte address when the descriptor says SWIZZLE_64B).  Tiles are 512 B aligned.
+__host__ __device__ __forceinline__ int tile_off(int r, int c) {
+    return (r >> 3) * SBO_BYTES + (r & 7) * (TK * 4) + ((c ^ ((r >> 1) & 3)) << 4);
+}
+
+// column-tile width for a layer with N outputs (the packed-weight layout depends on it)
+__host__ __device__ __forceinline__ int tile_n(int N) {
+#ifdef TC_FORCE_TN
+    return TC_FORCE_TN;
+#else
+    return (N >= 256 && N % 128 == 0) ? 128 : 64;
+#endif
+}
 
 // one-time packing of a weight matrix W [N,K] into per-(n-tile, k-tile) operand tiles [hi | lo]
-__global__ void k_pack_weight(const float* __restrict__ W, int N, int K, float* __restrict__ out) {
+__global__ void k_pack_weight(const float* __restrict__ W, int N, int K, int TN, float* __restrict__ out) {
     const int nkt = (K + TK - 1) / TK;
     const int64_t total = (int64_t)((N + TN - 1) / TN) * nkt * TN * TK;
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -165,17 +192,22 @@ __global__ void k_pack_weight(const float* __restrict__ W, int N, int K, float* 
     const int n = nt * TN + r, k = kt * TK + kk;
     const float w = (n < N && k < K) ? W[(int64_t)n * K + k] : 0.f;
     const float hi = tf32_rn(w), lo = w - hi;
-    float* tile = out + ((int64_t)nt * nkt + kt) * (2 * OPER_B / 4);
-    const int off = tile_off(r, kk >> 2, PLANE_B) / 4 + (kk & 3);
+    const int oper_b = TN * TK;                               // floats per operand tile
+    float* tile = out + ((int64_t)nt * nkt + kt) * (2 * oper_b);
+    const int off = tile_off(r, kk >> 2) / 4 + (kk & 3);
     tile[off] = hi;
-    tile[OPER_B / 4 + off] = lo;
+    tile[oper_b + off] = lo;
 }
 
-// Fast-path requirements (checked by the dispatcher, otherwise the fp32 kernel runs): lda, ldy, ld_add, K multiples of 4
+// Fast-path requirements (checked by the dispatcher, otherwise the fp32 kernel runs): lda, ldy, ld_add, K, N multiples of 4
 // and 16 B-aligned base pointers.
-template <int A_ACT, int ACT>
-__global__ void __launch_bounds__(NTHREADS, 1) k_dense_tc(TcArgs g) {
-    extern __shared__ __align__(128) uint8_t smem[];
+template <int TN, int A_ACT, int ACT>
+__global__ void __launch_bounds__(Cfg<TN>::NTHREADS, 1) k_dense_tc(TcArgs g) {
+    using C = Cfg<TN>;
+    constexpr int NST = C::NST, NPROD = C::NPROD, OPER_B = C::OPER_B, STAGE_BYTES = C::STAGE_BYTES, EP_LD = C::EP_LD,
+                  NTHREADS = C::NTHREADS, TMEM_COLS = C::TMEM_COLS, CW = C::CW;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     __shared__ __align__(8) uint64_t full_bar[NST];
     __shared__ __align__(8) uint64_t empty_bar[NST];
     __shared__ __align__(8) uint64_t acc_full[2];
@@ -183,11 +215,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dense_tc(TcArgs g) {
     __shared__ uint32_t s_tmem;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) TRACE(0);
     const int64_t m0 = (int64_t)blockIdx.x * TM;
     const int n0 = blockIdx.y * TN;
-    const int bn_real = min(TN, g.N - n0);            // valid columns of this tile
-    const int BN = TN;                                // UMMA N (weight tiles are zero padded to 64 rows)
-    (void)bn_real;
     const int nk = (g.K + TK - 1) / TK;
 
     if (tid == 0) {
@@ -198,8 +228,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dense_tc(TcArgs g) {
         }
         mbar_init(&acc_full[0], 1);
         mbar_init(&acc_full[1], 1);
-        mbar_init(&acc_empty[0], 4);
-        mbar_init(&acc_empty[1], 4);
+        mbar_init(&acc_empty[0], N_DRAIN);
+        mbar_init(&acc_empty[1], N_DRAIN);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == W_MMA) {   // the MMA warp owns the TMEM allocation
@@ -211,6 +241,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dense_tc(TcArgs g) {
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = s_tmem;
+    if (tid == 0) TRACE(1);
 
     if (warp >= W_PROD0) {
         // =========================================== producers ===========================================
@@ -239,6 +270,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dense_tc(TcArgs g) {
                 }
                 av[p] = v;
             }
+            if (kt < 16) TRACE(16 + kt);                       // loads issued
             if (use >= 1) mbar_wait(&empty_bar[s], (use - 1) & 1);      // MMAs that read this stage have retired
             if (lane == 0) {   // weight tile (hi|lo, already in operand layout): one TMA bulk copy
                 mbar_expect_tx(&full_bar[s], 2 * OPER_B);
@@ -250,7 +282,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dense_tc(TcArgs g) {
                 float4 hi, lo;
                 hi.x = tf32_rn(v.x); hi.y = tf32_rn(v.y); hi.z = tf32_rn(v.z); hi.w = tf32_rn(v.w);
                 lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
-                const int off = tile_off(p * 8 + rsub, chunk, PLANE_A);
+                const int off = tile_off(p * 8 + rsub, chunk);
                 *reinterpret_cast<float4*>(st + off) = hi;
                 *reinterpret_cast<float4*>(st + OPER_A + off) = lo;
             }
@@ -258,13 +290,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dense_tc(TcArgs g) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&full_bar[s]);
+            if (kt < 16) TRACE(32 + kt);                       // stage published
         }
     } else if (warp == W_MMA) {
         // =========================================== MMA issuer ===========================================
         if (lane == 0) {
             // instruction descriptor: D=F32 (1<<4), A=B=TF32 (2<<7, 2<<10), K-major, N>>3 at [17,23), M>>4 at [24,29)
             const uint32_t idesc =
-                (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+                (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
             for (int kt = 0; kt < nk; ++kt) {
                 const int s = kt % NST, buf = kt & 1;
                 mbar_wait(&full_bar[s], (kt / NST) & 1);
@@ -275,84 +308,98 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dense_tc(TcArgs g) {
                 const uint32_t d_corr = tmem_base + (uint32_t)(2 * TN);
 #pragma unroll
                 for (int ks = 0; ks < TK / 8; ++ks) {
-                    const uint64_t ah = make_desc(sa + 2 * ks * PLANE_A, PLANE_A);
-                    const uint64_t al = make_desc(sa + OPER_A + 2 * ks * PLANE_A, PLANE_A);
-                    const uint64_t bh = make_desc(sa + 2 * OPER_A + 2 * ks * PLANE_B, PLANE_B);
-                    const uint64_t bl = make_desc(sa + 2 * OPER_A + OPER_B + 2 * ks * PLANE_B, PLANE_B);
+                    const uint64_t ah = make_desc(sa + 32 * ks);                     // k-step = 8 floats = 32 B
+                    const uint64_t al = make_desc(sa + OPER_A + 32 * ks);
+                    const uint64_t bh = make_desc(sa + 2 * OPER_A + 32 * ks);
+                    const uint64_t bl = make_desc(sa + 2 * OPER_A + OPER_B + 32 * ks);
                     umma_tf32(d_corr, al, bh, idesc, (kt | ks) ? 1u : 0u);   // small terms: accumulate over all of K
                     umma_tf32(d_corr, ah, bl, idesc, 1u);
                     umma_tf32(d_main, ah, bh, idesc, ks ? 1u : 0u);          // main term: fresh accumulator per K-tile
                 }
                 umma_commit(&empty_bar[s]);      // stage reusable once these MMAs have read it
                 umma_commit(&acc_full[buf]);     // main buffer (and, after the last tile, the corrections) ready
+                if (kt < 16) TRACE(48 + kt);     // MMAs of this K-tile issued
             }
         }
     } else {
-        // =========================================== drain + epilogue ===========================================
+        // =========================================== drain ===========================================
         const int q = warp & 3;                          // TMEM lane quarter this warp may access
+        const int ch = warp >> 2;                        // column half
         const int row = q * 32 + lane;                   // output row inside the tile == TMEM lane
-        const int64_t m = m0 + row;
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-        float accr[TN];
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * CW);
+        float accr[CW];
 #pragma unroll
-        for (int i = 0; i < TN; ++i) accr[i] = 0.f;
+        for (int i = 0; i < CW; ++i) accr[i] = 0.f;
         for (int kt = 0; kt < nk; ++kt) {
             const int buf = kt & 1;
             mbar_wait(&acc_full[buf], (kt >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (warp == 0 && kt < 16) TRACE(80 + kt);          // accumulator ready
 #pragma unroll
-            for (int c0 = 0; c0 < TN; c0 += 32) {
-                if (c0 < BN) {
-                    uint32_t r[32];
-                    tmem_ld32(lane_addr + (uint32_t)(buf * TN + c0), r);
+            for (int c0 = 0; c0 < CW; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(lane_addr + (uint32_t)(buf * TN + c0), r);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) accr[c0 + j] += __uint_as_float(r[j]);
-                }
+                for (int j = 0; j < 32; ++j) accr[c0 + j] += __uint_as_float(r[j]);
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            if (warp == 0 && kt < 16) TRACE(64 + kt);          // drained
         }
-        // the last acc_full commit also covers every correction MMA
+        // the last acc_full commit also covers every correction MMA, and every MMA has finished reading the stages:
+        // their memory now stages the raw fp32 tile (row-major, padded rows) for the CTA-wide epilogue
+        float* ep = reinterpret_cast<float*>(smem) + row * EP_LD + ch * CW;
 #pragma unroll
-        for (int c0 = 0; c0 < TN; c0 += 32) {
-            if (c0 >= BN) break;
+        for (int c0 = 0; c0 < CW; c0 += 32) {
             uint32_t r[32];
             tmem_ld32(lane_addr + (uint32_t)(2 * TN + c0), r);
-            if (m < g.M) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const int n = n0 + c0 + j;
-                    if (n >= g.N) break;                      // N % 4 == 0: whole float4 groups only
-                    float4 v;
-                    v.x = accr[c0 + j + 0] + __uint_as_float(r[j + 0]);
-                    v.y = accr[c0 + j + 1] + __uint_as_float(r[j + 1]);
-                    v.z = accr[c0 + j + 2] + __uint_as_float(r[j + 2]);
-                    v.w = accr[c0 + j + 3] + __uint_as_float(r[j + 3]);
-                    if (g.bias) {
-                        const float4 bv = *reinterpret_cast<const float4*>(g.bias + n);
-                        v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-                    }
-                    if (g.y_pre && g.save_deriv && ACT != SPK_ACT_NONE) {
-                        float4 d;
-                        act_both4<ACT>(v, d);
-                        *reinterpret_cast<float4*>(g.y_pre + m * g.ldy + n) = d;
-                    } else {
-                        if (g.y_pre)
-                            *reinterpret_cast<float4*>(g.y_pre + m * g.ldy + n) =
-                                g.save_deriv ? make_float4(1.f, 1.f, 1.f, 1.f) : v;
-                        if (ACT != SPK_ACT_NONE) v = act4<ACT>(v);
-                    }
-                    if (g.addend) {
-                        const float4 a = *reinterpret_cast<const float4*>(g.addend + m * g.ld_add + n);
-                        v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
-                    }
-                    *reinterpret_cast<float4*>(g.Y + m * g.ldy + n) = v;
-                }
-            }
+            for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(ep + c0 + j) =
+                    make_float4(accr[c0 + j + 0] + __uint_as_float(r[j + 0]), accr[c0 + j + 1] + __uint_as_float(r[j + 1]),
+                                accr[c0 + j + 2] + __uint_as_float(r[j + 2]), accr[c0 + j + 3] + __uint_as_float(r[j + 3]));
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        if (warp == 0) TRACE(2);                               // tile staged
     }
+    __syncthreads();
+    // =========================================== epilogue: all warps, coalesced ===========================================
+    {
+        const float* ept = reinterpret_cast<const float*>(smem);
+#pragma unroll 1
+        for (int idx = tid; idx < TM * (TN / 4); idx += NTHREADS) {
+            const int row = idx / (TN / 4), c4 = idx % (TN / 4);
+            const int64_t m = m0 + row;
+            const int n = n0 + c4 * 4;
+            if (m >= g.M || n >= g.N) continue;                  // N % 4 == 0: whole float4 groups only
+            float4 v = *reinterpret_cast<const float4*>(ept + row * EP_LD + c4 * 4);
+            if (g.bias) {
+                const float4 bv = *reinterpret_cast<const float4*>(g.bias + n);
+                v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+            }
+            if (g.y_pre && g.save_deriv && ACT != SPK_ACT_NONE) {
+                float4 d;
+                spk_act_both(v.x, ACT, v.x, d.x);
+                spk_act_both(v.y, ACT, v.y, d.y);
+                spk_act_both(v.z, ACT, v.z, d.z);
+                spk_act_both(v.w, ACT, v.w, d.w);
+                *reinterpret_cast<float4*>(g.y_pre + m * g.ldy + n) = d;
+            } else {
+                if (g.y_pre)
+                    *reinterpret_cast<float4*>(g.y_pre + m * g.ldy + n) =
+                        g.save_deriv ? make_float4(1.f, 1.f, 1.f, 1.f) : v;
+                if (ACT != SPK_ACT_NONE)
+                    v = make_float4(spk_act(v.x, ACT), spk_act(v.y, ACT), spk_act(v.z, ACT), spk_act(v.w, ACT));
+            }
+            if (g.addend) {
+                const float4 a = *reinterpret_cast<const float4*>(g.addend + m * g.ld_add + n);
+                v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+            }
+            *reinterpret_cast<float4*>(g.Y + m * g.ldy + n) = v;
+        }
+    }
+    if (tid == 0) TRACE(3);
     __syncthreads();
     if (warp == W_MMA) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -362,29 +409,41 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dense_tc(TcArgs g) {
 
 }  // namespace
 
-template <int A_ACT, int ACT>
+template <int TN, int A_ACT, int ACT>
 static int launch_tc(const TcArgs& g, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_dense_tc<A_ACT, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(k_dense_tc<TN, A_ACT, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             Cfg<TN>::SMEM_BYTES);
         if (e != cudaSuccess) return SPK_CUDA_ERR(e);
         attr_set = true;
     }
     dim3 grid((unsigned)spk_cdiv(g.M, TM), (unsigned)spk_cdiv(g.N, TN));
-    k_dense_tc<A_ACT, ACT><<<grid, NTHREADS, SMEM_BYTES, st>>>(g);
+    k_dense_tc<TN, A_ACT, ACT><<<grid, Cfg<TN>::NTHREADS, Cfg<TN>::SMEM_BYTES, st>>>(g);
     return 0;
 }
 
+template <int TN>
+static int dispatch_tc(const TcArgs& g, cudaStream_t st) {
+    if (g.a_act == SPK_ACT_NONE)
+        return g.act == SPK_ACT_NONE   ? launch_tc<TN, 0, 0>(g, st)
+               : g.act == SPK_ACT_SILU ? launch_tc<TN, 0, 1>(g, st)
+                                       : launch_tc<TN, 0, 2>(g, st);
+    return g.a_act == SPK_ACT_SILU  ? launch_tc<TN, 1, 0>(g, st)
+           : g.a_act == SPK_ACT_SSP ? launch_tc<TN, 2, 0>(g, st)
+                                    : launch_tc<TN, 3, 0>(g, st);
+}
+
 extern "C" size_t spk_tc_packed_floats(int N, int K) {
-    return (size_t)((N + TN - 1) / TN) * ((K + TK - 1) / TK) * (2 * OPER_B / 4);
+    const int TN = tile_n(N);
+    return (size_t)((N + TN - 1) / TN) * ((K + TK - 1) / TK) * (2 * TN * TK);
 }
 
 extern "C" int spk_tc_pack_weight(const float* W, int N, int K, float* packed, spk_stream_t stream) {
     if (N <= 0 || K <= 0 || !W || !packed) return SPK_ERR_ARG;
-    cudaError_t e = cudaMemsetAsync(packed, 0, spk_tc_packed_floats(N, K) * sizeof(float), spk_st(stream));
-    if (e != cudaSuccess) return SPK_CUDA_ERR(e);
+    const int TN = tile_n(N);
     const int64_t total = (int64_t)((N + TN - 1) / TN) * ((K + TK - 1) / TK) * TN * TK;
-    k_pack_weight<<<(unsigned)spk_cdiv(total, 256), 256, 0, spk_st(stream)>>>(W, N, K, packed);
+    k_pack_weight<<<(unsigned)spk_cdiv(total, 256), 256, 0, spk_st(stream)>>>(W, N, K, TN, packed);
     SPK_LAUNCH_CHECK();
     return SPK_OK;
 }
@@ -408,14 +467,11 @@ extern "C" int spk_dense_tc(const float* A, int64_t M, int K, int64_t lda, const
     TcArgs g;
     g.A = A; g.a_pre = a_pre; g.Wp = W_packed; g.bias = bias; g.addend = addend; g.Y = Y; g.y_pre = y_pre;
     g.M = M; g.lda = lda; g.ld_add = ld_add; g.ldy = ldy; g.K = K; g.N = N; g.a_act = a_act; g.act = act; g.save_deriv = save_deriv;
+#ifdef SPK_TC_TRACE
+    g.dbg = nullptr;
+#endif
     cudaStream_t st = spk_st(stream);
-    int rc;
-    if (a_act == SPK_ACT_NONE) {
-        rc = act == SPK_ACT_NONE ? launch_tc<0, 0>(g, st) : act == SPK_ACT_SILU ? launch_tc<0, 1>(g, st) : launch_tc<0, 2>(g, st);
-    } else {
-        rc = a_act == SPK_ACT_SILU ? launch_tc<1, 0>(g, st)
-             : a_act == SPK_ACT_SSP ? launch_tc<2, 0>(g, st) : launch_tc<3, 0>(g, st);
-    }
+    const int rc = tile_n(N) == 128 ? dispatch_tc<128>(g, st) : dispatch_tc<64>(g, st);
     if (rc) return rc;
     SPK_LAUNCH_CHECK();
     return SPK_OK;

@@ -226,6 +226,7 @@ class GraphedPotential:
         self.model = model
         self.warmup = warmup
         self._cache = {}
+        self._last = None
 
     @staticmethod
     def _signature(inputs: Dict[str, torch.Tensor]):
@@ -265,4 +266,16 @@ class GraphedPotential:
         for k, v in inputs.items():
             static_in[k].copy_(v, non_blocking=True)
         graph.replay()
+        self._last = entry
         return static_out
+
+    def replay(self) -> Dict[str, torch.Tensor]:
+        """Re-evaluate the batch that already sits in the static device buffers of the last call (no input copies):
+        the device-resident loop of an MD driver that updates ``_positions`` in place, or a benchmark."""
+        graph, _, static_out = self._last
+        graph.replay()
+        return static_out
+
+    def static_inputs(self) -> Dict[str, torch.Tensor]:
+        """The static device buffers of the last call (write new positions / neighbour lists into them, then ``replay``)."""
+        return self._last[1]
