@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/spk_b200.h"
 
@@ -14,6 +15,48 @@
     } while (0)
 
 static inline cudaStream_t spk_st(spk_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ---- programmatic dependent launch ----------------------------------------------------------------------------------
+// One E+F evaluation is a chain of ~65 short kernels (median 10 us); a normal launch lets kernel n+1 start only after
+// kernel n has drained and its completion has been processed (~3 us per boundary).  Every kernel of the library is
+// therefore launched with the programmatic-stream-serialization attribute and begins with
+//     griddepcontrol.launch_dependents   -- the next kernel's CTAs may be scheduled as soon as all of ours are resident
+//     griddepcontrol.wait                -- block until the previous kernel has completed and its writes are visible
+// so the launch latency and CTA ramp-up of kernel n+1 overlap the tail of kernel n while the data dependence through
+// global memory stays exactly that of a serial stream (the wait precedes every global access).  SPK_B200_PDL=0 in the
+// environment restores plain launches.  Works under stream capture (programmatic graph edges, CUDA >= 12.3).
+#define SPK_PDL_LAUNCH_DEPENDENTS() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+#define SPK_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+#define SPK_PDL_ENTER()              \
+    do {                             \
+        SPK_PDL_LAUNCH_DEPENDENTS(); \
+        SPK_PDL_WAIT();              \
+    } while (0)
+
+static inline bool spk_use_pdl() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SPK_B200_PDL");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
+}
+
+template <typename... KArgs, typename... Args>
+static inline void spk_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = spk_use_pdl() ? 1 : 0;
+    (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // errors surface in SPK_LAUNCH_CHECK()
+}
 
 static inline int64_t spk_cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

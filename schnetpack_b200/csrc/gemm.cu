@@ -41,6 +41,7 @@ __device__ __noinline__ float2 act_both1(float v) {
 // BM = 128 (256 threads) for tall problems, BM = 64 / 32 when the 128-row grid would not fill the 148 SMs.
 template <int BM, int A_ACT, int ACT>
 __global__ void __launch_bounds__(BM * 2) k_dense(GemmArgs g) {
+    SPK_PDL_ENTER();
     constexpr int NT = BM * 2;
     constexpr int AS_LD = BM + 4;
     constexpr int A_IT = 2;                       // float4 A loads per thread per k-tile: BM*BK/4 / NT
@@ -239,9 +240,9 @@ extern "C" int spk_dense(const float* A, int64_t M, int K, int64_t lda, const fl
     cudaStream_t st = spk_st(stream);
 #define LAUNCH_BM(AA, AC)                                                        \
     do {                                                                         \
-        if (bm == 128) k_dense<128, AA, AC><<<grid, 256, 0, st>>>(g);            \
-        else if (bm == 64) k_dense<64, AA, AC><<<grid, 128, 0, st>>>(g);         \
-        else k_dense<32, AA, AC><<<grid, 64, 0, st>>>(g);                        \
+        if (bm == 128) spk_launch(k_dense<128, AA, AC>, grid, 256, 0, st, g);            \
+        else if (bm == 64) spk_launch(k_dense<64, AA, AC>, grid, 128, 0, st, g);         \
+        else spk_launch(k_dense<32, AA, AC>, grid, 64, 0, st, g);                        \
     } while (0)
     if (a_act == SPK_ACT_NONE) {
         if (act == SPK_ACT_NONE) LAUNCH_BM(0, 0); else if (act == SPK_ACT_SILU) LAUNCH_BM(0, 1); else LAUNCH_BM(0, 2);

@@ -181,6 +181,7 @@ __host__ __device__ __forceinline__ int tile_n(int N) {
 
 // one-time packing of a weight matrix W [N,K] into per-(n-tile, k-tile) operand tiles [hi | lo]
 __global__ void k_pack_weight(const float* __restrict__ W, int N, int K, int TN, float* __restrict__ out) {
+    SPK_PDL_ENTER();
     const int nkt = (K + TK - 1) / TK;
     const int64_t total = (int64_t)((N + TN - 1) / TN) * nkt * TN * TK;
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -215,6 +216,7 @@ __global__ void __launch_bounds__(Cfg<TN>::NTHREADS, 1) k_dense_tc(TcArgs g) {
     __shared__ uint32_t s_tmem;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    SPK_PDL_LAUNCH_DEPENDENTS();
     if (tid == 0) TRACE(0);
     const int64_t m0 = (int64_t)blockIdx.x * TM;
     const int n0 = blockIdx.y * TN;
@@ -241,6 +243,7 @@ __global__ void __launch_bounds__(Cfg<TN>::NTHREADS, 1) k_dense_tc(TcArgs g) {
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = s_tmem;
+    SPK_PDL_WAIT();      // barrier init and TMEM allocation above overlap the previous kernel's tail; no global access yet
     if (tid == 0) TRACE(1);
 
     if (warp >= W_PROD0) {
@@ -419,7 +422,7 @@ static int launch_tc(const TcArgs& g, cudaStream_t st) {
         attr_set = true;
     }
     dim3 grid((unsigned)spk_cdiv(g.M, TM), (unsigned)spk_cdiv(g.N, TN));
-    k_dense_tc<TN, A_ACT, ACT><<<grid, Cfg<TN>::NTHREADS, Cfg<TN>::SMEM_BYTES, st>>>(g);
+    spk_launch(k_dense_tc<TN, A_ACT, ACT>, grid, Cfg<TN>::NTHREADS, Cfg<TN>::SMEM_BYTES, st, g);
     return 0;
 }
 
@@ -443,7 +446,7 @@ extern "C" int spk_tc_pack_weight(const float* W, int N, int K, float* packed, s
     if (N <= 0 || K <= 0 || !W || !packed) return SPK_ERR_ARG;
     const int TN = tile_n(N);
     const int64_t total = (int64_t)((N + TN - 1) / TN) * ((K + TK - 1) / TK) * TN * TK;
-    k_pack_weight<<<(unsigned)spk_cdiv(total, 256), 256, 0, spk_st(stream)>>>(W, N, K, TN, packed);
+    spk_launch(k_pack_weight, (unsigned)spk_cdiv(total, 256), 256, 0, spk_st(stream), W, N, K, TN, packed);
     SPK_LAUNCH_CHECK();
     return SPK_OK;
 }

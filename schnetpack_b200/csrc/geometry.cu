@@ -43,6 +43,7 @@ __device__ __forceinline__ void cutoff_eval(float d, float rc, float& fc, float&
 __global__ void k_pairwise_fwd(const float* __restrict__ R, const int64_t* __restrict__ idx_i,
                                const int64_t* __restrict__ idx_j, const float* __restrict__ off, int64_t n_edges,
                                float* __restrict__ r_ij) {
+    SPK_PDL_ENTER();
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= n_edges * 3) return;
     int64_t e = t / 3;
@@ -56,6 +57,7 @@ __global__ void k_pairwise_bwd(const float* __restrict__ g, const int* __restric
                                const int* __restrict__ slot_eid, const int* __restrict__ sptr,
                                const int* __restrict__ pos_slot, int64_t n_atoms, float sign,
                                float* __restrict__ gR) {
+    SPK_PDL_ENTER();
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= n_atoms * 3) return;
     int64_t a = t / 3;
@@ -72,6 +74,7 @@ __global__ void k_edge_geometry(const float* __restrict__ r_ij, const int* __res
                                 int kind, int n_rbf, int KP, const float* __restrict__ p0, const float* __restrict__ p1,
                                 float rc, float* __restrict__ phi, float* __restrict__ dphi, float* __restrict__ geo,
                                 float* __restrict__ erec, int NRB) {
+    SPK_PDL_ENTER();
     // thread (s, k): k in [0, KP)
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= n_edges * KP) return;
@@ -114,6 +117,7 @@ __global__ void k_edge_geometry(const float* __restrict__ r_ij, const int* __res
 
 __global__ void k_rbf(const float* __restrict__ d, int64_t n, int kind, int n_rbf, const float* __restrict__ p0,
                       const float* __restrict__ p1, float* __restrict__ out, float* __restrict__ dout) {
+    SPK_PDL_ENTER();
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= n * n_rbf) return;
     int64_t r = t / n_rbf;
@@ -126,6 +130,7 @@ __global__ void k_rbf(const float* __restrict__ d, int64_t n, int kind, int n_rb
 
 __global__ void k_cutoff(const float* __restrict__ d, int64_t n, float rc, float* __restrict__ out,
                          float* __restrict__ dout) {
+    SPK_PDL_ENTER();
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= n) return;
     float fc, dfc;
@@ -135,6 +140,7 @@ __global__ void k_cutoff(const float* __restrict__ d, int64_t n, float rc, float
 }
 
 __global__ void k_act(const float* __restrict__ x, int64_t n, int act, float* __restrict__ y, float* __restrict__ dy) {
+    SPK_PDL_ENTER();
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= n) return;
     float v = x[t];
@@ -144,6 +150,7 @@ __global__ void k_act(const float* __restrict__ x, int64_t n, int act, float* __
 
 __global__ void k_embedding(const float* __restrict__ table, const int64_t* __restrict__ Z, int64_t n_atoms, int F4,
                             int n_rows, float* __restrict__ out) {
+    SPK_PDL_ENTER();
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= n_atoms * F4) return;
     int64_t a = t / F4;
@@ -157,6 +164,7 @@ __global__ void k_embedding(const float* __restrict__ table, const int64_t* __re
 // out[r, c] = sum_{s in row r} x[slot_eid[s], c]; thread per (r, c)
 __global__ void k_segment_sum(const float* __restrict__ x, const int* __restrict__ rowptr,
                               const int* __restrict__ slot_eid, int64_t n_out, int C, float* __restrict__ out) {
+    SPK_PDL_ENTER();
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= n_out * C) return;
     int64_t r = t / C;
@@ -170,6 +178,7 @@ __global__ void k_segment_sum(const float* __restrict__ x, const int* __restrict
 }
 
 __global__ void k_add(const float* __restrict__ a, const float* __restrict__ b, int64_t n, float* __restrict__ out) {
+    SPK_PDL_ENTER();
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= n) return;
     out[t] = b ? a[t] + b[t] : a[t];
@@ -184,7 +193,7 @@ extern "C" int spk_pairwise_fwd(const float* R, const int64_t* idx_i, const int6
     if (n_edges < 0) return SPK_ERR_ARG;
     if (n_edges == 0) return SPK_OK;
     if (!R || !idx_i || !idx_j || !r_ij) return SPK_ERR_ARG;
-    k_pairwise_fwd<<<GRID1D(n_edges * 3, 256)>>>(R, idx_i, idx_j, offsets, n_edges, r_ij);
+    spk_launch(k_pairwise_fwd, GRID1D(n_edges * 3, 256), R, idx_i, idx_j, offsets, n_edges, r_ij);
     SPK_LAUNCH_CHECK();
     return SPK_OK;
 }
@@ -194,7 +203,7 @@ extern "C" int spk_pairwise_bwd(const float* g_rij, const int32_t* rowptr, const
     if (n_atoms < 0) return SPK_ERR_ARG;
     if (n_atoms == 0) return SPK_OK;
     if (!rowptr || !sptr || !g_R) return SPK_ERR_ARG;
-    k_pairwise_bwd<<<GRID1D(n_atoms * 3, 128)>>>(g_rij, rowptr, slot_eid, sptr, pos_slot, n_atoms, sign, g_R);
+    spk_launch(k_pairwise_bwd, GRID1D(n_atoms * 3, 128), g_rij, rowptr, slot_eid, sptr, pos_slot, n_atoms, sign, g_R);
     SPK_LAUNCH_CHECK();
     return SPK_OK;
 }
@@ -209,7 +218,7 @@ extern "C" int spk_edge_geometry(const float* r_ij, const int32_t* slot_eid, int
     if (!r_ij || !rbf_p0 || !phi || !geo) return SPK_ERR_ARG;
     if (rbf_kind == SPK_RBF_GAUSSIAN && !rbf_p1) return SPK_ERR_ARG;
     int KP = spk_kp(n_rbf);
-    k_edge_geometry<<<GRID1D(n_edges * KP, 256)>>>(r_ij, slot_eid, n_edges, rbf_kind, n_rbf, KP, rbf_p0, rbf_p1,
+    spk_launch(k_edge_geometry, GRID1D(n_edges * KP, 256), r_ij, slot_eid, n_edges, rbf_kind, n_rbf, KP, rbf_p0, rbf_p1,
                                                    cutoff, phi, dphi, geo, erec, SPK_NRB(n_rbf));
     SPK_LAUNCH_CHECK();
     return SPK_OK;
@@ -221,7 +230,7 @@ extern "C" int spk_rbf_fwd(const float* d, int64_t n, int rbf_kind, int n_rbf, c
     if (rbf_kind != SPK_RBF_GAUSSIAN && rbf_kind != SPK_RBF_BESSEL) return SPK_ERR_ARG;
     if (n == 0) return SPK_OK;
     if (!d || !rbf_p0 || !out || (rbf_kind == SPK_RBF_GAUSSIAN && !rbf_p1)) return SPK_ERR_ARG;
-    k_rbf<<<GRID1D(n * n_rbf, 256)>>>(d, n, rbf_kind, n_rbf, rbf_p0, rbf_p1, out, dout);
+    spk_launch(k_rbf, GRID1D(n * n_rbf, 256), d, n, rbf_kind, n_rbf, rbf_p0, rbf_p1, out, dout);
     SPK_LAUNCH_CHECK();
     return SPK_OK;
 }
@@ -231,7 +240,7 @@ extern "C" int spk_cosine_cutoff_fwd(const float* d, int64_t n, float cutoff, fl
     if (n < 0) return SPK_ERR_ARG;
     if (n == 0) return SPK_OK;
     if (!d || !out) return SPK_ERR_ARG;
-    k_cutoff<<<GRID1D(n, 256)>>>(d, n, cutoff, out, dout);
+    spk_launch(k_cutoff, GRID1D(n, 256), d, n, cutoff, out, dout);
     SPK_LAUNCH_CHECK();
     return SPK_OK;
 }
@@ -240,7 +249,7 @@ extern "C" int spk_act_fwd(const float* x, int64_t n, int act, float* y, float* 
     if (n < 0 || act < 0 || act > 2) return SPK_ERR_ARG;
     if (n == 0) return SPK_OK;
     if (!x) return SPK_ERR_ARG;
-    k_act<<<GRID1D(n, 256)>>>(x, n, act, y, dy);
+    spk_launch(k_act, GRID1D(n, 256), x, n, act, y, dy);
     SPK_LAUNCH_CHECK();
     return SPK_OK;
 }
@@ -250,7 +259,7 @@ extern "C" int spk_embedding(const float* table, const int64_t* Z, int64_t n_ato
     if (n_atoms < 0 || F <= 0 || (F & 3) || n_rows <= 0) return SPK_ERR_ARG;
     if (n_atoms == 0) return SPK_OK;
     if (!table || !Z || !out) return SPK_ERR_ARG;
-    k_embedding<<<GRID1D(n_atoms * (F / 4), 256)>>>(table, Z, n_atoms, F / 4, n_rows, out);
+    spk_launch(k_embedding, GRID1D(n_atoms * (F / 4), 256), table, Z, n_atoms, F / 4, n_rows, out);
     SPK_LAUNCH_CHECK();
     return SPK_OK;
 }
@@ -260,7 +269,7 @@ extern "C" int spk_segment_sum(const float* x, const int32_t* rowptr, const int3
     if (n_out < 0 || C <= 0) return SPK_ERR_ARG;
     if (n_out == 0) return SPK_OK;
     if (!rowptr || !out) return SPK_ERR_ARG;
-    k_segment_sum<<<GRID1D(n_out * C, 256)>>>(x, rowptr, slot_eid, n_out, C, out);
+    spk_launch(k_segment_sum, GRID1D(n_out * C, 256), x, rowptr, slot_eid, n_out, C, out);
     SPK_LAUNCH_CHECK();
     return SPK_OK;
 }
@@ -269,7 +278,7 @@ extern "C" int spk_add(const float* a, const float* b, int64_t n, float* out, sp
     if (n < 0) return SPK_ERR_ARG;
     if (n == 0) return SPK_OK;
     if (!a || !out) return SPK_ERR_ARG;
-    k_add<<<GRID1D(n, 256)>>>(a, b, n, out);
+    spk_launch(k_add, GRID1D(n, 256), a, b, n, out);
     SPK_LAUNCH_CHECK();
     return SPK_OK;
 }

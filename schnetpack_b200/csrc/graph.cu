@@ -6,11 +6,13 @@
 namespace {
 
 __global__ void k_init_status(int* __restrict__ status) {
+    SPK_PDL_ENTER();
     if (threadIdx.x < 4) status[threadIdx.x] = (threadIdx.x == 0) ? 1 : 0;
 }
 
 __global__ void k_count(const int64_t* __restrict__ idx_i, const int64_t* __restrict__ idx_j, int64_t n_atoms,
                         int64_t n_edges, int* __restrict__ deg_i, int* __restrict__ deg_j, int* __restrict__ status) {
+    SPK_PDL_ENTER();
     int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (e >= n_edges) return;
     int64_t i = idx_i[e], j = idx_j[e];
@@ -27,6 +29,7 @@ __global__ void k_count(const int64_t* __restrict__ idx_i, const int64_t* __rest
 __global__ void __launch_bounds__(1024) k_scan2(const int* __restrict__ deg_a, int* __restrict__ ptr_a,
                                                 const int* __restrict__ deg_b, int* __restrict__ ptr_b, int n,
                                                 int* __restrict__ status) {
+    SPK_PDL_ENTER();
     const int* deg = blockIdx.x == 0 ? deg_a : deg_b;
     int* ptr = blockIdx.x == 0 ? ptr_a : ptr_b;
     __shared__ int s_sum[1024];
@@ -70,6 +73,7 @@ __global__ void __launch_bounds__(1024) k_scan2(const int* __restrict__ deg_a, i
 __global__ void k_fill_csr(const int64_t* __restrict__ idx_i, const int64_t* __restrict__ idx_j, int64_t n_edges,
                            const int* __restrict__ rowptr, int* __restrict__ cursor, const int* __restrict__ status,
                            int* __restrict__ slot_j, int* __restrict__ slot_eid, int* __restrict__ tmp_eid) {
+    SPK_PDL_ENTER();
     int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (e >= n_edges) return;
     if (status[1] != 0) return;
@@ -89,6 +93,7 @@ __global__ void k_fill_csr(const int64_t* __restrict__ idx_i, const int64_t* __r
 __global__ void k_rank_rows(const int* __restrict__ ptr, int n_rows, const int* __restrict__ tmp_key,
                             const int64_t* __restrict__ idx_src, const int* __restrict__ slot_eid_in, int mode,
                             const int* __restrict__ status, int* __restrict__ out_key, int* __restrict__ out_val) {
+    SPK_PDL_ENTER();
     if (status[1] != 0) return;
     if (mode == 0 && status[0] != 0) return;
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -107,6 +112,7 @@ __global__ void k_rank_rows(const int* __restrict__ ptr, int n_rows, const int* 
 
 __global__ void k_fill_csc(const int* __restrict__ slot_j, int64_t n_edges, const int* __restrict__ sptr,
                            int* __restrict__ cursor, const int* __restrict__ status, int* __restrict__ tmp_slot) {
+    SPK_PDL_ENTER();
     int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (s >= n_edges) return;
     if (status[1] != 0) return;
@@ -117,6 +123,7 @@ __global__ void k_fill_csc(const int* __restrict__ slot_j, int64_t n_edges, cons
 
 __global__ void k_segment_ptr(const int64_t* __restrict__ idx_m, int64_t n_atoms, int64_t n_mol,
                               int* __restrict__ mol_ptr) {
+    SPK_PDL_ENTER();
     int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (a > n_atoms) return;
     // boundary a: systems in (prev, cur] start at atom a
@@ -157,18 +164,18 @@ extern "C" int spk_graph_build(const int64_t* idx_i, const int64_t* idx_j, int64
     if (err != cudaSuccess) return SPK_CUDA_ERR(err);
     const int T = 256;
     int n_int = (int)n_atoms;
-    k_init_status<<<1, 32, 0, st>>>(status);
+    spk_launch(k_init_status, 1, 32, 0, st, status);
     if (n_edges > 0) {
-        k_count<<<(unsigned)spk_cdiv(n_edges, T), T, 0, st>>>(idx_i, idx_j, n_atoms, n_edges, deg_i, deg_j, status);
+        spk_launch(k_count, (unsigned)spk_cdiv(n_edges, T), T, 0, st, idx_i, idx_j, n_atoms, n_edges, deg_i, deg_j, status);
     }
-    k_scan2<<<2, 1024, 0, st>>>(deg_i, rowptr, deg_j, sptr, n_int, status);
+    spk_launch(k_scan2, 2, 1024, 0, st, deg_i, rowptr, deg_j, sptr, n_int, status);
     if (n_edges > 0) {
         unsigned ge = (unsigned)spk_cdiv(n_edges, T);
         unsigned gw = (unsigned)spk_cdiv(n_atoms * 32, T);
-        k_fill_csr<<<ge, T, 0, st>>>(idx_i, idx_j, n_edges, rowptr, cur_i, status, slot_j, slot_eid, tmp_a);
-        k_rank_rows<<<gw, T, 0, st>>>(rowptr, n_int, tmp_a, idx_j, nullptr, 0, status, slot_eid, slot_j);
-        k_fill_csc<<<ge, T, 0, st>>>(slot_j, n_edges, sptr, cur_j, status, tmp_a);
-        k_rank_rows<<<gw, T, 0, st>>>(sptr, n_int, tmp_a, idx_i, slot_eid, 1, status, pos_slot, pos_i);
+        spk_launch(k_fill_csr, ge, T, 0, st, idx_i, idx_j, n_edges, rowptr, cur_i, status, slot_j, slot_eid, tmp_a);
+        spk_launch(k_rank_rows, gw, T, 0, st, rowptr, n_int, tmp_a, idx_j, nullptr, 0, status, slot_eid, slot_j);
+        spk_launch(k_fill_csc, ge, T, 0, st, slot_j, n_edges, sptr, cur_j, status, tmp_a);
+        spk_launch(k_rank_rows, gw, T, 0, st, sptr, n_int, tmp_a, idx_i, slot_eid, 1, status, pos_slot, pos_i);
     }
     SPK_LAUNCH_CHECK();
     return SPK_OK;
@@ -178,7 +185,7 @@ extern "C" int spk_segment_ptr(const int64_t* idx_m, int64_t n_atoms, int64_t n_
                                spk_stream_t stream) {
     if (n_atoms < 0 || n_mol < 0 || !mol_ptr || (n_atoms > 0 && !idx_m)) return SPK_ERR_ARG;
     const int T = 256;
-    k_segment_ptr<<<(unsigned)spk_cdiv(n_atoms + 1, T), T, 0, spk_st(stream)>>>(idx_m, n_atoms, n_mol, mol_ptr);
+    spk_launch(k_segment_ptr, (unsigned)spk_cdiv(n_atoms + 1, T), T, 0, spk_st(stream), idx_m, n_atoms, n_mol, mol_ptr);
     SPK_LAUNCH_CHECK();
     return SPK_OK;
 }

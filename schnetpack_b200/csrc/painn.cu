@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(NW * 32, 512 / (NW * 32)) k_painn_edge_fwd(
     const float* __restrict__ phi, const float* __restrict__ geo, const int* __restrict__ rowptr,
     const int* __restrict__ slot_j, const float* __restrict__ wf, const float* __restrict__ bf, int n_atoms,
     int n_edges, int n_rbf, float* __restrict__ q_out, float* __restrict__ mu_out) {
+    SPK_PDL_ENTER();
     constexpr int F = NW * 32;
     constexpr int NTHR = NW * 32;
     __shared__ __align__(16) float s_phi[CH * NRB];
@@ -177,6 +178,7 @@ __global__ void __launch_bounds__(NW * 32, 512 / (NW * 32)) k_painn_edge_bwd(
     const int* __restrict__ pos_i, const int* __restrict__ slot_eid, const float* __restrict__ wf,
     const float* __restrict__ bf, int n_atoms, int n_edges, int n_rbf, float* __restrict__ g_x,
     float* __restrict__ g_mu_in, float* __restrict__ g_rij, int accumulate) {
+    SPK_PDL_ENTER();
     constexpr int F = NW * 32;
     constexpr int NTHR = NW * 32;
     __shared__ __align__(16) float s_phi[CH * NRB];
@@ -374,6 +376,7 @@ __global__ void __launch_bounds__(NW * 32, 512 / (NW * 32)) k_painn_edge_bwd(
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void k_mix_ctx(const float* __restrict__ q, const float* __restrict__ VW, int64_t n_atoms, int F, float eps,
                           float* __restrict__ ctx) {
+    SPK_PDL_ENTER();
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= n_atoms * F) return;
     int64_t a = t / F;
@@ -387,6 +390,7 @@ __global__ void k_mix_ctx(const float* __restrict__ q, const float* __restrict__
 __global__ void k_mix_update(const float* __restrict__ q, const float* __restrict__ mu, const float* __restrict__ s,
                              const float* __restrict__ VW, int64_t n_atoms, int F, float* __restrict__ q_out,
                              float* __restrict__ mu_out) {
+    SPK_PDL_ENTER();
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= n_atoms * F) return;
     int64_t a = t / F;
@@ -406,6 +410,7 @@ __global__ void k_mix_update(const float* __restrict__ q, const float* __restric
 __global__ void k_mix_update_bwd(const float* __restrict__ g_q, const float* __restrict__ g_mu,
                                  const float* __restrict__ s, const float* __restrict__ VW, int64_t n_atoms, int F,
                                  float* __restrict__ g_s, float* __restrict__ g_VW) {
+    SPK_PDL_ENTER();
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= n_atoms * F) return;
     int64_t a = t / F;
@@ -435,6 +440,7 @@ __global__ void k_mix_update_bwd(const float* __restrict__ g_q, const float* __r
 __global__ void k_mix_ctx_bwd(const float* __restrict__ g_ctx, const float* __restrict__ g_q,
                               const float* __restrict__ VW, int64_t n_atoms, int F, float eps,
                               float* __restrict__ g_q_out, float* __restrict__ g_VW) {
+    SPK_PDL_ENTER();
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= n_atoms * F) return;
     int64_t a = t / F;
@@ -467,10 +473,10 @@ int launch_edge_fwd(const float* x, const float* mu, const float* q, const float
     if (nb < 1) nb = 1;
     if (nb > n_atoms) nb = n_atoms;
     if (mu)
-        k_painn_edge_fwd<NW, NRB, true><<<(unsigned)nb, NW * 32, 0, st>>>(x, mu, q, phi, geo, rowptr, slot_j, wf, bf,
+        spk_launch(k_painn_edge_fwd<NW, NRB, true>, (unsigned)nb, NW * 32, 0, st, x, mu, q, phi, geo, rowptr, slot_j, wf, bf,
                                                                          n_atoms, n_edges, n_rbf, q_out, mu_out);
     else
-        k_painn_edge_fwd<NW, NRB, false><<<(unsigned)nb, NW * 32, 0, st>>>(x, mu, q, phi, geo, rowptr, slot_j, wf, bf,
+        spk_launch(k_painn_edge_fwd<NW, NRB, false>, (unsigned)nb, NW * 32, 0, st, x, mu, q, phi, geo, rowptr, slot_j, wf, bf,
                                                                           n_atoms, n_edges, n_rbf, q_out, mu_out);
     return 0;
 }
@@ -492,11 +498,11 @@ int launch_edge_bwd(const float* x, const float* mu, const float* g_q, const flo
     if (nb < 1) nb = 1;
     if (nb > n_atoms) nb = n_atoms;
     if (mu)
-        k_painn_edge_bwd<NW, NRB, true><<<(unsigned)nb, NW * 32, 0, st>>>(
+        spk_launch(k_painn_edge_bwd<NW, NRB, true>, (unsigned)nb, NW * 32, 0, st, 
             x, mu, g_q, g_mu, phi, dphi, geo, sptr, pos_slot, pos_i, slot_eid, wf, bf, n_atoms, n_edges, n_rbf, g_x,
             g_mu_in, g_rij, accumulate);
     else
-        k_painn_edge_bwd<NW, NRB, false><<<(unsigned)nb, NW * 32, 0, st>>>(
+        spk_launch(k_painn_edge_bwd<NW, NRB, false>, (unsigned)nb, NW * 32, 0, st, 
             x, mu, g_q, g_mu, phi, dphi, geo, sptr, pos_slot, pos_i, slot_eid, wf, bf, n_atoms, n_edges, n_rbf, g_x,
             g_mu_in, g_rij, accumulate);
     return 0;
@@ -596,7 +602,7 @@ extern "C" int spk_painn_mix_ctx(const float* q, const float* VW, int64_t n_atom
     if (n_atoms < 0 || F <= 0) return SPK_ERR_ARG;
     if (n_atoms == 0) return SPK_OK;
     if (!q || !VW || !ctx) return SPK_ERR_ARG;
-    k_mix_ctx<<<GRID1D(n_atoms * F, 256)>>>(q, VW, n_atoms, F, eps, ctx);
+    spk_launch(k_mix_ctx, GRID1D(n_atoms * F, 256), q, VW, n_atoms, F, eps, ctx);
     SPK_LAUNCH_CHECK();
     return SPK_OK;
 }
@@ -606,7 +612,7 @@ extern "C" int spk_painn_mix_update(const float* q, const float* mu, const float
     if (n_atoms < 0 || F <= 0) return SPK_ERR_ARG;
     if (n_atoms == 0) return SPK_OK;
     if (!q || !mu || !s || !VW || !q_out || !mu_out) return SPK_ERR_ARG;
-    k_mix_update<<<GRID1D(n_atoms * F, 256)>>>(q, mu, s, VW, n_atoms, F, q_out, mu_out);
+    spk_launch(k_mix_update, GRID1D(n_atoms * F, 256), q, mu, s, VW, n_atoms, F, q_out, mu_out);
     SPK_LAUNCH_CHECK();
     return SPK_OK;
 }
@@ -616,7 +622,7 @@ extern "C" int spk_painn_mix_update_bwd(const float* g_q, const float* g_mu, con
     if (n_atoms < 0 || F <= 0) return SPK_ERR_ARG;
     if (n_atoms == 0) return SPK_OK;
     if (!g_q || !g_mu || !s || !VW || !g_s || !g_VW) return SPK_ERR_ARG;
-    k_mix_update_bwd<<<GRID1D(n_atoms * F, 256)>>>(g_q, g_mu, s, VW, n_atoms, F, g_s, g_VW);
+    spk_launch(k_mix_update_bwd, GRID1D(n_atoms * F, 256), g_q, g_mu, s, VW, n_atoms, F, g_s, g_VW);
     SPK_LAUNCH_CHECK();
     return SPK_OK;
 }
@@ -626,7 +632,7 @@ extern "C" int spk_painn_mix_ctx_bwd(const float* g_ctx, const float* g_q, const
     if (n_atoms < 0 || F <= 0) return SPK_ERR_ARG;
     if (n_atoms == 0) return SPK_OK;
     if (!g_ctx || !g_q || !VW || !g_q_out || !g_VW) return SPK_ERR_ARG;
-    k_mix_ctx_bwd<<<GRID1D(n_atoms * F, 256)>>>(g_ctx, g_q, VW, n_atoms, F, eps, g_q_out, g_VW);
+    spk_launch(k_mix_ctx_bwd, GRID1D(n_atoms * F, 256), g_ctx, g_q, VW, n_atoms, F, eps, g_q_out, g_VW);
     SPK_LAUNCH_CHECK();
     return SPK_OK;
 }

@@ -32,6 +32,7 @@ __global__ void __launch_bounds__(NW * 32) k_painn_edge_fwd_sys(
     const int* __restrict__ slot_j, const float* __restrict__ wf, const float* __restrict__ bf,
     const int* __restrict__ mol_ptr, int parts, int cap_atoms, int n_rbf, float* __restrict__ q_out,
     float* __restrict__ mu_out) {
+    SPK_PDL_ENTER();
     constexpr int F = NW * 32;
     constexpr int NTHR = NW * 32;
     extern __shared__ __align__(16) float s_tab[];           // [cap][3F] x rows, then [cap][3F] mu rows
@@ -173,6 +174,7 @@ __global__ void __launch_bounds__(NW * 32) k_painn_edge_bwd_sys(
     const int* __restrict__ pos_i, const int* __restrict__ slot_eid, const float* __restrict__ wf,
     const float* __restrict__ bf, const int* __restrict__ mol_ptr, int parts, int cap_atoms, int n_rbf,
     float* __restrict__ g_x, float* __restrict__ g_mu_in, float* __restrict__ g_rij, int accumulate) {
+    SPK_PDL_ENTER();
     constexpr int F = NW * 32;
     constexpr int NTHR = NW * 32;
     extern __shared__ __align__(16) float s_tab[];           // [cap][F] g_q rows, then [cap][3F] g_mu rows
@@ -398,11 +400,11 @@ int launch_fwd_sys(const float* x, const float* mu, const float* q, const float*
     int rc;
     if (mu) {
         if ((rc = set_smem(k_painn_edge_fwd_sys<NW, NRB, true>, sm, &cur_mu))) return rc;
-        k_painn_edge_fwd_sys<NW, NRB, true><<<n_mol * parts, NW * 32, sm, st>>>(x, mu, q, phi, geo, rowptr, slot_j, wf, bf,
+        spk_launch(k_painn_edge_fwd_sys<NW, NRB, true>, n_mol * parts, NW * 32, sm, st, x, mu, q, phi, geo, rowptr, slot_j, wf, bf,
                                                                               mol_ptr, parts, cap, n_rbf, q_out, mu_out);
     } else {
         if ((rc = set_smem(k_painn_edge_fwd_sys<NW, NRB, false>, sm, &cur_nomu))) return rc;
-        k_painn_edge_fwd_sys<NW, NRB, false><<<n_mol * parts, NW * 32, sm, st>>>(x, mu, q, phi, geo, rowptr, slot_j, wf,
+        spk_launch(k_painn_edge_fwd_sys<NW, NRB, false>, n_mol * parts, NW * 32, sm, st, x, mu, q, phi, geo, rowptr, slot_j, wf,
                                                                                bf, mol_ptr, parts, cap, n_rbf, q_out, mu_out);
     }
     return 0;
@@ -419,12 +421,12 @@ int launch_bwd_sys(const float* x, const float* mu, const float* g_q, const floa
     int rc;
     if (mu) {
         if ((rc = set_smem(k_painn_edge_bwd_sys<NW, NRB, true>, sm, &cur_mu))) return rc;
-        k_painn_edge_bwd_sys<NW, NRB, true><<<n_mol * parts, NW * 32, sm, st>>>(
+        spk_launch(k_painn_edge_bwd_sys<NW, NRB, true>, n_mol * parts, NW * 32, sm, st, 
             x, mu, g_q, g_mu, phi, dphi, geo, sptr, pos_slot, pos_i, slot_eid, wf, bf, mol_ptr, parts, cap, n_rbf, g_x,
             g_mu_in, g_rij, accumulate);
     } else {
         if ((rc = set_smem(k_painn_edge_bwd_sys<NW, NRB, false>, sm, &cur_nomu))) return rc;
-        k_painn_edge_bwd_sys<NW, NRB, false><<<n_mol * parts, NW * 32, sm, st>>>(
+        spk_launch(k_painn_edge_bwd_sys<NW, NRB, false>, n_mol * parts, NW * 32, sm, st, 
             x, mu, g_q, g_mu, phi, dphi, geo, sptr, pos_slot, pos_i, slot_eid, wf, bf, mol_ptr, parts, cap, n_rbf, g_x,
             g_mu_in, g_rij, accumulate);
     }

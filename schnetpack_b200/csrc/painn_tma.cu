@@ -74,6 +74,7 @@ __global__ void __launch_bounds__((NW + 1) * 32) k_painn_edge_fwd_tma(
     const float* __restrict__ phi, const float* __restrict__ geo, const int* __restrict__ rowptr,
     const int* __restrict__ slot_j, const float* __restrict__ wf, const float* __restrict__ bf, int n_atoms,
     int n_edges, int n_rbf, float* __restrict__ q_out, float* __restrict__ mu_out) {
+    SPK_PDL_ENTER();
     constexpr int F = NW * 32;
     using Stage = FwdStage<F, HAS_MU>;
     using Chunk = FwdChunk<NRB>;
@@ -251,6 +252,7 @@ __global__ void __launch_bounds__((NW + 1) * 32) k_painn_edge_bwd_tma(
     const int* __restrict__ pos_slot, const int* __restrict__ pos_i, const int* __restrict__ slot_eid,
     const float* __restrict__ wf, const float* __restrict__ bf, int n_atoms, int n_edges, int n_rbf,
     float* __restrict__ g_x, float* __restrict__ g_mu_in, float* __restrict__ g_rij, int accumulate) {
+    SPK_PDL_ENTER();
     constexpr int F = NW * 32;
     constexpr int REC = 2 * NRB + SPK_GEO_STRIDE;
     using Stage = BwdStage<F, NRB>;
@@ -478,12 +480,12 @@ int spk_launch_edge_fwd_tma(const float* x, const float* mu, const float* q, con
     if (mu) {
         const size_t sm = DEPTH * sizeof(FwdStage<F, true>) + 2 * sizeof(FwdChunk<NRB>);
         int nb = single_wave_grid(k_painn_edge_fwd_tma<NW, NRB, true>, T, sm, n_atoms, n_edges, &occ_mu);
-        k_painn_edge_fwd_tma<NW, NRB, true><<<nb, T, sm, st>>>(x, mu, q, phi, geo, rowptr, slot_j, wf, bf, n_atoms,
+        spk_launch(k_painn_edge_fwd_tma<NW, NRB, true>, nb, T, sm, st, x, mu, q, phi, geo, rowptr, slot_j, wf, bf, n_atoms,
                                                                n_edges, n_rbf, q_out, mu_out);
     } else {
         const size_t sm = DEPTH * sizeof(FwdStage<F, false>) + 2 * sizeof(FwdChunk<NRB>);
         int nb = single_wave_grid(k_painn_edge_fwd_tma<NW, NRB, false>, T, sm, n_atoms, n_edges, &occ_nomu);
-        k_painn_edge_fwd_tma<NW, NRB, false><<<nb, T, sm, st>>>(x, mu, q, phi, geo, rowptr, slot_j, wf, bf, n_atoms,
+        spk_launch(k_painn_edge_fwd_tma<NW, NRB, false>, nb, T, sm, st, x, mu, q, phi, geo, rowptr, slot_j, wf, bf, n_atoms,
                                                                 n_edges, n_rbf, q_out, mu_out);
     }
     return 0;
@@ -499,12 +501,12 @@ int spk_launch_edge_bwd_tma(const float* x, const float* mu, const float* g_q, c
     const size_t sm = DEPTH * sizeof(BwdStage<F, NRB>);
     if (mu) {
         int nb = single_wave_grid(k_painn_edge_bwd_tma<NW, NRB, true>, T, sm, n_atoms, n_edges, &occ_mu);
-        k_painn_edge_bwd_tma<NW, NRB, true><<<nb, T, sm, st>>>(x, mu, g_q, g_mu, erec, sptr, pos_slot, pos_i,
+        spk_launch(k_painn_edge_bwd_tma<NW, NRB, true>, nb, T, sm, st, x, mu, g_q, g_mu, erec, sptr, pos_slot, pos_i,
                                                                slot_eid, wf, bf, n_atoms, n_edges, n_rbf, g_x, g_mu_in,
                                                                g_rij, accumulate);
     } else {
         int nb = single_wave_grid(k_painn_edge_bwd_tma<NW, NRB, false>, T, sm, n_atoms, n_edges, &occ_nomu);
-        k_painn_edge_bwd_tma<NW, NRB, false><<<nb, T, sm, st>>>(x, mu, g_q, g_mu, erec, sptr, pos_slot, pos_i,
+        spk_launch(k_painn_edge_bwd_tma<NW, NRB, false>, nb, T, sm, st, x, mu, g_q, g_mu, erec, sptr, pos_slot, pos_i,
                                                                 slot_eid, wf, bf, n_atoms, n_edges, n_rbf, g_x, g_mu_in,
                                                                 g_rij, accumulate);
     }

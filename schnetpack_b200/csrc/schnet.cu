@@ -13,6 +13,7 @@ __global__ void __launch_bounds__(NW * 32) k_cfconv_fwd(const float* __restrict_
                                                         const float* __restrict__ geo, const int* __restrict__ rowptr,
                                                         const int* __restrict__ slot_j, int n_atoms, int n_edges,
                                                         float* __restrict__ m) {
+    SPK_PDL_ENTER();
     constexpr int F = NW * 32;
     const int c = threadIdx.x;
     const int row_lo = spk_block_row_begin(rowptr, n_atoms, n_edges, gridDim.x, blockIdx.x);
@@ -37,6 +38,7 @@ __global__ void __launch_bounds__(NW * 32) k_cfconv_bwd(const float* __restrict_
                                                         const int* __restrict__ pos_i, int n_atoms, int n_edges,
                                                         float* __restrict__ g_h, float* __restrict__ g_wraw,
                                                         float* __restrict__ g_fc) {
+    SPK_PDL_ENTER();
     constexpr int F = NW * 32;
     __shared__ float s_red[CH][NW];
     __shared__ int s_slot[CH];
@@ -93,6 +95,7 @@ __global__ void k_radial_bwd(const float* __restrict__ g_phi, const float* __res
                              const float* __restrict__ dphi, const float* __restrict__ geo,
                              const int* __restrict__ slot_eid, int64_t n_edges, int n_rbf, int KP,
                              float* __restrict__ g_rij, int accumulate) {
+    SPK_PDL_ENTER();
     int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (s >= n_edges) return;
     float gd = 0.f;
@@ -115,6 +118,7 @@ __global__ void k_radial_bwd(const float* __restrict__ g_phi, const float* __res
 // y[a] = hid[a,:] . w1 + b1 : one warp per atom
 __global__ void k_atom_dot(const float* __restrict__ hid, const float* __restrict__ w1, const float* __restrict__ b1,
                            int64_t n_atoms, int H, float* __restrict__ y) {
+    SPK_PDL_ENTER();
     int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (warp >= n_atoms) return;
@@ -127,6 +131,7 @@ __global__ void k_atom_dot(const float* __restrict__ hid, const float* __restric
 // energy[m] = sum_{a in [mol_ptr[m], mol_ptr[m+1])} y[a] : one 256-thread CTA per system, fixed reduction tree
 __global__ void __launch_bounds__(256) k_mol_sum(const float* __restrict__ y, const int* __restrict__ mol_ptr,
                                                  float* __restrict__ energy) {
+    SPK_PDL_ENTER();
     __shared__ float s_w[8];
     const int m = blockIdx.x;
     const int a0 = mol_ptr[m], a1 = mol_ptr[m + 1];
@@ -145,6 +150,7 @@ __global__ void __launch_bounds__(256) k_mol_sum(const float* __restrict__ y, co
 
 __global__ void k_atomwise_out_bwd(const float* __restrict__ g_energy, const int64_t* __restrict__ idx_m,
                                    const float* __restrict__ w1, int64_t n_atoms, int H, float* __restrict__ g_hid) {
+    SPK_PDL_ENTER();
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= n_atoms * H) return;
     int64_t a = t / H;
@@ -171,10 +177,10 @@ extern "C" int spk_cfconv_fwd(const float* h, const float* w_raw, const float* g
     cudaStream_t st = spk_st(stream);
     int na = (int)n_atoms, ne = (int)n_edges;
     switch (F / 32) {
-        case 1: k_cfconv_fwd<1><<<(unsigned)nb, 32, 0, st>>>(h, w_raw, geo, rowptr, slot_j, na, ne, m); break;
-        case 2: k_cfconv_fwd<2><<<(unsigned)nb, 64, 0, st>>>(h, w_raw, geo, rowptr, slot_j, na, ne, m); break;
-        case 4: k_cfconv_fwd<4><<<(unsigned)nb, 128, 0, st>>>(h, w_raw, geo, rowptr, slot_j, na, ne, m); break;
-        case 8: k_cfconv_fwd<8><<<(unsigned)nb, 256, 0, st>>>(h, w_raw, geo, rowptr, slot_j, na, ne, m); break;
+        case 1: spk_launch(k_cfconv_fwd<1>, (unsigned)nb, 32, 0, st, h, w_raw, geo, rowptr, slot_j, na, ne, m); break;
+        case 2: spk_launch(k_cfconv_fwd<2>, (unsigned)nb, 64, 0, st, h, w_raw, geo, rowptr, slot_j, na, ne, m); break;
+        case 4: spk_launch(k_cfconv_fwd<4>, (unsigned)nb, 128, 0, st, h, w_raw, geo, rowptr, slot_j, na, ne, m); break;
+        case 8: spk_launch(k_cfconv_fwd<8>, (unsigned)nb, 256, 0, st, h, w_raw, geo, rowptr, slot_j, na, ne, m); break;
         default: return SPK_ERR_UNSUPPORTED;
     }
     SPK_LAUNCH_CHECK();
@@ -195,10 +201,10 @@ extern "C" int spk_cfconv_bwd(const float* h, const float* w_raw, const float* g
     cudaStream_t st = spk_st(stream);
     int na = (int)n_atoms, ne = (int)n_edges;
     switch (F / 32) {
-        case 1: k_cfconv_bwd<1><<<(unsigned)nb, 32, 0, st>>>(h, w_raw, geo, g_m, sptr, pos_slot, pos_i, na, ne, g_h, g_wraw, g_fc); break;
-        case 2: k_cfconv_bwd<2><<<(unsigned)nb, 64, 0, st>>>(h, w_raw, geo, g_m, sptr, pos_slot, pos_i, na, ne, g_h, g_wraw, g_fc); break;
-        case 4: k_cfconv_bwd<4><<<(unsigned)nb, 128, 0, st>>>(h, w_raw, geo, g_m, sptr, pos_slot, pos_i, na, ne, g_h, g_wraw, g_fc); break;
-        case 8: k_cfconv_bwd<8><<<(unsigned)nb, 256, 0, st>>>(h, w_raw, geo, g_m, sptr, pos_slot, pos_i, na, ne, g_h, g_wraw, g_fc); break;
+        case 1: spk_launch(k_cfconv_bwd<1>, (unsigned)nb, 32, 0, st, h, w_raw, geo, g_m, sptr, pos_slot, pos_i, na, ne, g_h, g_wraw, g_fc); break;
+        case 2: spk_launch(k_cfconv_bwd<2>, (unsigned)nb, 64, 0, st, h, w_raw, geo, g_m, sptr, pos_slot, pos_i, na, ne, g_h, g_wraw, g_fc); break;
+        case 4: spk_launch(k_cfconv_bwd<4>, (unsigned)nb, 128, 0, st, h, w_raw, geo, g_m, sptr, pos_slot, pos_i, na, ne, g_h, g_wraw, g_fc); break;
+        case 8: spk_launch(k_cfconv_bwd<8>, (unsigned)nb, 256, 0, st, h, w_raw, geo, g_m, sptr, pos_slot, pos_i, na, ne, g_h, g_wraw, g_fc); break;
         default: return SPK_ERR_UNSUPPORTED;
     }
     SPK_LAUNCH_CHECK();
@@ -211,7 +217,7 @@ extern "C" int spk_radial_bwd(const float* g_phi, const float* g_fc, const float
     if (n_edges < 0 || n_rbf <= 0 || n_rbf > 32) return SPK_ERR_ARG;
     if (n_edges == 0) return SPK_OK;
     if (!geo || !g_rij || (g_phi && !dphi)) return SPK_ERR_ARG;
-    k_radial_bwd<<<GRID1D(n_edges, 256)>>>(g_phi, g_fc, dphi, geo, slot_eid, n_edges, n_rbf, spk_kp(n_rbf), g_rij,
+    spk_launch(k_radial_bwd, GRID1D(n_edges, 256), g_phi, g_fc, dphi, geo, slot_eid, n_edges, n_rbf, spk_kp(n_rbf), g_rij,
                                            accumulate);
     SPK_LAUNCH_CHECK();
     return SPK_OK;
@@ -223,11 +229,11 @@ extern "C" int spk_atomwise_out(const float* hid, const float* w1, const float* 
     if (!y) return SPK_ERR_ARG;
     if (n_atoms > 0) {
         if (!hid || !w1) return SPK_ERR_ARG;
-        k_atom_dot<<<GRID1D(n_atoms * 32, 256)>>>(hid, w1, b1, n_atoms, H, y);
+        spk_launch(k_atom_dot, GRID1D(n_atoms * 32, 256), hid, w1, b1, n_atoms, H, y);
     }
     if (energy && n_mol > 0) {
         if (!mol_ptr) return SPK_ERR_ARG;
-        k_mol_sum<<<(unsigned)n_mol, 256, 0, spk_st(stream)>>>(y, mol_ptr, energy);
+        spk_launch(k_mol_sum, (unsigned)n_mol, 256, 0, spk_st(stream), y, mol_ptr, energy);
     }
     SPK_LAUNCH_CHECK();
     return SPK_OK;
@@ -238,7 +244,7 @@ extern "C" int spk_atomwise_out_bwd(const float* g_energy, const int64_t* idx_m,
     if (n_atoms < 0 || H <= 0) return SPK_ERR_ARG;
     if (n_atoms == 0) return SPK_OK;
     if (!w1 || !g_hid || (g_energy && !idx_m)) return SPK_ERR_ARG;
-    k_atomwise_out_bwd<<<GRID1D(n_atoms * H, 256)>>>(g_energy, idx_m, w1, n_atoms, H, g_hid);
+    spk_launch(k_atomwise_out_bwd, GRID1D(n_atoms * H, 256), g_energy, idx_m, w1, n_atoms, H, g_hid);
     SPK_LAUNCH_CHECK();
     return SPK_OK;
 }
