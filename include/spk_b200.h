@@ -143,6 +143,17 @@ int spk_painn_edge_bwd(const float* x, const float* mu, const float* g_q, const 
                        const int32_t* pos_i, const int32_t* slot_eid, const float* wf, const float* bf,
                        int64_t n_atoms, int64_t n_edges, int F, int n_rbf, float* g_x, float* g_mu_in, float* g_rij,
                        int accumulate, spk_stream_t stream);
+/* Tensor-core variant of spk_painn_edge_fwd (csrc/painn_tc.cu): the filter W = fc * (phi . w^T + b) of a chunk of edges is
+ * one 3xTF32 tcgen05 GEMM per filter third with the channels on the TMEM lanes, so the gather/accumulate threads read their
+ * channel's filter values with tcgen05.ld instead of recomputing them from warp-broadcast shared-memory loads (the
+ * streaming kernel is bound by the load/store unit).  wf_packed = spk_painn_pack_filter(wf, bf) (hi/lo operand tiles,
+ * spk_painn_filter_packed_floats() floats).  Same results as spk_painn_edge_fwd to fp32 rounding.  Returns
+ * SPK_ERR_UNSUPPORTED unless F == 128, n_rbf <= 31 and n_edges > 0 (the caller then uses spk_painn_edge_fwd). */
+size_t spk_painn_filter_packed_floats(void);
+int spk_painn_pack_filter(const float* wf, const float* bf, int F, int n_rbf, float* packed, spk_stream_t stream);
+int spk_painn_edge_fwd_tc(const float* x, const float* mu, const float* q, const float* phi, const float* geo,
+                          const int32_t* rowptr, const int32_t* slot_j, const float* wf_packed, int64_t n_atoms,
+                          int64_t n_edges, int F, int n_rbf, float* q_out, float* mu_out, spk_stream_t stream);
 /* "System-resident" variants for batches of small systems (molecules): edges never cross systems
  * (data/loader.py:35-46), so one CTA stages a system's sender rows in shared memory once and every gather is an LDS.
  * mol_ptr[n_mol+1] = first atom of each system (spk_segment_ptr).  Systems larger than the shared-memory capacity chosen

@@ -10,7 +10,7 @@ import os
 from ctypes import c_float, c_int, c_int64, c_size_t, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libspk_b200.so")
+LIB_PATH = os.environ.get("SPK_B200_LIB") or os.path.join(HERE, "csrc", "libspk_b200.so")   # override: A/B builds
 
 SPK_OK = 0
 ACT_NONE, ACT_SILU, ACT_SSP, ACT_GIVEN = 0, 1, 2, 3
@@ -40,6 +40,9 @@ SIGNATURES = {
     "spk_dense_tc": [P, c_int64, c_int, c_int64, P, c_int, P, c_int, P, c_int, P, c_int64, P, c_int64, P, P],
     "spk_painn_edge_fwd": [P, P, P, P, P, P, P, P, P, c_int64, c_int64, c_int, c_int, P, P, P],
     "spk_painn_edge_bwd": [P, P, P, P, P, P, P, P, P, P, P, P, P, P, c_int64, c_int64, c_int, c_int, P, P, P, c_int, P],
+    "spk_painn_filter_packed_floats": [],
+    "spk_painn_pack_filter": [P, P, c_int, c_int, P, P],
+    "spk_painn_edge_fwd_tc": [P, P, P, P, P, P, P, P, c_int64, c_int64, c_int, c_int, P, P, P],
     "spk_painn_edge_fwd_sys": [P, P, P, P, P, P, P, P, P, P, c_int64, c_int64, c_int64, c_int, c_int, P, P, P],
     "spk_painn_edge_bwd_sys": [P, P, P, P, P, P, P, P, P, P, P, P, P, P, c_int64, c_int64, c_int64, c_int, c_int, P, P, P,
                                c_int, P],
@@ -54,7 +57,8 @@ SIGNATURES = {
     "spk_atomwise_out_bwd": [P, P, P, c_int64, c_int, P, P],
     "spk_add": [P, P, c_int64, P, P],
 }
-_RESTYPE = {"spk_graph_workspace_bytes": c_size_t, "spk_tc_packed_floats": c_size_t}
+_RESTYPE = {"spk_graph_workspace_bytes": c_size_t, "spk_tc_packed_floats": c_size_t,
+            "spk_painn_filter_packed_floats": c_size_t}
 
 _lib = None
 

@@ -14,7 +14,24 @@
 
 namespace {
 
+#ifndef SPK_EDGE_MINB
+#define SPK_EDGE_MINB(NW) (512 / ((NW) * 32))   // resident CTAs per SM the register allocation is sized for
+#endif
 constexpr int CH = 32;   // edges staged per chunk (multiple of the 4-edge reduction groups of the reverse kernel)
+
+// Gather pipeline: every thread copies ITS channel of the next DEPTH edges' rows global -> shared with 4-byte cp.async
+// (LDGSTS, a coalesced 128 B request per warp) into slots only it reads back, so the ring needs no barrier -- just
+// cp.async.wait_group.  With plain register loads a CTA had one edge in flight (measured: the kernel ran at the
+// L2 latency x edges / resident CTAs bound); register prefetching did not help because the six scoreboards alias.
+__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 
 // cooperative staging of contiguous per-slot records [n, KP] -> smem [n, NRB] (zero padded)
 template <int NRB, int NTHR>
@@ -28,8 +45,8 @@ __device__ __forceinline__ void stage_rows_contig(float* __restrict__ dst, const
     }
 }
 
-template <int NW, int NRB, bool HAS_MU>
-__global__ void __launch_bounds__(NW * 32, 512 / (NW * 32)) k_painn_edge_fwd(
+template <int NW, int NRB, bool HAS_MU, int DEPTH>
+__global__ void __launch_bounds__(NW * 32, SPK_EDGE_MINB(NW)) k_painn_edge_fwd(
     const float* __restrict__ x, const float* __restrict__ mu, const float* __restrict__ q,
     const float* __restrict__ phi, const float* __restrict__ geo, const int* __restrict__ rowptr,
     const int* __restrict__ slot_j, const float* __restrict__ wf, const float* __restrict__ bf, int n_atoms,
@@ -40,6 +57,8 @@ __global__ void __launch_bounds__(NW * 32, 512 / (NW * 32)) k_painn_edge_fwd(
     __shared__ __align__(16) float s_phi[CH * NRB];
     __shared__ __align__(16) float s_geo[CH * SPK_GEO_STRIDE];
     __shared__ int s_j[CH];
+    constexpr int NV = HAS_MU ? 6 : 2;                       // gathered values per edge and channel
+    __shared__ float s_ring[DEPTH > 0 ? DEPTH : 1][NV][F];
 
     const int c = threadIdx.x;
     const int nb = gridDim.x, b = blockIdx.x;
@@ -81,7 +100,28 @@ __global__ void __launch_bounds__(NW * 32, 512 / (NW * 32)) k_painn_edge_fwd(
         for (int t = threadIdx.x; t < n; t += NTHR) s_j[t] = slot_j[cs + t];
         __syncthreads();
 
-#pragma unroll 2
+        auto issue = [&](int t, int slot) {
+            const int j = s_j[t];
+            const float* __restrict__ xj = x + (size_t)j * (3 * F) + c;
+            cp_async4(&s_ring[slot][0][c], xj);
+            cp_async4(&s_ring[slot][1][c], xj + F);
+            if (HAS_MU) {
+                cp_async4(&s_ring[slot][2][c], xj + 2 * F);
+                const float* __restrict__ mj = mu + (size_t)j * (3 * F) + c;
+                cp_async4(&s_ring[slot][3][c], mj);
+                cp_async4(&s_ring[slot][4][c], mj + F);
+                cp_async4(&s_ring[slot][5][c], mj + 2 * F);
+            }
+        };
+        if (DEPTH > 0) {
+#pragma unroll
+            for (int d = 0; d < DEPTH; ++d) {
+                if (d < n) issue(d, d);
+                cp_async_commit();
+            }
+        }
+
+#pragma unroll(DEPTH > 0 ? DEPTH : 2)
         for (int t = 0; t < n; ++t) {
             const int s = cs + t;
             while (s >= next_boundary) {
@@ -89,16 +129,32 @@ __global__ void __launch_bounds__(NW * 32, 512 / (NW * 32)) k_painn_edge_fwd(
                 ++i;
                 next_boundary = rowptr[i + 1];
             }
-            const int j = s_j[t];
-            const float* __restrict__ xj = x + (size_t)j * (3 * F) + c;
-            const float xa = xj[0], xb = xj[F];
-            float xc = 0.f, m0 = 0.f, m1 = 0.f, m2 = 0.f;
-            if (HAS_MU) {
-                xc = xj[2 * F];
-                const float* __restrict__ mj = mu + (size_t)j * (3 * F) + c;
-                m0 = mj[0];
-                m1 = mj[F];
-                m2 = mj[2 * F];
+            float xa, xb, xc = 0.f, m0 = 0.f, m1 = 0.f, m2 = 0.f;
+            if (DEPTH > 0) {
+                const int slot = t % (DEPTH > 0 ? DEPTH : 1);
+                cp_async_wait<(DEPTH > 0 ? DEPTH - 1 : 0)>();
+                xa = s_ring[slot][0][c];
+                xb = s_ring[slot][1][c];
+                if (HAS_MU) {
+                    xc = s_ring[slot][2][c];
+                    m0 = s_ring[slot][3][c];
+                    m1 = s_ring[slot][4][c];
+                    m2 = s_ring[slot][5][c];
+                }
+                if (t + DEPTH < n) issue(t + DEPTH, slot);      // the slot's values are in registers: refill it
+                cp_async_commit();
+            } else {
+                const int j = s_j[t];
+                const float* __restrict__ xj = x + (size_t)j * (3 * F) + c;
+                xa = xj[0];
+                xb = xj[F];
+                if (HAS_MU) {
+                    xc = xj[2 * F];
+                    const float* __restrict__ mj = mu + (size_t)j * (3 * F) + c;
+                    m0 = mj[0];
+                    m1 = mj[F];
+                    m2 = mj[2 * F];
+                }
             }
             const float4 g0 = *reinterpret_cast<const float4*>(s_geo + t * SPK_GEO_STRIDE);      // ux uy uz d
             const float fc = s_geo[t * SPK_GEO_STRIDE + 4];
@@ -170,8 +226,8 @@ __device__ __forceinline__ float butterfly16(float (&v)[16], int lane) {
     return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
-template <int NW, int NRB, bool HAS_MU>
-__global__ void __launch_bounds__(NW * 32, 512 / (NW * 32)) k_painn_edge_bwd(
+template <int NW, int NRB, bool HAS_MU, int DEPTH>
+__global__ void __launch_bounds__(NW * 32, SPK_EDGE_MINB(NW)) k_painn_edge_bwd(
     const float* __restrict__ x, const float* __restrict__ mu, const float* __restrict__ g_q,
     const float* __restrict__ g_mu, const float* __restrict__ phi, const float* __restrict__ dphi,
     const float* __restrict__ geo, const int* __restrict__ sptr, const int* __restrict__ pos_slot,
@@ -187,6 +243,8 @@ __global__ void __launch_bounds__(NW * 32, 512 / (NW * 32)) k_painn_edge_bwd(
     __shared__ int s_i[CH];
     __shared__ int s_eid[CH];
     __shared__ float s_red[CH][NW][4];
+    static_assert(DEPTH == 0 || DEPTH == 4, "the gather ring is indexed by the position in the 4-edge reduction group");
+    __shared__ float s_ring[DEPTH > 0 ? DEPTH : 1][4][F];    // g_q[i], g_mu[i,0..2] of the next DEPTH edges
 
     const int c = threadIdx.x;
     const int lane = c & 31, warp = c >> 5;
@@ -260,6 +318,21 @@ __global__ void __launch_bounds__(NW * 32, 512 / (NW * 32)) k_painn_edge_bwd(
         }
         __syncthreads();
 
+        auto issue = [&](int t, int slot) {
+            const int i = s_i[t];
+            cp_async4(&s_ring[slot][0][c], g_q + (size_t)i * F + c);
+            const float* __restrict__ gmi = g_mu + (size_t)i * (3 * F) + c;
+            cp_async4(&s_ring[slot][1][c], gmi);
+            cp_async4(&s_ring[slot][2][c], gmi + F);
+            cp_async4(&s_ring[slot][3][c], gmi + 2 * F);
+        };
+        if (DEPTH > 0) {
+#pragma unroll
+            for (int d = 0; d < DEPTH; ++d) {
+                if (d < n) issue(d, d);
+                cp_async_commit();
+            }
+        }
         for (int t0 = 0; t0 < n; t0 += 4) {
             float red[16];
 #pragma unroll
@@ -276,10 +349,23 @@ __global__ void __launch_bounds__(NW * 32, 512 / (NW * 32)) k_painn_edge_bwd(
                         } while (p >= next_boundary);
                         load_own(j);
                     }
-                    const int i = s_i[t];
-                    const float gq = g_q[(size_t)i * F + c];
-                    const float* __restrict__ gmi = g_mu + (size_t)i * (3 * F) + c;
-                    const float g0 = gmi[0], g1 = gmi[F], g2 = gmi[2 * F];
+                    float gq, g0, g1, g2;
+                    if (DEPTH > 0) {
+                        cp_async_wait<(DEPTH > 0 ? DEPTH - 1 : 0)>();
+                        gq = s_ring[u][0][c];
+                        g0 = s_ring[u][1][c];
+                        g1 = s_ring[u][2][c];
+                        g2 = s_ring[u][3][c];
+                        if (t + DEPTH < n) issue(t + DEPTH, u);      // values are in registers: refill the slot
+                        cp_async_commit();
+                    } else {
+                        const int i = s_i[t];
+                        gq = g_q[(size_t)i * F + c];
+                        const float* __restrict__ gmi = g_mu + (size_t)i * (3 * F) + c;
+                        g0 = gmi[0];
+                        g1 = gmi[F];
+                        g2 = gmi[2 * F];
+                    }
                     const float4 ge = *reinterpret_cast<const float4*>(s_geo + t * SPK_GEO_STRIDE);   // ux uy uz d
                     const float fc = s_geo[t * SPK_GEO_STRIDE + 4], dfc = s_geo[t * SPK_GEO_STRIDE + 5];
                     float2 pa2 = make_float2(w.ba, 0.f), pb2 = make_float2(w.bb, 0.f), pc2 = make_float2(w.bc, 0.f);
@@ -456,15 +542,25 @@ __global__ void k_mix_ctx_bwd(const float* __restrict__ g_ctx, const float* __re
     gv[4 * F] += gn * v2;
 }
 
-template <int NW, int NRB>
-int launch_edge_fwd(const float* x, const float* mu, const float* q, const float* phi, const float* geo,
+// gather pipeline depth of the streaming kernels: 4 (cp.async ring, default) or 0 (plain register loads, SPK_B200_EDGE=ldg)
+int edge_depth() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SPK_B200_EDGE");
+        v = (e && e[0] == 'l') ? 0 : 4;
+    }
+    return v;
+}
+
+template <int NW, int NRB, int DEPTH>
+int launch_edge_fwd_d(const float* x, const float* mu, const float* q, const float* phi, const float* geo,
                     const int* rowptr, const int* slot_j, const float* wf, const float* bf, int n_atoms, int n_edges,
                     int n_rbf, float* q_out, float* mu_out, cudaStream_t st) {
     // exactly one resident wave of CTAs (no tail), >= 32 edges per CTA, at most one CTA per atom
     static int occ_mu = 0, occ_nomu = 0;
     if (!occ_mu) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_mu, k_painn_edge_fwd<NW, NRB, true>, NW * 32, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_nomu, k_painn_edge_fwd<NW, NRB, false>, NW * 32, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_mu, k_painn_edge_fwd<NW, NRB, true, DEPTH>, NW * 32, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_nomu, k_painn_edge_fwd<NW, NRB, false, DEPTH>, NW * 32, 0);
         if (occ_mu < 1) occ_mu = 1;
         if (occ_nomu < 1) occ_nomu = 1;
     }
@@ -473,12 +569,49 @@ int launch_edge_fwd(const float* x, const float* mu, const float* q, const float
     if (nb < 1) nb = 1;
     if (nb > n_atoms) nb = n_atoms;
     if (mu)
-        spk_launch(k_painn_edge_fwd<NW, NRB, true>, (unsigned)nb, NW * 32, 0, st, x, mu, q, phi, geo, rowptr, slot_j, wf, bf,
+        spk_launch(k_painn_edge_fwd<NW, NRB, true, DEPTH>, (unsigned)nb, NW * 32, 0, st, x, mu, q, phi, geo, rowptr, slot_j, wf, bf,
                                                                          n_atoms, n_edges, n_rbf, q_out, mu_out);
     else
-        spk_launch(k_painn_edge_fwd<NW, NRB, false>, (unsigned)nb, NW * 32, 0, st, x, mu, q, phi, geo, rowptr, slot_j, wf, bf,
+        spk_launch(k_painn_edge_fwd<NW, NRB, false, DEPTH>, (unsigned)nb, NW * 32, 0, st, x, mu, q, phi, geo, rowptr, slot_j, wf, bf,
                                                                           n_atoms, n_edges, n_rbf, q_out, mu_out);
     return 0;
+}
+
+template <int NW, int NRB, int DEPTH>
+int launch_edge_bwd_d(const float* x, const float* mu, const float* g_q, const float* g_mu, const float* phi,
+                    const float* dphi, const float* geo, const int* sptr, const int* pos_slot, const int* pos_i,
+                    const int* slot_eid, const float* wf, const float* bf, int n_atoms, int n_edges, int n_rbf,
+                    float* g_x, float* g_mu_in, float* g_rij, int accumulate, cudaStream_t st) {
+    static int occ_mu = 0, occ_nomu = 0;
+    if (!occ_mu) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_mu, k_painn_edge_bwd<NW, NRB, true, DEPTH>, NW * 32, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_nomu, k_painn_edge_bwd<NW, NRB, false, DEPTH>, NW * 32, 0);
+        if (occ_mu < 1) occ_mu = 1;
+        if (occ_nomu < 1) occ_nomu = 1;
+    }
+    int64_t nb = (int64_t)spk_num_sms() * (mu ? occ_mu : occ_nomu);
+    if (nb > spk_cdiv((int64_t)n_edges, 32)) nb = spk_cdiv((int64_t)n_edges, 32);
+    if (nb < 1) nb = 1;
+    if (nb > n_atoms) nb = n_atoms;
+    if (mu)
+        spk_launch(k_painn_edge_bwd<NW, NRB, true, DEPTH>, (unsigned)nb, NW * 32, 0, st, 
+            x, mu, g_q, g_mu, phi, dphi, geo, sptr, pos_slot, pos_i, slot_eid, wf, bf, n_atoms, n_edges, n_rbf, g_x,
+            g_mu_in, g_rij, accumulate);
+    else
+        spk_launch(k_painn_edge_bwd<NW, NRB, false, DEPTH>, (unsigned)nb, NW * 32, 0, st, 
+            x, mu, g_q, g_mu, phi, dphi, geo, sptr, pos_slot, pos_i, slot_eid, wf, bf, n_atoms, n_edges, n_rbf, g_x,
+            g_mu_in, g_rij, accumulate);
+    return 0;
+}
+
+template <int NW, int NRB>
+int launch_edge_fwd(const float* x, const float* mu, const float* q, const float* phi, const float* geo,
+                    const int* rowptr, const int* slot_j, const float* wf, const float* bf, int n_atoms, int n_edges,
+                    int n_rbf, float* q_out, float* mu_out, cudaStream_t st) {
+    return edge_depth() ? launch_edge_fwd_d<NW, NRB, 4>(x, mu, q, phi, geo, rowptr, slot_j, wf, bf, n_atoms, n_edges, n_rbf,
+                                                        q_out, mu_out, st)
+                        : launch_edge_fwd_d<NW, NRB, 0>(x, mu, q, phi, geo, rowptr, slot_j, wf, bf, n_atoms, n_edges, n_rbf,
+                                                        q_out, mu_out, st);
 }
 
 template <int NW, int NRB>
@@ -486,26 +619,10 @@ int launch_edge_bwd(const float* x, const float* mu, const float* g_q, const flo
                     const float* dphi, const float* geo, const int* sptr, const int* pos_slot, const int* pos_i,
                     const int* slot_eid, const float* wf, const float* bf, int n_atoms, int n_edges, int n_rbf,
                     float* g_x, float* g_mu_in, float* g_rij, int accumulate, cudaStream_t st) {
-    static int occ_mu = 0, occ_nomu = 0;
-    if (!occ_mu) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_mu, k_painn_edge_bwd<NW, NRB, true>, NW * 32, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_nomu, k_painn_edge_bwd<NW, NRB, false>, NW * 32, 0);
-        if (occ_mu < 1) occ_mu = 1;
-        if (occ_nomu < 1) occ_nomu = 1;
-    }
-    int64_t nb = (int64_t)spk_num_sms() * (mu ? occ_mu : occ_nomu);
-    if (nb > spk_cdiv((int64_t)n_edges, 32)) nb = spk_cdiv((int64_t)n_edges, 32);
-    if (nb < 1) nb = 1;
-    if (nb > n_atoms) nb = n_atoms;
-    if (mu)
-        spk_launch(k_painn_edge_bwd<NW, NRB, true>, (unsigned)nb, NW * 32, 0, st, 
-            x, mu, g_q, g_mu, phi, dphi, geo, sptr, pos_slot, pos_i, slot_eid, wf, bf, n_atoms, n_edges, n_rbf, g_x,
-            g_mu_in, g_rij, accumulate);
-    else
-        spk_launch(k_painn_edge_bwd<NW, NRB, false>, (unsigned)nb, NW * 32, 0, st, 
-            x, mu, g_q, g_mu, phi, dphi, geo, sptr, pos_slot, pos_i, slot_eid, wf, bf, n_atoms, n_edges, n_rbf, g_x,
-            g_mu_in, g_rij, accumulate);
-    return 0;
+    return edge_depth() ? launch_edge_bwd_d<NW, NRB, 4>(x, mu, g_q, g_mu, phi, dphi, geo, sptr, pos_slot, pos_i, slot_eid, wf,
+                                                        bf, n_atoms, n_edges, n_rbf, g_x, g_mu_in, g_rij, accumulate, st)
+                        : launch_edge_bwd_d<NW, NRB, 0>(x, mu, g_q, g_mu, phi, dphi, geo, sptr, pos_slot, pos_i, slot_eid, wf,
+                                                        bf, n_atoms, n_edges, n_rbf, g_x, g_mu_in, g_rij, accumulate, st);
 }
 
 // one-time choice of the streaming edge-kernel variant via SPK_B200_EDGE: "ldg" (this file; default, fastest in r1) or "tma"
@@ -513,7 +630,7 @@ bool use_tma_variant() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("SPK_B200_EDGE");
-        v = (e && e[0] == 't') ? 1 : 0;
+        v = (e && e[0] == 't' && e[1] == 'm') ? 1 : 0;   // "tma" ("tc" selects painn_tc.cu, in ops.py)
     }
     return v == 1;
 }

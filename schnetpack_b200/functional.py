@@ -64,6 +64,7 @@ class PaiNNPack(ParamPack):
             else:
                 self.wf.append(fw[t * 3 * F:(t + 1) * 3 * F].contiguous())
                 self.bf.append(fb[t * 3 * F:(t + 1) * 3 * F].contiguous())
+        self.wfp = [None] * T                                  # tensor-core operand tiles of (wf, bf), built on first use
         self.blocks = []
         for t in range(T):
             it, mx = mod.interactions[t], mod.mixing[t]
@@ -73,6 +74,14 @@ class PaiNNPack(ParamPack):
                 c0=ops.Lin(c0.weight, c0.bias), c1=ops.Lin(c1.weight, c1.bias),
                 mix=ops.Lin(mx.mu_channel_mix.weight), m0=ops.Lin(m0.weight, m0.bias), m1=ops.Lin(m1.weight, m1.bias),
             ))
+
+
+def _packed_filter(pk: "PaiNNPack", t: int, n_rbf: int, n_edges: int):
+    if not ops.edge_tc_ok(pk.F, n_rbf, n_edges):
+        return None
+    if pk.wfp[t] is None:
+        pk.wfp[t] = ops.painn_pack_filter(pk.wf[t], pk.bf[t], pk.F, n_rbf)
+    return pk.wfp[t]
 
 
 def painn_forward(pk: PaiNNPack, q0: Tensor, r_ij: Tensor, graph: ops.EdgeGraph, rbf_kind: int, n_rbf: int,
@@ -93,7 +102,8 @@ def painn_forward(pk: PaiNNPack, q0: Tensor, r_ij: Tensor, graph: ops.EdgeGraph,
         a, hpre = b["c0"].fwd(q, act, save_deriv=True)                                         # painn.py:54
         x = b["c1"].fwd(a)
         q1, mu1 = ops.painn_edge_fwd(x, mu, q, phi, geo, graph, pk.wf[t], pk.bf[t], F, n_rbf,   # :55-65
-                                     mol_ptr=mol_ptr, n_mol=n_mol)
+                                     mol_ptr=mol_ptr, n_mol=n_mol,
+                                     wf_packed=_packed_filter(pk, t, n_rbf, graph.n_edges))
         VW = b["mix"].fwd(mu1.view(3 * N, F))                                                # :103  [3N,2F]
         ctx = ops.painn_mix_ctx(q1, VW, F, pk.eps)                                           # :104-107
         c, cpre = b["m0"].fwd(ctx, act, save_deriv=True)                                       # :108

@@ -333,24 +333,42 @@ def dense_into(A: Tensor, B: Tensor, out: Tensor, ldy: int, **kw):
 
 
 # ------------------------------------------------------------------------------------------------------------ PaiNN
-# edge-kernel variant (r1 measurements on cfg2, fwd/bwd us per launch: ldg 59/115, tma 71/145, sys 80/170):
-#   "ldg" (default) streaming kernels with coalesced global gathers (csrc/painn.cu);
+# edge-kernel variant (r1 measurements on cfg2, fwd/bwd us per launch: ldg 59/108, tma 71/145, sys 80/170):
+#   "async" (default) streaming kernels, sender rows gathered through a per-thread cp.async ring (csrc/painn.cu);
+#   "ldg"           the same kernels with plain register loads (one edge in flight per CTA);
 #   "tma"           streaming kernels with a TMA bulk-copy + mbarrier producer/consumer ring (csrc/painn_tma.cu);
 #   "sys"           system-resident kernels for batches of small systems when the caller supplies mol_ptr
-#                   (csrc/painn_sys.cu).  The C library reads SPK_B200_EDGE for the ldg-vs-tma choice.
-EDGE_IMPL = os.environ.get("SPK_B200_EDGE", "ldg")
+#                   (csrc/painn_sys.cu).  The C library reads SPK_B200_EDGE itself for the async / ldg / tma choice.
+EDGE_IMPL = os.environ.get("SPK_B200_EDGE", "async")
 SYS_MAX_AVG_ATOMS = 48
+EDGE_TC_MIN_EDGES = 4096
 
 
 def _use_sys(n_atoms: int, mol_ptr, n_mol: int) -> bool:
     return (EDGE_IMPL == "sys" and mol_ptr is not None and n_mol > 0 and n_atoms / n_mol <= SYS_MAX_AVG_ATOMS)
 
 
-def painn_edge_fwd(x, mu, q, phi, geo, graph: EdgeGraph, wf, bf, F: int, n_rbf: int, mol_ptr=None, n_mol: int = 0):
+def edge_tc_ok(F: int, n_rbf: int, n_edges: int) -> bool:
+    """The tensor-core filter path (csrc/painn_tc.cu) covers F == 128, n_rbf <= 31; tiny edge lists stay on the
+    streaming kernel (a persistent CTA per SM needs work for its 4 consumer groups)."""
+    return EDGE_IMPL == "tc" and F == 128 and n_rbf <= 31 and n_edges >= EDGE_TC_MIN_EDGES
+
+
+def painn_pack_filter(wf: Tensor, bf: Tensor, F: int, n_rbf: int) -> Tensor:
+    out = torch.empty(_lib.lib().spk_painn_filter_packed_floats(), dtype=torch.float32, device=wf.device)
+    _lib.call("spk_painn_pack_filter", _p(f32(wf, "wf")), _p(f32(bf, "bf")), F, n_rbf, _p(out), _stream())
+    return out
+
+
+def painn_edge_fwd(x, mu, q, phi, geo, graph: EdgeGraph, wf, bf, F: int, n_rbf: int, mol_ptr=None, n_mol: int = 0,
+                   wf_packed=None):
     N = graph.n_atoms
     q_out = torch.empty((N, F), dtype=torch.float32, device=x.device)
     mu_out = torch.empty((N, 3, F), dtype=torch.float32, device=x.device)
-    if _use_sys(N, mol_ptr, n_mol):
+    if wf_packed is not None and edge_tc_ok(F, n_rbf, graph.n_edges):
+        _lib.call("spk_painn_edge_fwd_tc", _p(x), _p(mu), _p(q), _p(phi), _p(geo), _p(graph.rowptr), _p(graph.slot_j),
+                  _p(wf_packed), N, graph.n_edges, F, n_rbf, _p(q_out), _p(mu_out), _stream())
+    elif _use_sys(N, mol_ptr, n_mol):
         _lib.call("spk_painn_edge_fwd_sys", _p(x), _p(mu), _p(q), _p(phi), _p(geo), _p(graph.rowptr), _p(graph.slot_j),
                   _p(wf), _p(bf), _p(mol_ptr), n_mol, N, graph.n_edges, F, n_rbf, _p(q_out), _p(mu_out), _stream())
     else:

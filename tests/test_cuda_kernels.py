@@ -440,3 +440,46 @@ def test_lin_saved_derivative_backward(impl):
             assert rel(gx, gx_ref) < 5e-6
     finally:
         ops.DENSE_IMPL = old
+
+
+@pytest.mark.parametrize("gen,n_rbf", [("aspirin", 20), ("qm9like", 20), ("aspirin", 13), ("periodic", 20)])
+def test_painn_edge_fwd_tensor_core_filter_matches_streaming(gen, n_rbf):
+    """csrc/painn_tc.cu (filter on tcgen05, channels on TMEM lanes) == csrc/painn.cu (filter in FFMA2) to fp32 rounding,
+    with and without mu, on ragged row lengths, tail chunks and an n_rbf that is not a multiple of 4."""
+    from schnetpack_b200 import ops
+    from schnetpack_b200 import synthetic as S
+
+    if gen == "aspirin":
+        b = S.aspirin_batch(37, seed=21)
+    elif gen == "qm9like":
+        b = S.qm9like_batch(64, seed=22)
+    else:
+        b = S.periodic_box(600, seed=23)
+    ti, tj = torch.as_tensor(b["_idx_i"], device=DEV), torch.as_tensor(b["_idx_j"], device=DEV)
+    N = b["_atomic_numbers"].shape[0]
+    g = ops.EdgeGraph(ti, tj, N)
+    torch.manual_seed(31)
+    F, rc = 128, 5.0
+    R = torch.as_tensor(b["_positions"], device=DEV)
+    off = torch.as_tensor(b["_offsets"], device=DEV) if "_offsets" in b else 0.0
+    r = (R[tj] - R[ti] + off).contiguous()
+    p0 = torch.linspace(0, rc, n_rbf, device=DEV)
+    p1 = torch.full((n_rbf,), float(p0[1] - p0[0]), device=DEV)
+    phi, dphi, geo = ops.edge_geometry(r, g, ops.RBF_GAUSSIAN, n_rbf, p0, p1, rc, False)
+    x = torch.randn(N, 3 * F, device=DEV)
+    q = torch.randn(N, F, device=DEV)
+    wf = torch.randn(3 * F, n_rbf, device=DEV) * 0.3
+    bf = torch.randn(3 * F, device=DEV) * 0.3
+    wpk = ops.painn_pack_filter(wf, bf, F, n_rbf)
+    saved = ops.EDGE_IMPL, ops.EDGE_TC_MIN_EDGES
+    try:
+        for mu in (torch.randn(N, 3, F, device=DEV), None):
+            ops.EDGE_IMPL = "ldg"
+            q_ref, mu_ref = ops.painn_edge_fwd(x, mu, q, phi, geo, g, wf, bf, F, n_rbf)
+            ops.EDGE_IMPL, ops.EDGE_TC_MIN_EDGES = "tc", 1
+            q_tc, mu_tc = ops.painn_edge_fwd(x, mu, q, phi, geo, g, wf, bf, F, n_rbf, wf_packed=wpk)
+            torch.cuda.synchronize()
+            assert rel(q_tc, q_ref.double()) < 2e-6, (gen, mu is None, rel(q_tc, q_ref.double()))
+            assert rel(mu_tc, mu_ref.double()) < 2e-6, (gen, mu is None, rel(mu_tc, mu_ref.double()))
+    finally:
+        ops.EDGE_IMPL, ops.EDGE_TC_MIN_EDGES = saved

@@ -1,0 +1,16 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 300 python -m pytest tests/test_cuda_kernels.py -q -m gpu --timeout=120 -x -k "tensor_core_filter" > gpurun_out/tcedge_test.log 2>&1; echo "tc edge test rc=$?"; tail -3 gpurun_out/tcedge_test.log | cut -c1-300
+SPK_B200_LIB=$PWD/tools/build/libspk_trace.so timeout 300 python tools/edge_trace.py > gpurun_out/edge_trace.log 2>&1; echo rc=$?; sed -n 1,14p gpurun_out/edge_trace.log
+for e in tc; do
+SPK_B200_EDGE=$e timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_$e.json 2> gpurun_out/bench_$e.err
+python - $e <<'PY'
+import json, sys
+n = "gpurun_out/bench_" + sys.argv[1]
+try:
+    d = json.load(open(n + ".json"))
+    print(sys.argv[1], "ms/step", round(d["ms_per_step"],3), "value", round(d["value"]), "e2e", round(d["e2e"]["value"]), {k:(round(v["avg_us"],1), round(v["frac"],3), round(v["share_of_step"],3)) for k,v in d["roofline_all"].items()})
+except Exception as e:
+    print("failed", e); print(open(n + ".err").read()[-1500:])
+PY
+done
