@@ -383,7 +383,9 @@ def run_cuda(args, rank, world, local_rank):
             n = len(kernel_ms[kind])
             ach = tot_bytes / (tot_ms * 1e-3) / 1e9
             roof_all[kind] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                              "traffic": None, "kernel": f"k_painn_edge_{kind}", "launches_timed": n,
+                              "traffic": None,
+                              "kernel": f"k_painn_edge_{kind}" + ("_tc" if ops.edge_tc_ok(F, spec.get("n_rbf", 20), E) else ""),
+                              "launches_timed": n,
                               "avg_us": 1e3 * tot_ms / n, "algorithmic_bytes_per_launch": tot_bytes / n,
                               "share_of_step": tot_ms / dev_ms, "peak_source": peak_src,
                               "timing": "CUDA events around the kernel, inside the timed region"

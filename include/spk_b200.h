@@ -154,6 +154,15 @@ int spk_painn_pack_filter(const float* wf, const float* bf, int F, int n_rbf, fl
 int spk_painn_edge_fwd_tc(const float* x, const float* mu, const float* q, const float* phi, const float* geo,
                           const int32_t* rowptr, const int32_t* slot_j, const float* wf_packed, int64_t n_atoms,
                           int64_t n_edges, int F, int n_rbf, float* q_out, float* mu_out, spk_stream_t stream);
+/* Tensor-core variant of spk_painn_edge_bwd: one operand of 64 rows per chunk of 32 edges, rows 0..31 = fc [phi | 1],
+ * rows 32..63 = dfc [phi | 1] + fc [dphi | 0], so the same 27 MMAs produce W and dW/dd for the 8 edges of each of the 4
+ * sender groups.  Same outputs as spk_painn_edge_bwd to fp32 rounding; SPK_ERR_UNSUPPORTED under the conditions of
+ * spk_painn_edge_fwd_tc. */
+int spk_painn_edge_bwd_tc(const float* x, const float* mu, const float* g_q, const float* g_mu, const float* phi,
+                          const float* dphi, const float* geo, const int32_t* sptr, const int32_t* pos_slot,
+                          const int32_t* pos_i, const int32_t* slot_eid, const float* wf_packed, int64_t n_atoms,
+                          int64_t n_edges, int F, int n_rbf, float* g_x, float* g_mu_in, float* g_rij, int accumulate,
+                          spk_stream_t stream);
 /* "System-resident" variants for batches of small systems (molecules): edges never cross systems
  * (data/loader.py:35-46), so one CTA stages a system's sender rows in shared memory once and every gather is an LDS.
  * mol_ptr[n_mol+1] = first atom of each system (spk_segment_ptr).  Systems larger than the shared-memory capacity chosen

@@ -43,6 +43,7 @@ SIGNATURES = {
     "spk_painn_filter_packed_floats": [],
     "spk_painn_pack_filter": [P, P, c_int, c_int, P, P],
     "spk_painn_edge_fwd_tc": [P, P, P, P, P, P, P, P, c_int64, c_int64, c_int, c_int, P, P, P],
+    "spk_painn_edge_bwd_tc": [P, P, P, P, P, P, P, P, P, P, P, P, c_int64, c_int64, c_int, c_int, P, P, P, c_int, P],
     "spk_painn_edge_fwd_sys": [P, P, P, P, P, P, P, P, P, P, c_int64, c_int64, c_int64, c_int, c_int, P, P, P],
     "spk_painn_edge_bwd_sys": [P, P, P, P, P, P, P, P, P, P, P, P, P, P, c_int64, c_int64, c_int64, c_int, c_int, P, P, P,
                                c_int, P],

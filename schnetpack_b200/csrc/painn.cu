@@ -542,12 +542,13 @@ __global__ void k_mix_ctx_bwd(const float* __restrict__ g_ctx, const float* __re
     gv[4 * F] += gn * v2;
 }
 
-// gather pipeline depth of the streaming kernels: 4 (cp.async ring, default) or 0 (plain register loads, SPK_B200_EDGE=ldg)
+// gather pipeline depth of the streaming kernels: 0 (plain register loads, default) or 4 (cp.async ring, SPK_B200_EDGE=async;
+// measured slower: LDGSTS costs 8 LSU cycles per operation and the kernel is bound by the LSU / L2 fill path)
 int edge_depth() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("SPK_B200_EDGE");
-        v = (e && e[0] == 'l') ? 0 : 4;
+        v = (e && e[0] == 'a') ? 4 : 0;
     }
     return v;
 }

@@ -136,7 +136,8 @@ def painn_backward(pk: PaiNNPack, saved, graph: ops.EdgeGraph, n_rbf: int, act: 
         g_mu1 = b["mix"].bwd(g_VW.view(3 * N, 2 * F), addend=g_mu.view(3 * N, F)).view(N, 3, F)
         # --- interaction (painn.py:54-65) reversed
         g_x, g_mu0 = ops.painn_edge_bwd(x, mu_in, g_q1, g_mu1, phi, dphi, geo, graph, pk.wf[t], pk.bf[t], F, n_rbf,
-                                        g_rij, accumulate=(t != pk.T - 1), erec=erec, mol_ptr=mol_ptr, n_mol=n_mol)
+                                        g_rij, accumulate=(t != pk.T - 1), erec=erec, mol_ptr=mol_ptr, n_mol=n_mol,
+                                        wf_packed=_packed_filter(pk, t, n_rbf, graph.n_edges))
         if t == 0:
             break   # dE/dq0 would only reach the (position-independent) embedding: the first context net is not reversed
         g_a = b["c1"].bwd(g_x)                                                               # [N,3F]x[3F,F]

@@ -333,13 +333,16 @@ def dense_into(A: Tensor, B: Tensor, out: Tensor, ldy: int, **kw):
 
 
 # ------------------------------------------------------------------------------------------------------------ PaiNN
-# edge-kernel variant (r1 measurements on cfg2, fwd/bwd us per launch: ldg 59/108, tma 71/145, sys 80/170):
-#   "async" (default) streaming kernels, sender rows gathered through a per-thread cp.async ring (csrc/painn.cu);
-#   "ldg"           the same kernels with plain register loads (one edge in flight per CTA);
+# edge-kernel variant (r1 measurements on cfg2, fwd/bwd us per launch: tc 47/76, ldg 58/108, async 65/112, tma 71/145,
+# sys 80/170):
+#   "tc" (default)  persistent kernels with the continuous filter on the tensor cores (csrc/painn_tc.cu: tcgen05 3xTF32,
+#                   channels on TMEM lanes); F == 128, n_rbf <= 31 and >= EDGE_TC_MIN_EDGES edges, otherwise "ldg";
+#   "ldg"           streaming kernels, filter in packed FFMA2, plain register gathers (csrc/painn.cu);
+#   "async"         the same with a per-thread cp.async gather ring;
 #   "tma"           streaming kernels with a TMA bulk-copy + mbarrier producer/consumer ring (csrc/painn_tma.cu);
 #   "sys"           system-resident kernels for batches of small systems when the caller supplies mol_ptr
-#                   (csrc/painn_sys.cu).  The C library reads SPK_B200_EDGE itself for the async / ldg / tma choice.
-EDGE_IMPL = os.environ.get("SPK_B200_EDGE", "async")
+#                   (csrc/painn_sys.cu).  The C library reads SPK_B200_EDGE itself for the ldg / async / tma choice.
+EDGE_IMPL = os.environ.get("SPK_B200_EDGE", "tc")
 SYS_MAX_AVG_ATOMS = 48
 EDGE_TC_MIN_EDGES = 4096
 
@@ -378,11 +381,15 @@ def painn_edge_fwd(x, mu, q, phi, geo, graph: EdgeGraph, wf, bf, F: int, n_rbf: 
 
 
 def painn_edge_bwd(x, mu, g_q, g_mu, phi, dphi, geo, graph: EdgeGraph, wf, bf, F: int, n_rbf: int, g_rij: Tensor,
-                   accumulate: bool, erec: Optional[Tensor] = None, mol_ptr=None, n_mol: int = 0):
+                   accumulate: bool, erec: Optional[Tensor] = None, mol_ptr=None, n_mol: int = 0, wf_packed=None):
     N = graph.n_atoms
     g_x = torch.empty((N, 3 * F), dtype=torch.float32, device=x.device)
     g_mu_in = torch.empty((N, 3, F), dtype=torch.float32, device=x.device) if mu is not None else None
-    if _use_sys(N, mol_ptr, n_mol):
+    if wf_packed is not None and edge_tc_ok(F, n_rbf, graph.n_edges):
+        _lib.call("spk_painn_edge_bwd_tc", _p(x), _p(mu), _p(g_q), _p(g_mu), _p(phi), _p(dphi), _p(geo), _p(graph.sptr),
+                  _p(graph.pos_slot), _p(graph.pos_i), _p(graph.slot_eid), _p(wf_packed), N, graph.n_edges, F, n_rbf,
+                  _p(g_x), _p(g_mu_in), _p(g_rij), 1 if accumulate else 0, _stream())
+    elif _use_sys(N, mol_ptr, n_mol):
         _lib.call("spk_painn_edge_bwd_sys", _p(x), _p(mu), _p(g_q), _p(g_mu), _p(phi), _p(dphi), _p(geo),
                   _p(graph.sptr), _p(graph.pos_slot), _p(graph.pos_i), _p(graph.slot_eid), _p(wf), _p(bf), _p(mol_ptr),
                   n_mol, N, graph.n_edges, F, n_rbf, _p(g_x), _p(g_mu_in), _p(g_rij), 1 if accumulate else 0, _stream())

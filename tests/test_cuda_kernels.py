@@ -443,9 +443,9 @@ def test_lin_saved_derivative_backward(impl):
 
 
 @pytest.mark.parametrize("gen,n_rbf", [("aspirin", 20), ("qm9like", 20), ("aspirin", 13), ("periodic", 20)])
-def test_painn_edge_fwd_tensor_core_filter_matches_streaming(gen, n_rbf):
+def test_painn_edge_tensor_core_filter_matches_streaming(gen, n_rbf):
     """csrc/painn_tc.cu (filter on tcgen05, channels on TMEM lanes) == csrc/painn.cu (filter in FFMA2) to fp32 rounding,
-    with and without mu, on ragged row lengths, tail chunks and an n_rbf that is not a multiple of 4."""
+    forward and reverse, with and without mu, on ragged row lengths, tail chunks and an n_rbf that is not a multiple of 4."""
     from schnetpack_b200 import ops
     from schnetpack_b200 import synthetic as S
 
@@ -465,11 +465,14 @@ def test_painn_edge_fwd_tensor_core_filter_matches_streaming(gen, n_rbf):
     r = (R[tj] - R[ti] + off).contiguous()
     p0 = torch.linspace(0, rc, n_rbf, device=DEV)
     p1 = torch.full((n_rbf,), float(p0[1] - p0[0]), device=DEV)
-    phi, dphi, geo = ops.edge_geometry(r, g, ops.RBF_GAUSSIAN, n_rbf, p0, p1, rc, False)
+    phi, dphi, geo = ops.edge_geometry(r, g, ops.RBF_GAUSSIAN, n_rbf, p0, p1, rc, True)
     x = torch.randn(N, 3 * F, device=DEV)
     q = torch.randn(N, F, device=DEV)
     wf = torch.randn(3 * F, n_rbf, device=DEV) * 0.3
     bf = torch.randn(3 * F, device=DEV) * 0.3
+    g_q = torch.randn(N, F, device=DEV)
+    g_mu = torch.randn(N, 3, F, device=DEV)
+    E = ti.shape[0]
     wpk = ops.painn_pack_filter(wf, bf, F, n_rbf)
     saved = ops.EDGE_IMPL, ops.EDGE_TC_MIN_EDGES
     try:
@@ -481,5 +484,19 @@ def test_painn_edge_fwd_tensor_core_filter_matches_streaming(gen, n_rbf):
             torch.cuda.synchronize()
             assert rel(q_tc, q_ref.double()) < 2e-6, (gen, mu is None, rel(q_tc, q_ref.double()))
             assert rel(mu_tc, mu_ref.double()) < 2e-6, (gen, mu is None, rel(mu_tc, mu_ref.double()))
+            for acc in (False, True):
+                seed = torch.randn(E, 3, device=DEV)
+                ops.EDGE_IMPL = "ldg"
+                gr_ref = seed.clone()
+                gx_ref, gm_ref = ops.painn_edge_bwd(x, mu, g_q, g_mu, phi, dphi, geo, g, wf, bf, F, n_rbf, gr_ref, acc)
+                ops.EDGE_IMPL = "tc"
+                gr_tc = seed.clone()
+                gx_tc, gm_tc = ops.painn_edge_bwd(x, mu, g_q, g_mu, phi, dphi, geo, g, wf, bf, F, n_rbf, gr_tc, acc,
+                                                  wf_packed=wpk)
+                torch.cuda.synchronize()
+                assert rel(gx_tc, gx_ref.double()) < 2e-6, (gen, mu is None, acc, rel(gx_tc, gx_ref.double()))
+                assert rel(gr_tc, gr_ref.double()) < 3e-6, (gen, mu is None, acc, rel(gr_tc, gr_ref.double()))
+                if mu is not None:
+                    assert rel(gm_tc, gm_ref.double()) < 2e-6, (gen, acc, rel(gm_tc, gm_ref.double()))
     finally:
         ops.EDGE_IMPL, ops.EDGE_TC_MIN_EDGES = saved

@@ -1,7 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_cuda_kernels.py -q -m gpu --timeout=120 -x -k "tensor_core_filter" > gpurun_out/tcedge_test.log 2>&1; echo "tc edge test rc=$?"; tail -3 gpurun_out/tcedge_test.log | cut -c1-300
-SPK_B200_LIB=$PWD/tools/build/libspk_trace.so timeout 300 python tools/edge_trace.py > gpurun_out/edge_trace.log 2>&1; echo rc=$?; sed -n 1,14p gpurun_out/edge_trace.log
+timeout 300 python -m pytest tests/test_cuda_kernels.py -q -m gpu --timeout=120 -x -k "tensor_core_filter" > gpurun_out/tcedge_test.log 2>&1; echo "tc edge test rc=$?"; tail -12 gpurun_out/tcedge_test.log | cut -c1-300
 for e in tc; do
 SPK_B200_EDGE=$e timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_$e.json 2> gpurun_out/bench_$e.err
 python - $e <<'PY'
