@@ -388,6 +388,9 @@ def run_cuda(args, rank, world, local_rank):
                               "launches_timed": n,
                               "avg_us": 1e3 * tot_ms / n, "algorithmic_bytes_per_launch": tot_bytes / n,
                               "share_of_step": tot_ms / dev_ms, "peak_source": peak_src,
+                              "model": "algorithmic bytes = no-reuse gather model of SURVEY 8(d): every gathered row counted as "
+                                       "HBM traffic; rows served by the 126 MB L2 let frac approach or exceed 1 -- `traffic` is "
+                                       "the DRAM bytes ncu measured",
                               "timing": "CUDA events around the kernel, inside the timed region"
                                         + (" (external event nodes of the replayed graph)" if use_graph else "")}
         dom = max(roof_all, key=lambda k: roof_all[k]["share_of_step"])

@@ -170,12 +170,19 @@ __host__ __device__ __forceinline__ int tile_off(int r, int c) {
     return (r >> 3) * SBO_BYTES + (r & 7) * (TK * 4) + ((c ^ ((r >> 1) & 3)) << 4);
 }
 
-// column-tile width for a layer with N outputs (the packed-weight layout depends on it)
-__host__ __device__ __forceinline__ int tile_n(int N) {
+// Column-tile width.  A weight with N % 128 == 0 is packed in BOTH tile widths (the layouts differ); the launch picks 128
+// when N >= 256 or when 64-wide tiles would need more than one wave of CTAs (M = 3 x atoms in the mu channel mix).
+__host__ __device__ __forceinline__ bool has_wide(int N) { return N % 128 == 0; }
+__host__ __device__ __forceinline__ size_t packed_floats_tn(int N, int K, int TN) {
+    return (size_t)((N + TN - 1) / TN) * ((K + TK - 1) / TK) * (2 * TN * TK);
+}
+static inline int tile_n(int64_t M, int N) {
 #ifdef TC_FORCE_TN
     return TC_FORCE_TN;
 #else
-    return (N >= 256 && N % 128 == 0) ? 128 : 64;
+    if (!has_wide(N)) return 64;
+    if (N >= 256) return 128;
+    return spk_cdiv(M, TM) * (N / 64) > spk_num_sms() ? 128 : 64;
 #endif
 }
 
@@ -438,15 +445,16 @@ static int dispatch_tc(const TcArgs& g, cudaStream_t st) {
 }
 
 extern "C" size_t spk_tc_packed_floats(int N, int K) {
-    const int TN = tile_n(N);
-    return (size_t)((N + TN - 1) / TN) * ((K + TK - 1) / TK) * (2 * TN * TK);
+    return packed_floats_tn(N, K, 64) + (has_wide(N) ? packed_floats_tn(N, K, 128) : 0);
 }
 
 extern "C" int spk_tc_pack_weight(const float* W, int N, int K, float* packed, spk_stream_t stream) {
     if (N <= 0 || K <= 0 || !W || !packed) return SPK_ERR_ARG;
-    const int TN = tile_n(N);
-    const int64_t total = (int64_t)((N + TN - 1) / TN) * ((K + TK - 1) / TK) * TN * TK;
-    spk_launch(k_pack_weight, (unsigned)spk_cdiv(total, 256), 256, 0, spk_st(stream), W, N, K, TN, packed);
+    for (int TN = 64; TN <= (has_wide(N) ? 128 : 64); TN *= 2) {
+        const int64_t total = (int64_t)((N + TN - 1) / TN) * ((K + TK - 1) / TK) * TN * TK;
+        float* out = packed + (TN == 128 ? packed_floats_tn(N, K, 64) : 0);     // [64-wide tiles | 128-wide tiles]
+        spk_launch(k_pack_weight, (unsigned)spk_cdiv(total, 256), 256, 0, spk_st(stream), W, N, K, TN, out);
+    }
     SPK_LAUNCH_CHECK();
     return SPK_OK;
 }
@@ -474,7 +482,13 @@ extern "C" int spk_dense_tc(const float* A, int64_t M, int K, int64_t lda, const
     g.dbg = nullptr;
 #endif
     cudaStream_t st = spk_st(stream);
-    const int rc = tile_n(N) == 128 ? dispatch_tc<128>(g, st) : dispatch_tc<64>(g, st);
+    int rc;
+    if (tile_n(M, N) == 128) {
+        g.Wp = W_packed + packed_floats_tn(N, K, 64);
+        rc = dispatch_tc<128>(g, st);
+    } else {
+        rc = dispatch_tc<64>(g, st);
+    }
     if (rc) return rc;
     SPK_LAUNCH_CHECK();
     return SPK_OK;

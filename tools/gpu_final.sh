@@ -21,6 +21,6 @@ PY
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -s 230 -c 420 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/bench_under_ncu.log 2>&1
 echo "launchlist rc=$?"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_painn_edge|k_dense_tc" -s 24 -c 12 -f -o gpurun_out/prof_final \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_painn_edge|k_dense_tc" -s 6 -c 30 -f -o gpurun_out/prof_final \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/bench_under_ncu2.log 2>&1
 echo "fullset rc=$?"; ls -la gpurun_out/prof_final.ncu-rep

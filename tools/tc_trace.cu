@@ -28,7 +28,7 @@ static void run(int64_t M, int K, int N, int act, bool prologue) {
     CK(cudaMalloc(&bias, N * 4));
     CK(cudaMalloc(&Y, M * N * 4));
     CK(cudaMalloc(&Ypre, M * N * 4));
-    const int TN = tile_n(N);
+    const int TN = tile_n(M, N);
     const int ncta = (int)(((M + TM - 1) / TM) * ((N + TN - 1) / TN));
     CK(cudaMalloc(&dbg, (size_t)ncta * 128 * 8));
     CK(cudaMemset(dbg, 0, (size_t)ncta * 128 * 8));
@@ -40,7 +40,7 @@ static void run(int64_t M, int K, int N, int act, bool prologue) {
     CK(cudaMemcpy(bias, h.data(), N * 4, cudaMemcpyHostToDevice));
     if (spk_tc_pack_weight(W, N, K, Wp, nullptr)) { printf("pack failed\n"); exit(1); }
     TcArgs g;
-    g.A = A; g.a_pre = prologue ? Apre : nullptr; g.Wp = Wp; g.bias = bias; g.addend = nullptr; g.Y = Y;
+    g.A = A; g.a_pre = prologue ? Apre : nullptr; g.Wp = TN == 128 ? Wp + packed_floats_tn(N, K, 64) : Wp; g.bias = bias; g.addend = nullptr; g.Y = Y;
     g.y_pre = act ? Ypre : nullptr;
     g.M = M; g.lda = K; g.ld_add = N; g.ldy = N; g.K = K; g.N = N; g.a_act = prologue ? 3 : 0; g.act = act;
     g.save_deriv = act ? 1 : 0;
