@@ -187,6 +187,8 @@ def run_cuda(args, rank, world, local_rank):
         import torch.distributed as dist_mod
 
         dist = dist_mod
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # NCCL's version banner goes to stdout: keep the ONE JSON line clean
         if not dist.is_initialized():
             dist.init_process_group("nccl", device_id=dev)
 
