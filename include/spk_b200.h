@@ -219,6 +219,25 @@ int spk_atomwise_out_bwd(const float* g_energy, const int64_t* idx_m, const floa
 /* elementwise helpers for residual streams: out = a + b (b nullable -> copy), may alias */
 int spk_add(const float* a, const float* b, int64_t n, float* out, spk_stream_t stream);
 
+/* ---- "next" row f1: device-resident neighbour list (replaces the host round trip of md/neighborlist_md.py:129,213-232 and
+ * the ASE / matscipy / vesin / torch builders of transform/neighborlist.py:213-286,428-553) ---------------------------------
+ * Linked-cell search per system of a collated batch.  Listed: every (i, j, S) with |R[j] - R[i] + S @ cell| < cutoff, S
+ * integer with S_a = 0 on non-periodic axes, except (i == j, S == 0); offsets = S @ cell (fp32); rows sorted by idx_i, a row
+ * in traversal order (deterministic; compare after the canonical (i, j, S) sort as the reference's tests do).
+ *   R [n_atoms,3] fp32, cell [n_sys,3,3] fp32 (rows = lattice vectors; ignored where pbc is all zero), pbc [n_sys,3] uint8,
+ *   sys_ptr [n_sys+1] int32 = first atom of every system (spk_segment_ptr).
+ *   idx_i, idx_j [capacity] int64, offsets [capacity,3] fp32, shifts [capacity,3] int32 (nullable).
+ *   n_pairs [2] int64 on the DEVICE: [0] = pairs found, [1] = 1 if they exceeded `capacity` (then only the first
+ *   `capacity` were written).  pad != 0 fills entries [n_pairs, capacity) with self pairs of the last atom at distance
+ *   2 * cutoff -- outside the cutoff, so they contribute nothing to energies or forces -- which lets a caller run a fixed-size
+ *   edge list without ever reading n_pairs on the host (CUDA-graph capturable MD step).  capacity == 0 only counts.
+ * Enqueue-only on `stream`; workspace of spk_neighbor_list_workspace_bytes(n_atoms, n_sys) bytes. */
+size_t spk_neighbor_list_workspace_bytes(int64_t n_atoms, int64_t n_sys);
+int spk_neighbor_list(const float* R, const float* cell, const uint8_t* pbc, const int32_t* sys_ptr, int64_t n_atoms,
+                      int64_t n_sys, float cutoff, int64_t capacity, int pad, int64_t* idx_i, int64_t* idx_j,
+                      float* offsets, int32_t* shifts, int64_t* n_pairs, void* workspace, size_t workspace_bytes,
+                      spk_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,9 +57,11 @@ SIGNATURES = {
     "spk_atomwise_out": [P, P, P, P, c_int64, c_int64, c_int, P, P, P],
     "spk_atomwise_out_bwd": [P, P, P, c_int64, c_int, P, P],
     "spk_add": [P, P, c_int64, P, P],
+    "spk_neighbor_list_workspace_bytes": [c_int64, c_int64],
+    "spk_neighbor_list": [P, P, P, P, c_int64, c_int64, c_float, c_int64, c_int, P, P, P, P, P, P, c_size_t, P],
 }
 _RESTYPE = {"spk_graph_workspace_bytes": c_size_t, "spk_tc_packed_floats": c_size_t,
-            "spk_painn_filter_packed_floats": c_size_t}
+            "spk_painn_filter_packed_floats": c_size_t, "spk_neighbor_list_workspace_bytes": c_size_t}
 
 _lib = None
 
@@ -98,7 +100,7 @@ def check(rc: int, name: str):
 
 
 # kernels launched per C-ABI call (default 1); bench.py reports the running total as ``gpu_launches``
-LAUNCHES = {"spk_graph_build": 7, "spk_atomwise_out": 2}
+LAUNCHES = {"spk_graph_build": 7, "spk_atomwise_out": 2, "spk_neighbor_list": 9}
 launch_count = 0
 
 

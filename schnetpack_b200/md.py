@@ -1,0 +1,100 @@
+"""Device-resident NVE step ("next" rows f1 + f2): the reference's simulation loop
+(/root/reference/src/schnetpack/md/simulator.py:93-144 -- half_step, main_step, calculator.calculate, half_step with the
+velocity-Verlet integrator of md/integrators.py:59-70,97-110) with NOTHING leaving the GPU between steps:
+
+  * the neighbour list is rebuilt on the device every step (``neighbors.CellListNeighborList`` with a fixed capacity and
+    inert padding -- no Verlet skin, no host copy of positions as in md/neighborlist_md.py:129,213-232);
+  * momenta / positions are updated by device kernels on static buffers;
+  * the whole step (kick, drift, neighbour list, graph views, energy + forces, kick) is captured once as a CUDA graph and
+    replayed; the host only counts steps.  ``n_pairs`` (true pair count, overflow flag) stays on the device for the caller
+    to poll when it wants to.
+
+Units are the caller's: forces = -dE/dR in the model's energy / length units, ``masses`` and ``time_step`` consistent with
+them (the reference converts to its internal MD units in md/system.py; that bookkeeping is outside the hot path).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from . import ops
+from . import properties as P
+from .neighbors import CellListNeighborList
+
+__all__ = ["DeviceMD"]
+
+Tensor = torch.Tensor
+
+
+class DeviceMD:
+    def __init__(self, model: torch.nn.Module, batch: Dict[str, Tensor], masses: Tensor, time_step: float, cutoff: float,
+                 capacity: int, momenta: Optional[Tensor] = None, use_graph: bool = True):
+        dev = batch[P.R].device
+        if dev.type != "cuda":
+            raise ValueError("DeviceMD needs a CUDA batch (no CPU fallback)")
+        self.model = model
+        self.dt = float(time_step)
+        self.static = {k: v.detach().clone() for k, v in batch.items() if k not in (P.idx_i, P.idx_j, P.offsets)}
+        self.positions = self.static[P.R]
+        self.masses = masses.to(dev, torch.float32).reshape(-1, 1).clone()
+        self.momenta = torch.zeros_like(self.positions) if momenta is None else momenta.to(dev, torch.float32).clone()
+        self.nl = CellListNeighborList(cutoff, capacity=int(capacity), pad=True)
+        self.use_graph = use_graph
+        self.energy: Optional[Tensor] = None
+        self.forces: Optional[Tensor] = None
+        self.n_pairs: Optional[Tensor] = None
+        self._graph = None
+        self.steps_done = 0
+        self._calculate()                       # forces at t = 0 (simulator.py:118)
+
+    # ---- one force evaluation on the current positions (calculator.calculate) ---------------------------------------------
+    def _calculate(self):
+        ops._GRAPH_CACHE.clear()
+        x = {k: (v.detach() if v.is_floating_point() else v) for k, v in self.static.items()}
+        x = self.nl(x)
+        out = self.model(x)
+        e, f = out["energy"].detach(), out["forces"].detach()
+        if self.energy is None:
+            self.energy, self.forces, self.n_pairs = e.clone(), f.clone(), x["_n_pairs"].clone()
+        else:
+            self.energy.copy_(e)
+            self.forces.copy_(f)
+            self.n_pairs.copy_(x["_n_pairs"])
+
+    def _step(self):
+        self.momenta.add_(self.forces, alpha=0.5 * self.dt)                  # integrators.py:70   half_step
+        self.positions.addcdiv_(self.momenta, self.masses, value=self.dt)    # integrators.py:108  main_step
+        self._calculate()                                                    # simulator.py:137
+        self.momenta.add_(self.forces, alpha=0.5 * self.dt)                  # simulator.py:144    half_step
+
+    def _capture(self):
+        dev = self.positions.device
+        # capture works on copies of the state so that warm-up iterations do not advance the trajectory
+        saved = (self.positions.clone(), self.momenta.clone(), self.forces.clone(), self.energy.clone())
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            self._step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self._step()
+        for dst, src in zip((self.positions, self.momenta, self.forces, self.energy), saved):
+            dst.copy_(src)
+        self._graph = graph
+
+    def run(self, n_steps: int):
+        """Advance ``n_steps`` velocity-Verlet steps; returns (energy, forces) buffers of the last step (device)."""
+        if self.use_graph and self._graph is None:
+            self._capture()
+        for _ in range(int(n_steps)):
+            if self.use_graph:
+                self._graph.replay()
+            else:
+                self._step()
+        self.steps_done += int(n_steps)
+        return self.energy, self.forces
+
+    def kinetic_energy(self) -> Tensor:
+        return 0.5 * (self.momenta ** 2 / self.masses).sum()

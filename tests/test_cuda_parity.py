@@ -86,12 +86,13 @@ def test_cfg4_box_painn_1000():
     _oracle_vs_cuda("cfg4", n_atoms_total=1000)
 
 
-def test_unsorted_neighbor_list_matches_sorted():
+@pytest.mark.parametrize("batch", [8, 20])   # 2.4k edges: streaming edge kernels; 6.1k edges: tensor-core edge kernels
+def test_unsorted_neighbor_list_matches_sorted(batch):
     """idx_i is not guaranteed sorted (vesin / LAMMPS order): a random permutation of the edge list must give the same
     energy and forces (graph build falls back to a stable grouping)."""
     from schnetpack_b200 import synthetic as S
 
-    spec, inputs = S.make_config("cfg2", batch=8)
+    spec, inputs = S.make_config("cfg2", batch=batch)
     params = S.init_params(spec, seed=3)
     a = _run_cuda(spec, params, inputs)
     rng = np.random.default_rng(0)
