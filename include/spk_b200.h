@@ -228,9 +228,10 @@ int spk_add(const float* a, const float* b, int64_t n, float* out, spk_stream_t 
  *   sys_ptr [n_sys+1] int32 = first atom of every system (spk_segment_ptr).
  *   idx_i, idx_j [capacity] int64, offsets [capacity,3] fp32, shifts [capacity,3] int32 (nullable).
  *   n_pairs [2] int64 on the DEVICE: [0] = pairs found, [1] = 1 if they exceeded `capacity` (then only the first
- *   `capacity` were written).  pad != 0 fills entries [n_pairs, capacity) with self pairs of the last atom at distance
- *   2 * cutoff -- outside the cutoff, so they contribute nothing to energies or forces -- which lets a caller run a fixed-size
- *   edge list without ever reading n_pairs on the host (CUDA-graph capturable MD step).  capacity == 0 only counts.
+ *   `capacity` were written).  pad != 0 spreads the unused capacity over the rows as self pairs (i, i) at distance
+ *   2 * cutoff appended to each row -- outside the cutoff, so they contribute nothing to energies or forces, idx_i stays
+ *   sorted and no row grows long -- which lets a caller run a fixed-size edge list without ever reading n_pairs on the host
+ *   (CUDA-graph capturable MD step).  Without pad the pairs are contiguous in [0, n_pairs).  capacity == 0 only counts.
  * Enqueue-only on `stream`; workspace of spk_neighbor_list_workspace_bytes(n_atoms, n_sys) bytes. */
 size_t spk_neighbor_list_workspace_bytes(int64_t n_atoms, int64_t n_sys);
 int spk_neighbor_list(const float* R, const float* cell, const uint8_t* pbc, const int32_t* sys_ptr, int64_t n_atoms,

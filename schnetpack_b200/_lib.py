@@ -100,7 +100,7 @@ def check(rc: int, name: str):
 
 
 # kernels launched per C-ABI call (default 1); bench.py reports the running total as ``gpu_launches``
-LAUNCHES = {"spk_graph_build": 7, "spk_atomwise_out": 2, "spk_neighbor_list": 9}
+LAUNCHES = {"spk_graph_build": 7, "spk_atomwise_out": 2, "spk_neighbor_list": 6}
 launch_count = 0
 
 

@@ -147,9 +147,9 @@ __global__ void __launch_bounds__(256) k_nl_search(const float* __restrict__ R, 
                                                    const int* __restrict__ sorted_atom, const int* __restrict__ cell_start,
                                                    const int* __restrict__ cell_end, float cutoff2,
                                                    int* __restrict__ deg, const int* __restrict__ row_start,
-                                                   long long capacity, int64_t* __restrict__ idx_i,
-                                                   int64_t* __restrict__ idx_j, float* __restrict__ offsets,
-                                                   int32_t* __restrict__ shifts) {
+                                                   long long capacity, int pad, float cutoff,
+                                                   int64_t* __restrict__ idx_i, int64_t* __restrict__ idx_j,
+                                                   float* __restrict__ offsets, int32_t* __restrict__ shifts) {
     SPK_PDL_ENTER();
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -162,7 +162,16 @@ __global__ void __launch_bounds__(256) k_nl_search(const float* __restrict__ R, 
     const int c2 = lc % g.n[2];
     lc /= g.n[2];
     const int c1 = lc % g.n[1], c0 = lc / g.n[1];
-    long long out = FILL ? (long long)row_start[i] : 0;
+    // padding (fixed-capacity mode): the unused capacity P is spread over the rows -- row i is followed by
+    // floor((i+1) P / N) - floor(i P / N) inert self pairs -- so idx_i stays sorted and no atom collects a long row
+    long long out = 0, pads_before = 0, pads_mine = 0;
+    if (FILL) {
+        const long long total = row_start[n_atoms];
+        const long long P = (pad && capacity > total) ? capacity - total : 0;
+        pads_before = ((long long)i * P) / n_atoms;
+        pads_mine = ((long long)(i + 1) * P) / n_atoms - pads_before;
+        out = (long long)row_start[i] + pads_before;
+    }
     int count = 0;
     for (int d0 = -g.reach[0]; d0 <= g.reach[0]; ++d0) {
         const int t0 = c0 + d0;
@@ -223,28 +232,29 @@ __global__ void __launch_bounds__(256) k_nl_search(const float* __restrict__ R, 
         }
     }
     if (!FILL && lane == 0) deg[i] = count;
+    if (FILL) {
+        for (long long t = lane; t < pads_mine; t += 32) {
+            const long long e = out + t;
+            if (e >= capacity) break;
+            idx_i[e] = i;                        // self pair at distance 2 cutoff: the cosine cutoff and its derivative vanish,
+            idx_j[e] = i;                        // so it contributes nothing to energies or forces
+            offsets[e * 3 + 0] = 2.0f * cutoff;
+            offsets[e * 3 + 1] = 0.f;
+            offsets[e * 3 + 2] = 0.f;
+            if (shifts) shifts[e * 3 + 0] = shifts[e * 3 + 1] = shifts[e * 3 + 2] = 0;
+        }
+    }
 }
 
-// n_pairs[0] = pairs found, n_pairs[1] = 1 if they did not fit; optional padding of the tail with out-of-cutoff self pairs
-__global__ void k_nl_finish(const int* __restrict__ row_start, int n_atoms, long long capacity, int pad, float cutoff,
-                            int64_t* __restrict__ idx_i, int64_t* __restrict__ idx_j, float* __restrict__ offsets,
-                            int32_t* __restrict__ shifts, int64_t* __restrict__ n_pairs) {
+// n_pairs[0] = pairs found, n_pairs[1] = 1 if they did not fit
+__global__ void k_nl_finish(const int* __restrict__ row_start, int n_atoms, long long capacity,
+                            int64_t* __restrict__ n_pairs) {
     SPK_PDL_ENTER();
-    const long long total = row_start[n_atoms];
-    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (t == 0) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const long long total = row_start[n_atoms];
         n_pairs[0] = total;
         n_pairs[1] = total > capacity ? 1 : 0;
     }
-    if (!pad) return;
-    const long long e = total + t;
-    if (e >= capacity) return;
-    idx_i[e] = n_atoms - 1;                      // keeps idx_i sorted; |offset| = 2 cutoff: the cosine cutoff and its
-    idx_j[e] = n_atoms - 1;                      // derivative vanish, so a padded edge contributes nothing
-    offsets[e * 3 + 0] = 2.0f * cutoff;
-    offsets[e * 3 + 1] = 0.f;
-    offsets[e * 3 + 2] = 0.f;
-    if (shifts) shifts[e * 3 + 0] = shifts[e * 3 + 1] = shifts[e * 3 + 2] = 0;
 }
 
 struct NlLayout {
@@ -328,17 +338,15 @@ extern "C" int spk_neighbor_list(const float* R, const float* cell, const uint8_
     const unsigned gw = (unsigned)spk_cdiv((int64_t)N * 32, 256);
     spk_launch(k_nl_search<false>, gw, 256, 0, st, R, sys_ptr, B, N, (const SysGrid*)grid, (const int*)cell_of,
                (const int*)wrap, (const int*)sorted_atom, (const int*)cell_start, (const int*)cell_end, cutoff * cutoff, deg,
-               (const int*)row_start, (long long)capacity, idx_i, idx_j, offsets, shifts);
+               (const int*)row_start, (long long)capacity, 0, cutoff, idx_i, idx_j, offsets, shifts);
     cub_bytes = L.cub_bytes;
     e = cub::DeviceScan::ExclusiveSum(ws + L.cub, cub_bytes, (const int*)deg, row_start, N + 1, st);
     if (e != cudaSuccess) return SPK_CUDA_ERR(e);
     if (capacity > 0)
         spk_launch(k_nl_search<true>, gw, 256, 0, st, R, sys_ptr, B, N, (const SysGrid*)grid, (const int*)cell_of,
                    (const int*)wrap, (const int*)sorted_atom, (const int*)cell_start, (const int*)cell_end, cutoff * cutoff,
-                   deg, (const int*)row_start, (long long)capacity, idx_i, idx_j, offsets, shifts);
-    const long long fin = pad ? (capacity > 0 ? capacity : 1) : 1;
-    spk_launch(k_nl_finish, (unsigned)spk_cdiv(fin, 256), 256, 0, st, (const int*)row_start, N, (long long)capacity, pad,
-               cutoff, idx_i, idx_j, offsets, shifts, n_pairs);
+                   deg, (const int*)row_start, (long long)capacity, pad, cutoff, idx_i, idx_j, offsets, shifts);
+    spk_launch(k_nl_finish, 1, 32, 0, st, (const int*)row_start, N, (long long)capacity, n_pairs);
     SPK_LAUNCH_CHECK();
     return SPK_OK;
 }

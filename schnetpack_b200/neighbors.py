@@ -33,9 +33,9 @@ def neighbor_list(positions: Tensor, cell: Optional[Tensor], pbc: Optional[Tenso
     n_atoms [B] atoms per system.  Returns ``idx_i, idx_j`` (int64), ``offsets`` [E,3] fp32 (and ``shifts`` int32).
 
     * ``capacity=None`` (default): exact size -- a counting pass, one host read of the pair count, then the fill pass;
-    * ``capacity=E_max``: no host synchronisation; with ``pad=True`` the result always has ``E_max`` entries, the tail being
-      self pairs at distance 2*cutoff (zero contribution to any cutoff-weighted model) -- the form to use under CUDA-graph
-      capture; the returned ``n_pairs`` tensor (device, int64 [2]) holds the true count and an overflow flag.
+    * ``capacity=E_max``: no host synchronisation; with ``pad=True`` the result always has ``E_max`` entries, the unused
+      capacity being spread over the rows as self pairs at distance 2*cutoff (zero contribution to any cutoff-weighted
+      model; ``idx_i`` stays sorted, no row grows long) -- the form to use under CUDA-graph capture; the returned ``n_pairs`` tensor (device, int64 [2]) holds the true count and an overflow flag.
     """
     if not positions.is_cuda:
         raise ValueError("schnetpack_b200.neighbors: positions must be a CUDA tensor (no CPU fallback)")
