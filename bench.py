@@ -282,6 +282,7 @@ def run_cuda(args, rank, world, local_rank):
         def step():
             return evaluate(fresh(resident))
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None   # polls every 100 ms from the warm-up on (GPU under load)
     for _ in range(max(args.warmup, 3)):
         out = step()
     torch.cuda.synchronize()
@@ -289,7 +290,6 @@ def run_cuda(args, rank, world, local_rank):
     ev["bwd"].clear()
     if dist is not None:
         dist.barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = _lib.launch_count
     step_ev = []
     torch.cuda.synchronize()
