@@ -78,3 +78,26 @@ def test_two_rank_sharded_evaluation_matches_single_process(tmp_path):
     z = np.load(out)
     np.testing.assert_allclose(z["e"], z["e_ref"], rtol=1e-12, atol=1e-12)
     np.testing.assert_allclose(z["f"], z["f_ref"], rtol=1e-10, atol=1e-12)
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the CUDA arm) needs no GPU and prints exactly one JSON
+    line with the contract keys; under N > 1 only rank 0 would print (exercised here at N = 1)."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--config", "cfg1",
+                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["higher_is_better"] is True and d["n_gpus"] == 1
+    for k in ("metric", "value", "unit", "steps", "warmup", "ms_per_step", "scaling", "dtype", "data", "config", "cpu_baseline",
+              "e2e"):
+        assert k in d, k
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
