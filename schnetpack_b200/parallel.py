@@ -80,7 +80,8 @@ def gather_results(results: Dict[str, torch.Tensor], n_systems_total: int, n_ato
         parts = [torch.empty_like(pad) for _ in range(world)]
         dist.all_gather(parts, pad, group=group)
         full = torch.cat([p[:s] for p, s in zip(parts, sizes)], dim=0)
-        assert full.shape[0] == (n_atoms_total if per_atom else n_systems_total) or True
+        if full.shape[0] != (n_atoms_total if per_atom else n_systems_total):
+            raise RuntimeError(f"gather_results: {k} has {full.shape[0]} rows after the gather")
         out[k] = full
     return out
 
