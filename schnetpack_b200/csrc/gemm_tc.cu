@@ -32,7 +32,7 @@
 //              correction accumulator and stages the raw tile in shared memory (the pipeline stages are free by then);
 //   all warps  epilogue: bias / activation (+ saved derivative) / addend / stores, 16 B per thread, whole 128 B lines
 //              per row segment (a thread-per-row epilogue kept only 4 warps busy and cost up to 60 % of the kernel).
-#include "common.cuh"
+#include "tcgen05.cuh"
 
 namespace {
 
@@ -42,7 +42,6 @@ constexpr int N_DRAIN = 8;                     // drain warps 0-7
 constexpr int W_MMA = 8;
 constexpr int W_PROD0 = 9;
 constexpr int OPER_A = TM * TK * 4;            // 8192 B: A tile, K-major, SWIZZLE_64B
-constexpr int SBO_BYTES = 8 * TK * 4;          // 512 B between consecutive 8-row groups
 
 template <int TN>
 struct Cfg {
@@ -71,61 +70,10 @@ struct Cfg {
 #define TRACE(slot) do { } while (0)
 #endif
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    // arrives on `bar` when every tcgen05.mma issued so far by this thread has completed (implies before_thread_sync)
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
 
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-    // K-major, SWIZZLE_64B: start>>4 [0,14) | LBO (unused, 1) [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout 4 [61,64)
-    return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(SBO_BYTES >> 4) << 32) | (1ull << 46) |
-           (4ull << 61);
-}
 
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
-}
 
-__device__ __forceinline__ float tf32_rn(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
 
 // 32 consecutive accumulator columns of this thread's TMEM lane -> registers
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -163,12 +111,6 @@ struct TcArgs {
 #endif
 };
 
-// byte offset of (row r, 16 B K-chunk c in 0..3) inside an operand tile: rows are 64 B, groups of 8 rows are 512 B atoms and
-// the chunk index is XOR-swizzled with bits [1,3) of the row (Swizzle<2,4,3>, the pattern the tensor core applies to the
-// byte address when the descriptor says SWIZZLE_64B).  Tiles are 512 B aligned.
-__host__ __device__ __forceinline__ int tile_off(int r, int c) {
-    return (r >> 3) * SBO_BYTES + (r & 7) * (TK * 4) + ((c ^ ((r >> 1) & 3)) << 4);
-}
 
 // Column-tile width.  A weight with N % 128 == 0 is packed in BOTH tile widths (the layouts differ); the launch picks 128
 // when N >= 256 or when 64-wide tiles would need more than one wave of CTAs (M = 3 x atoms in the mu channel mix).

@@ -193,38 +193,6 @@ __global__ void __launch_bounds__(NW * 32, SPK_EDGE_MINB(NW)) k_painn_edge_fwd(
 // ------------------------------------------------------------------------------------------------------------------
 // reverse pass, grouped by sender
 // ------------------------------------------------------------------------------------------------------------------
-// Sum over the 32 lanes of 16 values per lane (4 edges x 4 scalars) with a transposing butterfly: 16 shuffles instead of
-// 80.  Afterwards lane l holds the complete sum of value index 8*bit4 + 4*bit3 + 2*bit2 + bit1 (both lanes of a pair).
-__device__ __forceinline__ float butterfly16(float (&v)[16], int lane) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const bool up = lane & 16;
-        const float send = up ? v[i] : v[i + 8];
-        const float keep = up ? v[i + 8] : v[i];
-        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const bool up = lane & 8;
-        const float send = up ? v[i] : v[i + 4];
-        const float keep = up ? v[i + 4] : v[i];
-        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const bool up = lane & 4;
-        const float send = up ? v[i] : v[i + 2];
-        const float keep = up ? v[i + 2] : v[i];
-        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    }
-    {
-        const bool up = lane & 2;
-        const float send = up ? v[0] : v[1];
-        const float keep = up ? v[1] : v[0];
-        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-    }
-    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
-}
 
 template <int NW, int NRB, bool HAS_MU, int DEPTH>
 __global__ void __launch_bounds__(NW * 32, SPK_EDGE_MINB(NW)) k_painn_edge_bwd(

@@ -20,7 +20,8 @@
 //     edge-balanced receiver range, as a CTA of painn.cu did), 1 MMA-issuer warp, 2 producer warps; two Phi' stages and
 //     two TMEM accumulator sets (3 x 64 columns each) let chunk k+1's staging and MMAs overlap chunk k's gathers.
 // The reduction over a receiver's edges stays a private register accumulation in CSR order: deterministic, no atomics.
-#include "common.cuh"
+#include "painn_common.cuh"
+#include "tcgen05.cuh"
 
 #ifdef SPK_EDGE_TRACE
 __device__ long long g_edge_trace[148 * 256];
@@ -48,7 +49,6 @@ constexpr int NPROD = 3;                       // producer warps: chunk k -> war
 constexpr int NST = 3;                         // Phi' stages: chunk k -> stage k % NST (NPROD divides NST: one owner per stage)
 constexpr int NTHREADS = (W_PROD0 + NPROD) * 32;
 constexpr int KT = 16;                         // floats per operand K-tile (64 B rows, SWIZZLE_64B)
-constexpr int SBO_BYTES = 8 * KT * 4;          // 512 B between 8-row groups
 constexpr int A_TILE = F_TC * KT * 4;          // 8192 B
 constexpr int A_BYTES = 3 * 2 * 2 * A_TILE;    // [third][hi,lo][k-tile]
 constexpr int B_TILE = NE * KT * 4;            // 4096 B
@@ -58,56 +58,6 @@ constexpr int SMEM_BYTES = A_BYTES + NST * B_STAGE + NST * META_STAGE + 1024;
 constexpr int TMEM_COLS = 512;                 // [buf][third][64 edge columns] = 384 used
 constexpr int BUF_COLS = 3 * NE;
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-    // K-major, SWIZZLE_64B: start>>4 [0,14) | LBO (unused, 1) [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout 4 [61,64)
-    return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(SBO_BYTES >> 4) << 32) | (1ull << 46) |
-           (4ull << 61);
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-__device__ __forceinline__ float tf32_rn(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
 // 8 consecutive accumulator columns of this thread's TMEM lane -> registers (no wait: several loads are batched)
 __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, float (&v)[8]) {
     uint32_t r[8];
@@ -118,10 +68,6 @@ __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, float (&v)[8]) {
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// byte offset of (row r, 16 B K-chunk c in 0..3) inside a K-major SWIZZLE_64B operand tile (rows of 64 B)
-__host__ __device__ __forceinline__ int tile_off(int r, int c) {
-    return (r >> 3) * SBO_BYTES + (r & 7) * (KT * 4) + ((c ^ ((r >> 1) & 3)) << 4);
-}
 
 // [third][hi,lo][k-tile][128 x 16] operand tiles of  [w | b | 0]  (k = n_rbf is the bias column)
 __global__ void k_pack_filter(const float* __restrict__ wf, const float* __restrict__ bf, int n_rbf,
@@ -435,38 +381,6 @@ __device__ __forceinline__ void tmem_ld4_nowait(uint32_t taddr, float (&v)[4]) {
     for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// Sum over the 32 lanes of 16 values per lane (4 edges x 4 scalars) with a transposing butterfly: 16 shuffles instead of
-// 80.  Afterwards lane l holds the complete sum of value index 8*bit4 + 4*bit3 + 2*bit2 + bit1 (both lanes of a pair).
-__device__ __forceinline__ float butterfly16(float (&v)[16], int lane) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const bool up = lane & 16;
-        const float send = up ? v[i] : v[i + 8];
-        const float keep = up ? v[i + 8] : v[i];
-        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const bool up = lane & 8;
-        const float send = up ? v[i] : v[i + 4];
-        const float keep = up ? v[i + 4] : v[i];
-        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const bool up = lane & 4;
-        const float send = up ? v[i] : v[i + 2];
-        const float keep = up ? v[i + 2] : v[i];
-        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    }
-    {
-        const bool up = lane & 2;
-        const float send = up ? v[0] : v[1];
-        const float keep = up ? v[1] : v[0];
-        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-    }
-    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
-}
 
 template <bool HAS_MU>
 __global__ void __launch_bounds__(NTHREADS, 1) k_painn_edge_bwd_tc(

@@ -14,6 +14,7 @@
 //     forward kernel at all; the reverse kernel keeps one consumer-only named barrier per 32 edges for the cross-warp
 //     reduction of the four per-edge scalars.
 #include "painn_common.cuh"
+#include "tcgen05.cuh"
 
 namespace {
 
@@ -21,35 +22,6 @@ constexpr int DEPTH = 8;     // ring stages = edges in flight per CTA
 constexpr int RCH = 32;      // reverse kernel: edges per cross-warp reduction chunk
 constexpr int FCH = 32;      // forward kernel: slots per radial-basis/geometry chunk stage
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// TMA bulk copy global -> shared (1-D, size multiple of 16 B, both addresses 16 B aligned), completes on `bar`
-__device__ __forceinline__ void tma_load(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
 __device__ __forceinline__ void consumer_bar(int nthreads) {
     asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
 }
