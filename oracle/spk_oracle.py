@@ -164,8 +164,21 @@ def to_torch(d: dict, dtype=torch.float32, device=None) -> Dict[str, Tensor]:
     return out
 
 
+def apply_strain(x: Dict[str, Tensor]):
+    """atomistic/response.py:441-464 (Strain.forward): a zero strain leaf [B,3,3]; cell, positions and offsets are
+    multiplied by (1 + strain^T).  Returns (strain leaf, strained cell, positions, offsets)."""
+    strain = torch.zeros_like(x["_cell"]).requires_grad_(True)
+    st = strain.transpose(1, 2)
+    cell = x["_cell"] + torch.matmul(x["_cell"], st)                           # :448-450
+    s_i = st[x["_idx_m"]]
+    R = x["_positions"] + torch.matmul(x["_positions"][:, None, :], s_i).squeeze(1)      # :455-457
+    s_ij = s_i[x["_idx_i"]]
+    off = x["_offsets"] + torch.matmul(x["_offsets"][:, None, :], s_ij).squeeze(1)       # :461-463
+    return strain, cell, R, off
+
+
 def energy_forces(spec: dict, params: dict, inputs: dict, dtype=torch.float32, need_repr: bool = False, device=None,
-                  n_mol: Optional[int] = None):
+                  n_mol: Optional[int] = None, stress: bool = False):
     """model/base.py:174-190 (NeuralNetworkPotential.forward) for the modules
     [PairwiseDistances] -> {SchNet|PaiNN} -> [Atomwise, Forces]; forces = -dE/dR (atomistic/response.py:59-76).
 
@@ -180,9 +193,16 @@ def energy_forces(spec: dict, params: dict, inputs: dict, dtype=torch.float32, n
         n_mol = int(idx_m[-1]) + 1                                       # atomwise.py:80 (host sync, as in the reference)
     want_f = bool(spec.get("forces", True))
     direct_rij = "_Rij" in x
+    strain = cell_s = None
     if direct_rij:
         r_ij = x["_Rij"].clone().requires_grad_(want_f)
         R = None
+    elif stress:
+        x = dict(x)
+        x["_positions"] = x["_positions"].clone().requires_grad_(True)   # base.py:105-111
+        x["_cell"] = x["_cell"].reshape(-1, 3, 3)
+        strain, cell_s, R, off_s = apply_strain(x)                       # input module Strain before PairwiseDistances
+        r_ij = pairwise_distances(R, idx_i, idx_j, off_s)
     else:
         R = x["_positions"].clone().requires_grad_(want_f)               # base.py:105-111
         r_ij = pairwise_distances(R, idx_i, idx_j, x["_offsets"])
@@ -195,7 +215,12 @@ def energy_forces(spec: dict, params: dict, inputs: dict, dtype=torch.float32, n
     out["scalar_representation"] = q.detach()
     e = atomwise(p, q, idx_m, n_mol)
     out["energy"] = e.detach()
-    if want_f:
+    if stress:
+        g, gs = torch.autograd.grad([e], [R, strain], grad_outputs=[torch.ones_like(e)])      # response.py:62-68
+        out["forces"] = -g.detach()                                                           # wrt the strained positions
+        vol = torch.sum(cell_s[:, 0, :] * torch.cross(cell_s[:, 1, :], cell_s[:, 2, :], dim=1), dim=1, keepdim=True)[:, :, None]
+        out["stress"] = (gs / vol).detach()                                                   # :78-90
+    elif want_f:
         wrt = r_ij if direct_rij else R
         (g,) = torch.autograd.grad([e], [wrt], grad_outputs=[torch.ones_like(e)])   # response.py:62-68
         out["dEdRij" if direct_rij else "forces"] = g.detach() if direct_rij else -g.detach()

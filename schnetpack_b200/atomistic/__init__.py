@@ -15,7 +15,7 @@ from .. import nn as snn
 from .. import ops
 from .. import properties
 
-__all__ = ["PairwiseDistances", "Atomwise", "Forces"]
+__all__ = ["PairwiseDistances", "Atomwise", "Forces", "Strain"]
 
 
 class PairwiseDistances(nn.Module):
@@ -95,6 +95,25 @@ class Atomwise(nn.Module):
         return inputs
 
 
+class Strain(nn.Module):
+    """Adds a zero strain leaf and applies (1 + strain^T) to cell, positions and offsets so that ``Forces(calc_stress=True)``
+    can differentiate the energy with respect to it (response.py:434-464).  Plain tensor algebra on the device; the
+    derivative reaches the strain through the positions / offsets gradients of ``PairwiseDistances``."""
+
+    def forward(self, inputs: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        cell = inputs[properties.cell].reshape(-1, 3, 3)
+        eps = torch.zeros_like(cell).requires_grad_()
+        inputs[properties.strain] = eps
+        eps_t = eps.transpose(1, 2)
+        inputs[properties.cell] = cell + cell @ eps_t
+        per_atom = eps_t[inputs[properties.idx_m]]
+        R = inputs[properties.R]
+        inputs[properties.R] = R + torch.einsum("na,nab->nb", R, per_atom)
+        off = inputs[properties.offsets]
+        inputs[properties.offsets] = off + torch.einsum("ea,eab->eb", off, per_atom[inputs[properties.idx_i]])
+        return inputs
+
+
 class Forces(nn.Module):
     """forces = -dE/dR, stress = dE/dstrain / V via autograd over the kernel pipeline (response.py:18-92)."""
 
@@ -131,7 +150,7 @@ class Forces(nn.Module):
             stress = grads[-1]
             if stress is None:
                 stress = torch.zeros_like(inputs[properties.cell])
-            cell = inputs[properties.cell]
+            cell = inputs[properties.cell].reshape(-1, 3, 3)
             volume = torch.sum(cell[:, 0, :] * torch.cross(cell[:, 1, :], cell[:, 2, :], dim=1), dim=1,
                                keepdim=True)[:, :, None]
             inputs[self.stress_key] = stress / volume

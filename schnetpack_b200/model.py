@@ -178,10 +178,12 @@ def from_spec(spec: dict, params: Optional[dict] = None, device=None) -> NeuralN
         rep = representation.SchNet(spec["n_atom_basis"], spec["n_interactions"], rbf, cut,
                                     n_filters=spec["n_filters"], shared_interactions=spec["shared_interactions"])
     outs: List[nn.Module] = [atomistic.Atomwise(n_in=spec["n_atom_basis"], output_key="energy")]
-    if spec.get("forces", True):
-        outs.append(atomistic.Forces(energy_key="energy", force_key="forces"))
-    model = NeuralNetworkPotential(rep, [atomistic.PairwiseDistances()], outs, postprocessors=[],
-                                   do_postprocessing=False)
+    want_stress = bool(spec.get("stress", False))
+    if spec.get("forces", True) or want_stress:
+        outs.append(atomistic.Forces(calc_forces=bool(spec.get("forces", True)), calc_stress=want_stress,
+                                     energy_key="energy", force_key="forces"))
+    ins: List[nn.Module] = ([atomistic.Strain()] if want_stress else []) + [atomistic.PairwiseDistances()]
+    model = NeuralNetworkPotential(rep, ins, outs, postprocessors=[], do_postprocessing=False)
     if params is not None:
         import re
         sd = model.state_dict()

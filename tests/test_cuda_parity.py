@@ -210,3 +210,20 @@ def test_cuda_graph_replay_matches_eager_and_tracks_new_inputs():
     assert rel_err(out2["energy"].cpu().numpy(), ref["energy"].numpy()) < TOL
     assert rel_err(out2["forces"].cpu().numpy(), ref["forces"].numpy()) < TOL
     assert len(gp._cache) == 1
+
+
+def test_stress_through_strain_module_matches_reference():
+    """Optional part of row a14: ``Strain`` -> ``PairwiseDistances`` -> PaiNN -> ``Atomwise`` -> ``Forces(calc_stress=True)``
+    on the CUDA path == the unmodified reference (fixture painn_box_stress, fp64) within 1e-5 relative."""
+    import torch
+
+    from schnetpack_b200.model import batch_to_device, from_spec
+
+    spec, params, inputs, _, ref64 = load_case("painn_box_stress")
+    dev = torch.device("cuda:0")
+    model = from_spec(spec, params, dev)
+    out = model(batch_to_device(inputs, dev))
+    torch.cuda.synchronize()
+    for k in ("energy", "forces", "stress"):
+        err = rel_err(out[k].detach().cpu().numpy(), ref64[k])
+        assert err < 1e-5, (k, err)
