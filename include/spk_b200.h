@@ -10,7 +10,8 @@
  *   - every pointer is a DEVICE pointer to contiguous row-major data; floats are fp32, graph indices int32,
  *     user-facing neighbour indices (idx_i/idx_j/idx_m/Z) int64 exactly as the reference's tensors;
  *   - the caller owns every buffer (outputs and workspaces included); the library never allocates, never
- *     synchronises, keeps no global mutable state and only enqueues work on the given stream (graph-capturable);
+ *     synchronises, keeps no global mutable state (it reads no environment
+ *     variables; per-device launch attributes are cached) and only enqueues work on the given stream (graph-capturable);
  *   - return value: 0 = ok, SPK_ERR_ARG (-1) bad argument, SPK_ERR_UNSUPPORTED (-2) shape outside the compiled
  *     templates, -(1000 + cudaError_t) if a launch failed.  Nothing throws.
  *   - F = n_atom_basis (multiple of 32, <= 256), n_rbf <= 32, KP = SPK_KP(n_rbf) = n_rbf rounded up to 4.
@@ -43,7 +44,6 @@ typedef void* spk_stream_t; /* cudaStream_t */
 
 #define SPK_GEO_STRIDE 8 /* floats per edge in the geometry record: ux uy uz d fc dfc/dd 1/d 0 */
 #define SPK_NRB(n_rbf) ((n_rbf) <= 20 ? 20 : 32)          /* radial-basis capacity of the compiled edge kernels */
-#define SPK_REC(n_rbf) (2 * SPK_NRB(n_rbf) + SPK_GEO_STRIDE) /* floats of the combined per-slot record */
 
 int spk_version(void);
 
@@ -54,7 +54,8 @@ int spk_version(void);
  *       slot_j[s] and the position slot_eid[s] of that edge in the caller's idx_i/idx_j arrays.  If idx_i is already
  *       sorted (reference collate order) slots are the identity permutation; otherwise a stable grouping is built.
  *   sptr[N+1], pos_slot[E], pos_i[E]    : the same edges grouped by sender idx_j (ascending slot inside a group).
- *   status[4] (device int32): [0]=1 if idx_i was sorted, [1]=number of out-of-range indices (must be 0),
+ *   status[4] (device int32): [0]=1 if idx_i was sorted, [1]=number of out-of-range indices (must be 0; otherwise
+ *       rowptr and sptr are zeroed = an empty graph, so no consumer gathers through unwritten slots),
  *       [2]=max receiver degree, [3]=max sender degree.
  *   workspace: spk_graph_workspace_bytes(N, E) bytes.
  * ------------------------------------------------------------------------------------------------------------- */
@@ -70,26 +71,25 @@ int spk_segment_ptr(const int64_t* idx_m, int64_t n_atoms, int64_t n_mol, int32_
  * Geometry.  atomistic/distances.py:14-26 (PairwiseDistances), representation/painn.py:227-230,
  * representation/schnet.py:156-158, nn/radial.py, nn/cutoff.py:14-33.
  * ------------------------------------------------------------------------------------------------------------- */
-/* Rij[e] = R[idx_j[e]] - R[idx_i[e]] + offsets[e] */
-int spk_pairwise_fwd(const float* R, const int64_t* idx_i, const int64_t* idx_j, const float* offsets, int64_t n_edges,
-                     float* r_ij, spk_stream_t stream);
+/* Rij[e] = R[idx_j[e]] - R[idx_i[e]] + offsets[e]; an edge with an index outside [0, n_atoms) yields NaN (no OOB read) */
+int spk_pairwise_fwd(const float* R, const int64_t* idx_i, const int64_t* idx_j, const float* offsets, int64_t n_atoms,
+                     int64_t n_edges, float* r_ij, spk_stream_t stream);
 /* dE/dR[a] = sum_{e: j(e)=a} g[e] - sum_{e: i(e)=a} g[e]   (deterministic, no atomics); out = sign * that */
 int spk_pairwise_bwd(const float* g_rij, const int32_t* rowptr, const int32_t* slot_eid, const int32_t* sptr,
                      const int32_t* pos_slot, int64_t n_atoms, float sign, float* g_R, spk_stream_t stream);
 /* per CSR slot s (edge slot_eid[s]): phi[s,0:n_rbf] radial basis (zero padded to KP), dphi = d phi/dd,
- * geo[s] = (ux, uy, uz, d, fc, dfc/dd, 1/d, 0).  rbf_p0/p1 = offsets/widths (gaussian) or freqs/NULL (bessel).
- * erec (nullable): the same data as ONE record per slot, [E, SPK_REC(n_rbf)] = [phi (SPK_NRB, zero padded) | dphi | geo],
- * so that the reverse edge kernel stages a slot with a single TMA bulk copy. */
+ * geo[s] = (ux, uy, uz, d, fc, dfc/dd, 1/d, 0).  rbf_p0/p1 = offsets/widths (gaussian) or freqs/NULL (bessel). */
 int spk_edge_geometry(const float* r_ij, const int32_t* slot_eid, int64_t n_edges, int rbf_kind, int n_rbf,
                       const float* rbf_p0, const float* rbf_p1, float cutoff, float* phi, float* dphi, float* geo,
-                      float* erec, spk_stream_t stream);
+                      spk_stream_t stream);
 /* standalone radial basis / cutoff / activation (nn.GaussianRBF, nn.BesselRBF, nn.CosineCutoff, shifted_softplus
  * forward + derivative, used by the nn.* module mirrors).  d: [n]; out: [n, n_rbf]; dout nullable */
 int spk_rbf_fwd(const float* d, int64_t n, int rbf_kind, int n_rbf, const float* rbf_p0, const float* rbf_p1,
                 float* out, float* dout, spk_stream_t stream);
 int spk_cosine_cutoff_fwd(const float* d, int64_t n, float cutoff, float* out, float* dout, spk_stream_t stream);
 int spk_act_fwd(const float* x, int64_t n, int act, float* y, float* dy, spk_stream_t stream);
-/* out[a, :] = table[Z[a], :]   (nn.Embedding in representation/painn.py:239, schnet.py:161) */
+/* out[a, :] = table[Z[a], :]   (nn.Embedding in representation/painn.py:239, schnet.py:161); Z outside [0, n_rows)
+ * (nn.Embedding raises) gives a NaN row */
 int spk_embedding(const float* table, const int64_t* Z, int64_t n_atoms, int F, int n_rows, float* out,
                   spk_stream_t stream);
 /* out[idx[r], :] += x[r, :] for sorted-or-not idx via a row-pointer (deterministic): generic nn/scatter.py:7-34.
@@ -138,8 +138,7 @@ int spk_painn_edge_fwd(const float* x, const float* mu, const float* q, const fl
  *   g_rij[eid] (+)= dE/dr_ij through d (phi, fc) and u                           [E,3]   (accumulate != 0 -> +=)
  * The residual dE/dq_in = g_q is the caller's (identity).  */
 int spk_painn_edge_bwd(const float* x, const float* mu, const float* g_q, const float* g_mu, const float* phi,
-                       const float* dphi, const float* geo, const float* erec /* nullable, see spk_edge_geometry */,
-                       const int32_t* sptr, const int32_t* pos_slot,
+                       const float* dphi, const float* geo, const int32_t* sptr, const int32_t* pos_slot,
                        const int32_t* pos_i, const int32_t* slot_eid, const float* wf, const float* bf,
                        int64_t n_atoms, int64_t n_edges, int F, int n_rbf, float* g_x, float* g_mu_in, float* g_rij,
                        int accumulate, spk_stream_t stream);
@@ -163,20 +162,17 @@ int spk_painn_edge_bwd_tc(const float* x, const float* mu, const float* g_q, con
                           const int32_t* pos_i, const int32_t* slot_eid, const float* wf_packed, int64_t n_atoms,
                           int64_t n_edges, int F, int n_rbf, float* g_x, float* g_mu_in, float* g_rij, int accumulate,
                           spk_stream_t stream);
-/* "System-resident" variants for batches of small systems (molecules): edges never cross systems
- * (data/loader.py:35-46), so one CTA stages a system's sender rows in shared memory once and every gather is an LDS.
- * mol_ptr[n_mol+1] = first atom of each system (spk_segment_ptr).  Systems larger than the shared-memory capacity chosen
- * at launch (~1.1 x the average system size) use global gathers inside the same kernel; results are identical to the
- * streaming kernels above. */
-int spk_painn_edge_fwd_sys(const float* x, const float* mu, const float* q, const float* phi, const float* geo,
-                           const int32_t* rowptr, const int32_t* slot_j, const float* wf, const float* bf,
-                           const int32_t* mol_ptr, int64_t n_mol, int64_t n_atoms, int64_t n_edges, int F, int n_rbf,
-                           float* q_out, float* mu_out, spk_stream_t stream);
-int spk_painn_edge_bwd_sys(const float* x, const float* mu, const float* g_q, const float* g_mu, const float* phi,
-                           const float* dphi, const float* geo, const int32_t* sptr, const int32_t* pos_slot,
-                           const int32_t* pos_i, const int32_t* slot_eid, const float* wf, const float* bf,
-                           const int32_t* mol_ptr, int64_t n_mol, int64_t n_atoms, int64_t n_edges, int F, int n_rbf,
-                           float* g_x, float* g_mu_in, float* g_rij, int accumulate, spk_stream_t stream);
+/* Block-level interaction with a caller-supplied, materialised filter -- PaiNNInteraction.forward(q, mu, Wij, dir_ij, idx_i,
+ * idx_j, n_atoms), painn.py:31-67 (csrc/painn_block.cu).  Wij [E,3F] and dir [E,3] are in the CALLER's edge order (looked
+ * up through slot_eid); x = interatomic_context_net(q) [N,3F]; mu [N,3,F] required.  Reverse: g_x [N,3F], g_mu_in [N,3,F]
+ * (= g_mu + ...), g_W [E,3F], g_dir [E,3] in the caller's edge order, all overwritten. */
+int spk_painn_edge_wij_fwd(const float* x, const float* mu, const float* q, const float* Wij, const float* dir,
+                           const int32_t* rowptr, const int32_t* slot_j, const int32_t* slot_eid, int64_t n_atoms,
+                           int64_t n_edges, int F, float* q_out, float* mu_out, spk_stream_t stream);
+int spk_painn_edge_wij_bwd(const float* x, const float* mu, const float* g_q, const float* g_mu, const float* Wij,
+                           const float* dir, const int32_t* sptr, const int32_t* pos_slot, const int32_t* pos_i,
+                           const int32_t* slot_eid, int64_t n_atoms, int64_t n_edges, int F, float* g_x, float* g_mu_in,
+                           float* g_W, float* g_dir, spk_stream_t stream);
 /* painn.py:104-107: ctx[a] = [ q[a] | sqrt(sum_d V[a,d]^2 + eps) ], VW = mu_channel_mix(mu) [N,3,2F] */
 int spk_painn_mix_ctx(const float* q, const float* VW, int64_t n_atoms, int F, float eps, float* ctx,
                       spk_stream_t stream);

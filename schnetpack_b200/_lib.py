@@ -26,9 +26,9 @@ SIGNATURES = {
     "spk_graph_workspace_bytes": [c_int64, c_int64],
     "spk_graph_build": [P, P, c_int64, c_int64, P, P, P, P, P, P, P, P, c_size_t, P],
     "spk_segment_ptr": [P, c_int64, c_int64, P, P],
-    "spk_pairwise_fwd": [P, P, P, P, c_int64, P, P],
+    "spk_pairwise_fwd": [P, P, P, P, c_int64, c_int64, P, P],
     "spk_pairwise_bwd": [P, P, P, P, P, c_int64, c_float, P, P],
-    "spk_edge_geometry": [P, P, c_int64, c_int, c_int, P, P, c_float, P, P, P, P, P],
+    "spk_edge_geometry": [P, P, c_int64, c_int, c_int, P, P, c_float, P, P, P, P],
     "spk_rbf_fwd": [P, c_int64, c_int, c_int, P, P, P, P, P],
     "spk_cosine_cutoff_fwd": [P, c_int64, c_float, P, P, P],
     "spk_act_fwd": [P, c_int64, c_int, P, P, P],
@@ -39,14 +39,13 @@ SIGNATURES = {
     "spk_tc_pack_weight": [P, c_int, c_int, P, P],
     "spk_dense_tc": [P, c_int64, c_int, c_int64, P, c_int, P, c_int, P, c_int, P, c_int64, P, c_int64, P, P],
     "spk_painn_edge_fwd": [P, P, P, P, P, P, P, P, P, c_int64, c_int64, c_int, c_int, P, P, P],
-    "spk_painn_edge_bwd": [P, P, P, P, P, P, P, P, P, P, P, P, P, P, c_int64, c_int64, c_int, c_int, P, P, P, c_int, P],
+    "spk_painn_edge_bwd": [P, P, P, P, P, P, P, P, P, P, P, P, P, c_int64, c_int64, c_int, c_int, P, P, P, c_int, P],
     "spk_painn_filter_packed_floats": [],
     "spk_painn_pack_filter": [P, P, c_int, c_int, P, P],
     "spk_painn_edge_fwd_tc": [P, P, P, P, P, P, P, P, c_int64, c_int64, c_int, c_int, P, P, P],
     "spk_painn_edge_bwd_tc": [P, P, P, P, P, P, P, P, P, P, P, P, c_int64, c_int64, c_int, c_int, P, P, P, c_int, P],
-    "spk_painn_edge_fwd_sys": [P, P, P, P, P, P, P, P, P, P, c_int64, c_int64, c_int64, c_int, c_int, P, P, P],
-    "spk_painn_edge_bwd_sys": [P, P, P, P, P, P, P, P, P, P, P, P, P, P, c_int64, c_int64, c_int64, c_int, c_int, P, P, P,
-                               c_int, P],
+    "spk_painn_edge_wij_fwd": [P, P, P, P, P, P, P, P, c_int64, c_int64, c_int, P, P, P],
+    "spk_painn_edge_wij_bwd": [P, P, P, P, P, P, P, P, P, P, c_int64, c_int64, c_int, P, P, P, P, P],
     "spk_painn_mix_ctx": [P, P, c_int64, c_int, c_float, P, P],
     "spk_painn_mix_update": [P, P, P, P, c_int64, c_int, P, P, P],
     "spk_painn_mix_update_bwd": [P, P, P, P, c_int64, c_int, P, P, P],
@@ -100,7 +99,7 @@ def check(rc: int, name: str):
 
 
 # kernels launched per C-ABI call (default 1); bench.py reports the running total as ``gpu_launches``
-LAUNCHES = {"spk_graph_build": 7, "spk_atomwise_out": 2, "spk_neighbor_list": 6}
+LAUNCHES = {"spk_graph_build": 8, "spk_atomwise_out": 2, "spk_neighbor_list": 6}
 launch_count = 0
 
 

@@ -2,7 +2,6 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
-#include <stdlib.h>
 
 #include "../../include/spk_b200.h"
 
@@ -23,8 +22,7 @@ static inline cudaStream_t spk_st(spk_stream_t s) { return reinterpret_cast<cuda
 //     griddepcontrol.launch_dependents   -- the next kernel's CTAs may be scheduled as soon as all of ours are resident
 //     griddepcontrol.wait                -- block until the previous kernel has completed and its writes are visible
 // so the launch latency and CTA ramp-up of kernel n+1 overlap the tail of kernel n while the data dependence through
-// global memory stays exactly that of a serial stream (the wait precedes every global access).  SPK_B200_PDL=0 in the
-// environment restores plain launches.  Works under stream capture (programmatic graph edges, CUDA >= 12.3).
+// global memory stays exactly that of a serial stream (the wait precedes every global access).  Works under stream capture (programmatic graph edges, CUDA >= 12.3).
 #define SPK_PDL_LAUNCH_DEPENDENTS() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
 #define SPK_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
 #define SPK_PDL_ENTER()              \
@@ -33,14 +31,12 @@ static inline cudaStream_t spk_st(spk_stream_t s) { return reinterpret_cast<cuda
         SPK_PDL_WAIT();              \
     } while (0)
 
-static inline bool spk_use_pdl() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("SPK_B200_PDL");
-        v = (e && e[0] == '0') ? 0 : 1;
-    }
-    return v != 0;
-}
+// compile with -DSPK_NO_PDL to restore plain launches (A/B builds); the library reads no environment variables
+#ifdef SPK_NO_PDL
+constexpr int SPK_PDL_ATTRS = 0;
+#else
+constexpr int SPK_PDL_ATTRS = 1;
+#endif
 
 template <typename... KArgs, typename... Args>
 static inline void spk_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
@@ -54,7 +50,7 @@ static inline void spk_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = spk_use_pdl() ? 1 : 0;
+    cfg.numAttrs = SPK_PDL_ATTRS;
     (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // errors surface in SPK_LAUNCH_CHECK()
 }
 
@@ -62,17 +58,40 @@ static inline int64_t spk_cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 constexpr int SPK_NUM_SMS = 148;  // B200: 2 dies x 74 SMs
 
-// SM count of the current device (148 on B200); queried once.
-static inline int spk_num_sms() {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess ||
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-            n = SPK_NUM_SMS;
-    }
-    return n;
+// Per-device caches (a process may drive several GPUs): indexed by the CURRENT device of the calling thread, which the
+// host side sets to the device of the tensors before every call.  Entries are write-once values, so concurrent callers
+// at worst compute the same number twice.
+constexpr int SPK_MAX_DEVICES = 64;
+static inline int spk_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= SPK_MAX_DEVICES) dev = 0;
+    return dev;
 }
+
+// SM count of the current device (148 on B200).
+static inline int spk_num_sms() {
+    static int n[SPK_MAX_DEVICES] = {0};
+    const int dev = spk_device();
+    if (!n[dev]) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = SPK_NUM_SMS;
+        n[dev] = v;
+    }
+    return n[dev];
+}
+
+// opt a kernel in to `bytes` of dynamic shared memory once per device (the attribute is per device and function)
+struct SpkSmemOnce {
+    unsigned char done[SPK_MAX_DEVICES] = {0};
+    template <typename K>
+    cudaError_t set(K kernel, int bytes) {
+        const int dev = spk_device();
+        if (done[dev]) return cudaSuccess;
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e == cudaSuccess) done[dev] = 1;
+        return e;
+    }
+};
 
 __host__ __device__ __forceinline__ int spk_kp(int n_rbf) { return (n_rbf + 3) & ~3; }
 

@@ -363,13 +363,8 @@ __global__ void __launch_bounds__(Cfg<TN>::NTHREADS, 1) k_dense_tc(TcArgs g) {
 
 template <int TN, int A_ACT, int ACT>
 static int launch_tc(const TcArgs& g, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_dense_tc<TN, A_ACT, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             Cfg<TN>::SMEM_BYTES);
-        if (e != cudaSuccess) return SPK_CUDA_ERR(e);
-        attr_set = true;
-    }
+    static SpkSmemOnce once;
+    if (cudaError_t e = once.set(k_dense_tc<TN, A_ACT, ACT>, Cfg<TN>::SMEM_BYTES); e != cudaSuccess) return SPK_CUDA_ERR(e);
     dim3 grid((unsigned)spk_cdiv(g.M, TM), (unsigned)spk_cdiv(g.N, TN));
     spk_launch(k_dense_tc<TN, A_ACT, ACT>, grid, Cfg<TN>::NTHREADS, Cfg<TN>::SMEM_BYTES, st, g);
     return 0;

@@ -41,15 +41,19 @@ __device__ __forceinline__ void cutoff_eval(float d, float rc, float& fc, float&
 }
 
 __global__ void k_pairwise_fwd(const float* __restrict__ R, const int64_t* __restrict__ idx_i,
-                               const int64_t* __restrict__ idx_j, const float* __restrict__ off, int64_t n_edges,
-                               float* __restrict__ r_ij) {
+                               const int64_t* __restrict__ idx_j, const float* __restrict__ off, int64_t n_atoms,
+                               int64_t n_edges, float* __restrict__ r_ij) {
     SPK_PDL_ENTER();
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= n_edges * 3) return;
     int64_t e = t / 3;
     int c = (int)(t - e * 3);
     float o = off ? off[t] : 0.0f;
-    r_ij[t] = R[idx_j[e] * 3 + c] - R[idx_i[e] * 3 + c] + o;
+    const int64_t i = idx_i[e], j = idx_j[e];
+    // out-of-range neighbour indices (the reference raises IndexError): never read out of bounds, poison the edge instead
+    // (the graph build counts them in status[1] and empties the graph; the host raises on the first build of a new list)
+    const bool ok = i >= 0 && i < n_atoms && j >= 0 && j < n_atoms;
+    r_ij[t] = ok ? R[j * 3 + c] - R[i * 3 + c] + o : __int_as_float(0x7fc00000);
 }
 
 // one thread per (atom, component): deterministic sums over the receiver row and the sender row
@@ -72,8 +76,7 @@ __global__ void k_pairwise_bwd(const float* __restrict__ g, const int* __restric
 // one thread per slot computes the geometry record, then KP threads-worth of radial values are produced by a loop
 __global__ void k_edge_geometry(const float* __restrict__ r_ij, const int* __restrict__ slot_eid, int64_t n_edges,
                                 int kind, int n_rbf, int KP, const float* __restrict__ p0, const float* __restrict__ p1,
-                                float rc, float* __restrict__ phi, float* __restrict__ dphi, float* __restrict__ geo,
-                                float* __restrict__ erec, int NRB) {
+                                float rc, float* __restrict__ phi, float* __restrict__ dphi, float* __restrict__ geo) {
     SPK_PDL_ENTER();
     // thread (s, k): k in [0, KP)
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -87,17 +90,6 @@ __global__ void k_edge_geometry(const float* __restrict__ r_ij, const int* __res
     if (k < n_rbf) rbf_eval(kind, d, p0[k], p1 ? p1[k] : 0.0f, v, dv);
     phi[t] = v;
     if (dphi) dphi[t] = dv;
-    const int REC = 2 * NRB + SPK_GEO_STRIDE;
-    if (erec) {   // combined per-slot record [phi (NRB, zero padded) | dphi (NRB) | geo (8)]
-        float* rec = erec + s * REC;
-        rec[k] = v;
-        rec[NRB + k] = dv;
-        if (k == 0)
-            for (int kk = KP; kk < NRB; ++kk) {
-                rec[kk] = 0.f;
-                rec[NRB + kk] = 0.f;
-            }
-    }
     if (k == 0) {
         float fc, dfc;
         cutoff_eval(d, rc, fc, dfc);
@@ -107,11 +99,6 @@ __global__ void k_edge_geometry(const float* __restrict__ r_ij, const int* __res
         float4* gp = reinterpret_cast<float4*>(geo + s * SPK_GEO_STRIDE);
         gp[0] = g0;
         gp[1] = g1;
-        if (erec) {
-            float4* rp = reinterpret_cast<float4*>(erec + s * REC + 2 * NRB);
-            rp[0] = g0;
-            rp[1] = g1;
-        }
     }
 }
 
@@ -155,10 +142,12 @@ __global__ void k_embedding(const float* __restrict__ table, const int64_t* __re
     if (t >= n_atoms * F4) return;
     int64_t a = t / F4;
     int c = (int)(t - a * F4);
-    int64_t z = Z[a];
-    if (z < 0) z = 0;
-    if (z >= n_rows) z = n_rows - 1;
-    reinterpret_cast<float4*>(out)[t] = reinterpret_cast<const float4*>(table)[z * F4 + c];
+    const int64_t z = Z[a];
+    // nn.Embedding raises for z outside [0, n_rows); a kernel cannot raise, so the row is poisoned with NaN (loud in every
+    // output) instead of being clamped to a valid element
+    const float qn = __int_as_float(0x7fc00000);
+    reinterpret_cast<float4*>(out)[t] = (z >= 0 && z < n_rows) ? reinterpret_cast<const float4*>(table)[z * F4 + c]
+                                                                : make_float4(qn, qn, qn, qn);
 }
 
 // out[r, c] = sum_{s in row r} x[slot_eid[s], c]; thread per (r, c)
@@ -189,11 +178,11 @@ __global__ void k_add(const float* __restrict__ a, const float* __restrict__ b, 
 #define GRID1D(n, T) (unsigned)spk_cdiv((n), (T)), (T), 0, spk_st(stream)
 
 extern "C" int spk_pairwise_fwd(const float* R, const int64_t* idx_i, const int64_t* idx_j, const float* offsets,
-                                int64_t n_edges, float* r_ij, spk_stream_t stream) {
-    if (n_edges < 0) return SPK_ERR_ARG;
+                                int64_t n_atoms, int64_t n_edges, float* r_ij, spk_stream_t stream) {
+    if (n_edges < 0 || n_atoms < 0) return SPK_ERR_ARG;
     if (n_edges == 0) return SPK_OK;
     if (!R || !idx_i || !idx_j || !r_ij) return SPK_ERR_ARG;
-    spk_launch(k_pairwise_fwd, GRID1D(n_edges * 3, 256), R, idx_i, idx_j, offsets, n_edges, r_ij);
+    spk_launch(k_pairwise_fwd, GRID1D(n_edges * 3, 256), R, idx_i, idx_j, offsets, n_atoms, n_edges, r_ij);
     SPK_LAUNCH_CHECK();
     return SPK_OK;
 }
@@ -210,7 +199,7 @@ extern "C" int spk_pairwise_bwd(const float* g_rij, const int32_t* rowptr, const
 
 extern "C" int spk_edge_geometry(const float* r_ij, const int32_t* slot_eid, int64_t n_edges, int rbf_kind, int n_rbf,
                                  const float* rbf_p0, const float* rbf_p1, float cutoff, float* phi, float* dphi,
-                                 float* geo, float* erec, spk_stream_t stream) {
+                                 float* geo, spk_stream_t stream) {
     if (n_edges < 0 || n_rbf <= 0) return SPK_ERR_ARG;
     if (n_rbf > 32) return SPK_ERR_UNSUPPORTED;
     if (rbf_kind != SPK_RBF_GAUSSIAN && rbf_kind != SPK_RBF_BESSEL) return SPK_ERR_ARG;
@@ -219,7 +208,7 @@ extern "C" int spk_edge_geometry(const float* r_ij, const int32_t* slot_eid, int
     if (rbf_kind == SPK_RBF_GAUSSIAN && !rbf_p1) return SPK_ERR_ARG;
     int KP = spk_kp(n_rbf);
     spk_launch(k_edge_geometry, GRID1D(n_edges * KP, 256), r_ij, slot_eid, n_edges, rbf_kind, n_rbf, KP, rbf_p0, rbf_p1,
-                                                   cutoff, phi, dphi, geo, erec, SPK_NRB(n_rbf));
+                                                   cutoff, phi, dphi, geo);
     SPK_LAUNCH_CHECK();
     return SPK_OK;
 }

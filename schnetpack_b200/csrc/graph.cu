@@ -121,6 +121,19 @@ __global__ void k_fill_csc(const int* __restrict__ slot_j, int64_t n_edges, cons
     tmp_slot[p] = (int)s;
 }
 
+// Bad input (status[1] != 0: some idx_i/idx_j outside [0, n_atoms)): the fill/rank kernels above returned early and left the
+// slot arrays unwritten, so the row pointers are zeroed -- every consumer (edge, cfconv, pairwise kernels) then sees an
+// EMPTY graph instead of gathering through garbage indices.  The host raises IndexError when it builds a new list outside
+// stream capture (ops.EdgeGraph); inside a captured graph the caller can poll status[1].
+__global__ void k_guard(int* __restrict__ rowptr, int* __restrict__ sptr, int n, const int* __restrict__ status) {
+    SPK_PDL_ENTER();
+    if (status[1] == 0) return;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k <= n; k += gridDim.x * blockDim.x) {
+        rowptr[k] = 0;
+        sptr[k] = 0;
+    }
+}
+
 __global__ void k_segment_ptr(const int64_t* __restrict__ idx_m, int64_t n_atoms, int64_t n_mol,
                               int* __restrict__ mol_ptr) {
     SPK_PDL_ENTER();
@@ -176,6 +189,7 @@ extern "C" int spk_graph_build(const int64_t* idx_i, const int64_t* idx_j, int64
         spk_launch(k_rank_rows, gw, T, 0, st, rowptr, n_int, tmp_a, idx_j, nullptr, 0, status, slot_eid, slot_j);
         spk_launch(k_fill_csc, ge, T, 0, st, slot_j, n_edges, sptr, cur_j, status, tmp_a);
         spk_launch(k_rank_rows, gw, T, 0, st, sptr, n_int, tmp_a, idx_i, slot_eid, 1, status, pos_slot, pos_i);
+        spk_launch(k_guard, (unsigned)(n_atoms / 256 + 1 < 64 ? n_atoms / 256 + 1 : 64), 256, 0, st, rowptr, sptr, n_int, status);
     }
     SPK_LAUNCH_CHECK();
     return SPK_OK;

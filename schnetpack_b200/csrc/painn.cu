@@ -8,8 +8,6 @@
 // back as warp-broadcast LDS.128, sender rows x[j], mu[j] are gathered with fully coalesced 128 B requests, and the
 // reduction over a receiver's edges is a private register accumulation (CSR order) -- no atomics, no shuffles.
 // CTAs take edge-balanced contiguous row ranges (binary search in rowptr).
-#include <cstdlib>
-
 #include "painn_common.cuh"
 
 namespace {
@@ -18,20 +16,6 @@ namespace {
 #define SPK_EDGE_MINB(NW) (512 / ((NW) * 32))   // resident CTAs per SM the register allocation is sized for
 #endif
 constexpr int CH = 32;   // edges staged per chunk (multiple of the 4-edge reduction groups of the reverse kernel)
-
-// Gather pipeline: every thread copies ITS channel of the next DEPTH edges' rows global -> shared with 4-byte cp.async
-// (LDGSTS, a coalesced 128 B request per warp) into slots only it reads back, so the ring needs no barrier -- just
-// cp.async.wait_group.  With plain register loads a CTA had one edge in flight (measured: the kernel ran at the
-// L2 latency x edges / resident CTAs bound); register prefetching did not help because the six scoreboards alias.
-__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src)
-                 : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
 
 // cooperative staging of contiguous per-slot records [n, KP] -> smem [n, NRB] (zero padded)
 template <int NRB, int NTHR>
@@ -45,7 +29,7 @@ __device__ __forceinline__ void stage_rows_contig(float* __restrict__ dst, const
     }
 }
 
-template <int NW, int NRB, bool HAS_MU, int DEPTH>
+template <int NW, int NRB, bool HAS_MU>
 __global__ void __launch_bounds__(NW * 32, SPK_EDGE_MINB(NW)) k_painn_edge_fwd(
     const float* __restrict__ x, const float* __restrict__ mu, const float* __restrict__ q,
     const float* __restrict__ phi, const float* __restrict__ geo, const int* __restrict__ rowptr,
@@ -57,8 +41,6 @@ __global__ void __launch_bounds__(NW * 32, SPK_EDGE_MINB(NW)) k_painn_edge_fwd(
     __shared__ __align__(16) float s_phi[CH * NRB];
     __shared__ __align__(16) float s_geo[CH * SPK_GEO_STRIDE];
     __shared__ int s_j[CH];
-    constexpr int NV = HAS_MU ? 6 : 2;                       // gathered values per edge and channel
-    __shared__ float s_ring[DEPTH > 0 ? DEPTH : 1][NV][F];
 
     const int c = threadIdx.x;
     const int nb = gridDim.x, b = blockIdx.x;
@@ -100,28 +82,7 @@ __global__ void __launch_bounds__(NW * 32, SPK_EDGE_MINB(NW)) k_painn_edge_fwd(
         for (int t = threadIdx.x; t < n; t += NTHR) s_j[t] = slot_j[cs + t];
         __syncthreads();
 
-        auto issue = [&](int t, int slot) {
-            const int j = s_j[t];
-            const float* __restrict__ xj = x + (size_t)j * (3 * F) + c;
-            cp_async4(&s_ring[slot][0][c], xj);
-            cp_async4(&s_ring[slot][1][c], xj + F);
-            if (HAS_MU) {
-                cp_async4(&s_ring[slot][2][c], xj + 2 * F);
-                const float* __restrict__ mj = mu + (size_t)j * (3 * F) + c;
-                cp_async4(&s_ring[slot][3][c], mj);
-                cp_async4(&s_ring[slot][4][c], mj + F);
-                cp_async4(&s_ring[slot][5][c], mj + 2 * F);
-            }
-        };
-        if (DEPTH > 0) {
-#pragma unroll
-            for (int d = 0; d < DEPTH; ++d) {
-                if (d < n) issue(d, d);
-                cp_async_commit();
-            }
-        }
-
-#pragma unroll(DEPTH > 0 ? DEPTH : 2)
+#pragma unroll 2
         for (int t = 0; t < n; ++t) {
             const int s = cs + t;
             while (s >= next_boundary) {
@@ -130,20 +91,7 @@ __global__ void __launch_bounds__(NW * 32, SPK_EDGE_MINB(NW)) k_painn_edge_fwd(
                 next_boundary = rowptr[i + 1];
             }
             float xa, xb, xc = 0.f, m0 = 0.f, m1 = 0.f, m2 = 0.f;
-            if (DEPTH > 0) {
-                const int slot = t % (DEPTH > 0 ? DEPTH : 1);
-                cp_async_wait<(DEPTH > 0 ? DEPTH - 1 : 0)>();
-                xa = s_ring[slot][0][c];
-                xb = s_ring[slot][1][c];
-                if (HAS_MU) {
-                    xc = s_ring[slot][2][c];
-                    m0 = s_ring[slot][3][c];
-                    m1 = s_ring[slot][4][c];
-                    m2 = s_ring[slot][5][c];
-                }
-                if (t + DEPTH < n) issue(t + DEPTH, slot);      // the slot's values are in registers: refill it
-                cp_async_commit();
-            } else {
+            {
                 const int j = s_j[t];
                 const float* __restrict__ xj = x + (size_t)j * (3 * F) + c;
                 xa = xj[0];
@@ -194,7 +142,7 @@ __global__ void __launch_bounds__(NW * 32, SPK_EDGE_MINB(NW)) k_painn_edge_fwd(
 // reverse pass, grouped by sender
 // ------------------------------------------------------------------------------------------------------------------
 
-template <int NW, int NRB, bool HAS_MU, int DEPTH>
+template <int NW, int NRB, bool HAS_MU>
 __global__ void __launch_bounds__(NW * 32, SPK_EDGE_MINB(NW)) k_painn_edge_bwd(
     const float* __restrict__ x, const float* __restrict__ mu, const float* __restrict__ g_q,
     const float* __restrict__ g_mu, const float* __restrict__ phi, const float* __restrict__ dphi,
@@ -211,8 +159,6 @@ __global__ void __launch_bounds__(NW * 32, SPK_EDGE_MINB(NW)) k_painn_edge_bwd(
     __shared__ int s_i[CH];
     __shared__ int s_eid[CH];
     __shared__ float s_red[CH][NW][4];
-    static_assert(DEPTH == 0 || DEPTH == 4, "the gather ring is indexed by the position in the 4-edge reduction group");
-    __shared__ float s_ring[DEPTH > 0 ? DEPTH : 1][4][F];    // g_q[i], g_mu[i,0..2] of the next DEPTH edges
 
     const int c = threadIdx.x;
     const int lane = c & 31, warp = c >> 5;
@@ -286,21 +232,6 @@ __global__ void __launch_bounds__(NW * 32, SPK_EDGE_MINB(NW)) k_painn_edge_bwd(
         }
         __syncthreads();
 
-        auto issue = [&](int t, int slot) {
-            const int i = s_i[t];
-            cp_async4(&s_ring[slot][0][c], g_q + (size_t)i * F + c);
-            const float* __restrict__ gmi = g_mu + (size_t)i * (3 * F) + c;
-            cp_async4(&s_ring[slot][1][c], gmi);
-            cp_async4(&s_ring[slot][2][c], gmi + F);
-            cp_async4(&s_ring[slot][3][c], gmi + 2 * F);
-        };
-        if (DEPTH > 0) {
-#pragma unroll
-            for (int d = 0; d < DEPTH; ++d) {
-                if (d < n) issue(d, d);
-                cp_async_commit();
-            }
-        }
         for (int t0 = 0; t0 < n; t0 += 4) {
             float red[16];
 #pragma unroll
@@ -318,15 +249,7 @@ __global__ void __launch_bounds__(NW * 32, SPK_EDGE_MINB(NW)) k_painn_edge_bwd(
                         load_own(j);
                     }
                     float gq, g0, g1, g2;
-                    if (DEPTH > 0) {
-                        cp_async_wait<(DEPTH > 0 ? DEPTH - 1 : 0)>();
-                        gq = s_ring[u][0][c];
-                        g0 = s_ring[u][1][c];
-                        g1 = s_ring[u][2][c];
-                        g2 = s_ring[u][3][c];
-                        if (t + DEPTH < n) issue(t + DEPTH, u);      // values are in registers: refill the slot
-                        cp_async_commit();
-                    } else {
+                    {
                         const int i = s_i[t];
                         gq = g_q[(size_t)i * F + c];
                         const float* __restrict__ gmi = g_mu + (size_t)i * (3 * F) + c;
@@ -510,77 +433,30 @@ __global__ void k_mix_ctx_bwd(const float* __restrict__ g_ctx, const float* __re
     gv[4 * F] += gn * v2;
 }
 
-// gather pipeline depth of the streaming kernels: 0 (plain register loads, default) or 4 (cp.async ring, SPK_B200_EDGE=async;
-// measured slower: LDGSTS costs 8 LSU cycles per operation and the kernel is bound by the LSU / L2 fill path)
-int edge_depth() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("SPK_B200_EDGE");
-        v = (e && e[0] == 'a') ? 4 : 0;
-    }
-    return v;
-}
-
-template <int NW, int NRB, int DEPTH>
-int launch_edge_fwd_d(const float* x, const float* mu, const float* q, const float* phi, const float* geo,
-                    const int* rowptr, const int* slot_j, const float* wf, const float* bf, int n_atoms, int n_edges,
-                    int n_rbf, float* q_out, float* mu_out, cudaStream_t st) {
-    // exactly one resident wave of CTAs (no tail), >= 32 edges per CTA, at most one CTA per atom
-    static int occ_mu = 0, occ_nomu = 0;
-    if (!occ_mu) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_mu, k_painn_edge_fwd<NW, NRB, true, DEPTH>, NW * 32, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_nomu, k_painn_edge_fwd<NW, NRB, false, DEPTH>, NW * 32, 0);
-        if (occ_mu < 1) occ_mu = 1;
-        if (occ_nomu < 1) occ_nomu = 1;
-    }
-    int64_t nb = (int64_t)spk_num_sms() * (mu ? occ_mu : occ_nomu);
-    if (nb > spk_cdiv((int64_t)n_edges, 32)) nb = spk_cdiv((int64_t)n_edges, 32);
-    if (nb < 1) nb = 1;
-    if (nb > n_atoms) nb = n_atoms;
-    if (mu)
-        spk_launch(k_painn_edge_fwd<NW, NRB, true, DEPTH>, (unsigned)nb, NW * 32, 0, st, x, mu, q, phi, geo, rowptr, slot_j, wf, bf,
-                                                                         n_atoms, n_edges, n_rbf, q_out, mu_out);
-    else
-        spk_launch(k_painn_edge_fwd<NW, NRB, false, DEPTH>, (unsigned)nb, NW * 32, 0, st, x, mu, q, phi, geo, rowptr, slot_j, wf, bf,
-                                                                          n_atoms, n_edges, n_rbf, q_out, mu_out);
-    return 0;
-}
-
-template <int NW, int NRB, int DEPTH>
-int launch_edge_bwd_d(const float* x, const float* mu, const float* g_q, const float* g_mu, const float* phi,
-                    const float* dphi, const float* geo, const int* sptr, const int* pos_slot, const int* pos_i,
-                    const int* slot_eid, const float* wf, const float* bf, int n_atoms, int n_edges, int n_rbf,
-                    float* g_x, float* g_mu_in, float* g_rij, int accumulate, cudaStream_t st) {
-    static int occ_mu = 0, occ_nomu = 0;
-    if (!occ_mu) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_mu, k_painn_edge_bwd<NW, NRB, true, DEPTH>, NW * 32, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_nomu, k_painn_edge_bwd<NW, NRB, false, DEPTH>, NW * 32, 0);
-        if (occ_mu < 1) occ_mu = 1;
-        if (occ_nomu < 1) occ_nomu = 1;
-    }
-    int64_t nb = (int64_t)spk_num_sms() * (mu ? occ_mu : occ_nomu);
-    if (nb > spk_cdiv((int64_t)n_edges, 32)) nb = spk_cdiv((int64_t)n_edges, 32);
-    if (nb < 1) nb = 1;
-    if (nb > n_atoms) nb = n_atoms;
-    if (mu)
-        spk_launch(k_painn_edge_bwd<NW, NRB, true, DEPTH>, (unsigned)nb, NW * 32, 0, st, 
-            x, mu, g_q, g_mu, phi, dphi, geo, sptr, pos_slot, pos_i, slot_eid, wf, bf, n_atoms, n_edges, n_rbf, g_x,
-            g_mu_in, g_rij, accumulate);
-    else
-        spk_launch(k_painn_edge_bwd<NW, NRB, false, DEPTH>, (unsigned)nb, NW * 32, 0, st, 
-            x, mu, g_q, g_mu, phi, dphi, geo, sptr, pos_slot, pos_i, slot_eid, wf, bf, n_atoms, n_edges, n_rbf, g_x,
-            g_mu_in, g_rij, accumulate);
-    return 0;
-}
-
 template <int NW, int NRB>
 int launch_edge_fwd(const float* x, const float* mu, const float* q, const float* phi, const float* geo,
                     const int* rowptr, const int* slot_j, const float* wf, const float* bf, int n_atoms, int n_edges,
                     int n_rbf, float* q_out, float* mu_out, cudaStream_t st) {
-    return edge_depth() ? launch_edge_fwd_d<NW, NRB, 4>(x, mu, q, phi, geo, rowptr, slot_j, wf, bf, n_atoms, n_edges, n_rbf,
-                                                        q_out, mu_out, st)
-                        : launch_edge_fwd_d<NW, NRB, 0>(x, mu, q, phi, geo, rowptr, slot_j, wf, bf, n_atoms, n_edges, n_rbf,
-                                                        q_out, mu_out, st);
+    // exactly one resident wave of CTAs (no tail), >= 32 edges per CTA, at most one CTA per atom
+    static int occ_mu = 0, occ_nomu = 0;      // occupancy of a template instantiation: the same on every B200 of a box
+    if (!occ_mu) {
+        int a = 0, b = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_painn_edge_fwd<NW, NRB, true>, NW * 32, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_painn_edge_fwd<NW, NRB, false>, NW * 32, 0);
+        occ_nomu = b < 1 ? 1 : b;
+        occ_mu = a < 1 ? 1 : a;
+    }
+    int64_t nb = (int64_t)spk_num_sms() * (mu ? occ_mu : occ_nomu);
+    if (nb > spk_cdiv((int64_t)n_edges, 32)) nb = spk_cdiv((int64_t)n_edges, 32);
+    if (nb < 1) nb = 1;
+    if (nb > n_atoms) nb = n_atoms;
+    if (mu)
+        spk_launch(k_painn_edge_fwd<NW, NRB, true>, (unsigned)nb, NW * 32, 0, st, x, mu, q, phi, geo, rowptr, slot_j, wf, bf,
+                   n_atoms, n_edges, n_rbf, q_out, mu_out);
+    else
+        spk_launch(k_painn_edge_fwd<NW, NRB, false>, (unsigned)nb, NW * 32, 0, st, x, mu, q, phi, geo, rowptr, slot_j, wf, bf,
+                   n_atoms, n_edges, n_rbf, q_out, mu_out);
+    return 0;
 }
 
 template <int NW, int NRB>
@@ -588,34 +464,28 @@ int launch_edge_bwd(const float* x, const float* mu, const float* g_q, const flo
                     const float* dphi, const float* geo, const int* sptr, const int* pos_slot, const int* pos_i,
                     const int* slot_eid, const float* wf, const float* bf, int n_atoms, int n_edges, int n_rbf,
                     float* g_x, float* g_mu_in, float* g_rij, int accumulate, cudaStream_t st) {
-    return edge_depth() ? launch_edge_bwd_d<NW, NRB, 4>(x, mu, g_q, g_mu, phi, dphi, geo, sptr, pos_slot, pos_i, slot_eid, wf,
-                                                        bf, n_atoms, n_edges, n_rbf, g_x, g_mu_in, g_rij, accumulate, st)
-                        : launch_edge_bwd_d<NW, NRB, 0>(x, mu, g_q, g_mu, phi, dphi, geo, sptr, pos_slot, pos_i, slot_eid, wf,
-                                                        bf, n_atoms, n_edges, n_rbf, g_x, g_mu_in, g_rij, accumulate, st);
-}
-
-// one-time choice of the streaming edge-kernel variant via SPK_B200_EDGE: "ldg" (this file; default, fastest in r1) or "tma"
-bool use_tma_variant() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("SPK_B200_EDGE");
-        v = (e && e[0] == 't' && e[1] == 'm') ? 1 : 0;   // "tma" ("tc" selects painn_tc.cu, in ops.py)
+    static int occ_mu = 0, occ_nomu = 0;
+    if (!occ_mu) {
+        int a = 0, b = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_painn_edge_bwd<NW, NRB, true>, NW * 32, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_painn_edge_bwd<NW, NRB, false>, NW * 32, 0);
+        occ_nomu = b < 1 ? 1 : b;
+        occ_mu = a < 1 ? 1 : a;
     }
-    return v == 1;
+    int64_t nb = (int64_t)spk_num_sms() * (mu ? occ_mu : occ_nomu);
+    if (nb > spk_cdiv((int64_t)n_edges, 32)) nb = spk_cdiv((int64_t)n_edges, 32);
+    if (nb < 1) nb = 1;
+    if (nb > n_atoms) nb = n_atoms;
+    if (mu)
+        spk_launch(k_painn_edge_bwd<NW, NRB, true>, (unsigned)nb, NW * 32, 0, st, x, mu, g_q, g_mu, phi, dphi, geo, sptr,
+                   pos_slot, pos_i, slot_eid, wf, bf, n_atoms, n_edges, n_rbf, g_x, g_mu_in, g_rij, accumulate);
+    else
+        spk_launch(k_painn_edge_bwd<NW, NRB, false>, (unsigned)nb, NW * 32, 0, st, x, mu, g_q, g_mu, phi, dphi, geo, sptr,
+                   pos_slot, pos_i, slot_eid, wf, bf, n_atoms, n_edges, n_rbf, g_x, g_mu_in, g_rij, accumulate);
+    return 0;
 }
-inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace
-
-template <int NW, int NRB>
-int spk_launch_edge_fwd_tma(const float* x, const float* mu, const float* q, const float* phi, const float* geo,
-                            const int* rowptr, const int* slot_j, const float* wf, const float* bf, int n_atoms,
-                            int n_edges, int n_rbf, float* q_out, float* mu_out, cudaStream_t st);
-template <int NW, int NRB>
-int spk_launch_edge_bwd_tma(const float* x, const float* mu, const float* g_q, const float* g_mu, const float* erec,
-                            const int* sptr, const int* pos_slot, const int* pos_i,
-                            const int* slot_eid, const float* wf, const float* bf, int n_atoms, int n_edges, int n_rbf,
-                            float* g_x, float* g_mu_in, float* g_rij, int accumulate, cudaStream_t st);
 
 #define DISPATCH_F_NRB(CALL)                                                   \
     do {                                                                       \
@@ -642,14 +512,9 @@ extern "C" int spk_painn_edge_fwd(const float* x, const float* mu, const float* 
     if (n_edges > 0 && (!phi || !geo || !slot_j)) return SPK_ERR_ARG;
     if (mu && mu == mu_out) return SPK_ERR_ARG;
     cudaStream_t st = spk_st(stream);
-    // the TMA variant needs 16 B-aligned rows (true for every torch allocation; F % 32 == 0 keeps row strides aligned)
-    const bool tma = use_tma_variant() && n_edges > 0 && aligned16(x) && aligned16(mu) && aligned16(phi) && aligned16(geo) &&
-                     spk_kp(n_rbf) == SPK_NRB(n_rbf);   // chunked radial-basis rows need an unpadded [E, NRB] array
-#define CALL_FWD(NW, NRB)                                                                                              \
-    (tma ? spk_launch_edge_fwd_tma<NW, NRB>(x, mu, q, phi, geo, rowptr, slot_j, wf, bf, (int)n_atoms, (int)n_edges,    \
-                                            n_rbf, q_out, mu_out, st)                                                  \
-         : launch_edge_fwd<NW, NRB>(x, mu, q, phi, geo, rowptr, slot_j, wf, bf, (int)n_atoms, (int)n_edges, n_rbf,     \
-                                    q_out, mu_out, st))
+#define CALL_FWD(NW, NRB)                                                                                          \
+    launch_edge_fwd<NW, NRB>(x, mu, q, phi, geo, rowptr, slot_j, wf, bf, (int)n_atoms, (int)n_edges, n_rbf, q_out, \
+                             mu_out, st)
     DISPATCH_F_NRB(CALL_FWD);
 #undef CALL_FWD
     SPK_LAUNCH_CHECK();
@@ -657,8 +522,7 @@ extern "C" int spk_painn_edge_fwd(const float* x, const float* mu, const float* 
 }
 
 extern "C" int spk_painn_edge_bwd(const float* x, const float* mu, const float* g_q, const float* g_mu,
-                                  const float* phi, const float* dphi, const float* geo, const float* erec,
-                                  const int32_t* sptr,
+                                  const float* phi, const float* dphi, const float* geo, const int32_t* sptr,
                                   const int32_t* pos_slot, const int32_t* pos_i, const int32_t* slot_eid,
                                   const float* wf, const float* bf, int64_t n_atoms, int64_t n_edges, int F, int n_rbf,
                                   float* g_x, float* g_mu_in, float* g_rij, int accumulate, spk_stream_t stream) {
@@ -669,12 +533,9 @@ extern "C" int spk_painn_edge_bwd(const float* x, const float* mu, const float* 
     if (mu && !g_mu_in) return SPK_ERR_ARG;
     if (n_edges > 0 && (!phi || !dphi || !geo || !pos_slot || !pos_i || !slot_eid || !g_rij)) return SPK_ERR_ARG;
     cudaStream_t st = spk_st(stream);
-    const bool tma = use_tma_variant() && n_edges > 0 && erec && aligned16(g_q) && aligned16(g_mu) && aligned16(erec);
-#define CALL_BWD(NW, NRB)                                                                                               \
-    (tma ? spk_launch_edge_bwd_tma<NW, NRB>(x, mu, g_q, g_mu, erec, sptr, pos_slot, pos_i, slot_eid, wf, bf,            \
-                                            (int)n_atoms, (int)n_edges, n_rbf, g_x, g_mu_in, g_rij, accumulate, st)     \
-         : launch_edge_bwd<NW, NRB>(x, mu, g_q, g_mu, phi, dphi, geo, sptr, pos_slot, pos_i, slot_eid, wf, bf,          \
-                                    (int)n_atoms, (int)n_edges, n_rbf, g_x, g_mu_in, g_rij, accumulate, st))
+#define CALL_BWD(NW, NRB)                                                                                           \
+    launch_edge_bwd<NW, NRB>(x, mu, g_q, g_mu, phi, dphi, geo, sptr, pos_slot, pos_i, slot_eid, wf, bf, (int)n_atoms, \
+                             (int)n_edges, n_rbf, g_x, g_mu_in, g_rij, accumulate, st)
     DISPATCH_F_NRB(CALL_BWD);
 #undef CALL_BWD
     SPK_LAUNCH_CHECK();

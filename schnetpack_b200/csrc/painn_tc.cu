@@ -740,14 +740,9 @@ extern "C" int spk_painn_edge_fwd_tc(const float* x, const float* mu, const floa
     if (mu && mu == mu_out) return SPK_ERR_ARG;
     if ((reinterpret_cast<uintptr_t>(phi) | reinterpret_cast<uintptr_t>(geo) | reinterpret_cast<uintptr_t>(wf_packed)) & 15)
         return SPK_ERR_UNSUPPORTED;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_painn_edge_fwd_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(k_painn_edge_fwd_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        if (e != cudaSuccess) return SPK_CUDA_ERR(e);
-        attr_set = true;
-    }
+    static SpkSmemOnce once_mu, once_nomu;
+    if (cudaError_t e = once_mu.set(k_painn_edge_fwd_tc<true>, SMEM_BYTES); e != cudaSuccess) return SPK_CUDA_ERR(e);
+    if (cudaError_t e = once_nomu.set(k_painn_edge_fwd_tc<false>, SMEM_BYTES); e != cudaSuccess) return SPK_CUDA_ERR(e);
     int64_t nb = spk_num_sms();
     if (nb > spk_cdiv(n_edges, NE)) nb = spk_cdiv(n_edges, NE);
     if (nb > n_atoms) nb = n_atoms;
@@ -778,14 +773,9 @@ extern "C" int spk_painn_edge_bwd_tc(const float* x, const float* mu, const floa
     if ((reinterpret_cast<uintptr_t>(phi) | reinterpret_cast<uintptr_t>(dphi) | reinterpret_cast<uintptr_t>(geo) |
          reinterpret_cast<uintptr_t>(wf_packed)) & 15)
         return SPK_ERR_UNSUPPORTED;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_painn_edge_bwd_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_B);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(k_painn_edge_bwd_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_B);
-        if (e != cudaSuccess) return SPK_CUDA_ERR(e);
-        attr_set = true;
-    }
+    static SpkSmemOnce once_mu, once_nomu;
+    if (cudaError_t e = once_mu.set(k_painn_edge_bwd_tc<true>, SMEM_BYTES_B); e != cudaSuccess) return SPK_CUDA_ERR(e);
+    if (cudaError_t e = once_nomu.set(k_painn_edge_bwd_tc<false>, SMEM_BYTES_B); e != cudaSuccess) return SPK_CUDA_ERR(e);
     int64_t nb = spk_num_sms();
     if (nb > spk_cdiv(n_edges, NEB)) nb = spk_cdiv(n_edges, NEB);
     if (nb > n_atoms) nb = n_atoms;

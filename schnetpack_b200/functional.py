@@ -54,7 +54,6 @@ class PaiNNPack(ParamPack):
         F, T = mod.n_atom_basis, mod.n_interactions
         self.F, self.T = F, T
         self.eps = float(mod.mixing[0].epsilon)
-        self.emb = _c(mod.embedding.weight)
         fw, fb = _c(mod.filter_net.weight), _c(mod.filter_net.bias)
         self.wf, self.bf = [], []
         for t in range(T):
@@ -84,42 +83,66 @@ def _packed_filter(pk: "PaiNNPack", t: int, n_rbf: int, n_edges: int):
     return pk.wfp[t]
 
 
+# ---- per-block pipelines (pure functions over detached fp32 CUDA tensors) -------------------------------------------
+def painn_context_fwd(b, q: Tensor, act: int):
+    """x = interatomic_context_net(q) [N,3F] (painn.py:54) and the saved act'(pre) of its first layer."""
+    a, hpre = b["c0"].fwd(q, act, save_deriv=True)
+    return b["c1"].fwd(a), hpre
+
+
+def painn_context_bwd(b, g_x: Tensor, hpre: Tensor, addend: Optional[Tensor] = None) -> Tensor:
+    """dE/dq through the context net (+ ``addend``, the residual stream's gradient)."""
+    g_a = b["c1"].bwd(g_x)                                                                   # [N,3F]x[3F,F]
+    return b["c0"].bwd(g_a, a_pre=hpre, a_act=ops.ACT_GIVEN, addend=addend)                  # [N,F]x[F,F]
+
+
+def painn_mixing_fwd(b, q1: Tensor, mu1: Tensor, F: int, eps: float, act: int):
+    """PaiNNMixing.forward (painn.py:103-116): returns q2, mu2 and the tape (VW, act'(cpre), s)."""
+    N = q1.shape[0]
+    VW = b["mix"].fwd(mu1.view(3 * N, F))                                                    # :103  [3N,2F]
+    ctx = ops.painn_mix_ctx(q1, VW, F, eps)                                                  # :104-107
+    c, cpre = b["m0"].fwd(ctx, act, save_deriv=True)                                         # :108
+    s = b["m1"].fwd(c)
+    q2, mu2 = ops.painn_mix_update(q1, mu1, s, VW, F)                                        # :110-116
+    return q2, mu2, (VW, cpre, s)
+
+
+def painn_mixing_bwd(b, g_q: Tensor, g_mu: Tensor, tape, F: int, eps: float):
+    """(dE/dq2, dE/dmu2) -> (dE/dq1, dE/dmu1)."""
+    VW, cpre, s = tape
+    N = g_q.shape[0]
+    g_s, g_VW = ops.painn_mix_update_bwd(g_q, g_mu, s, VW, F)
+    g_c = b["m1"].bwd(g_s)                                                                   # [N,3F]x[3F,F]
+    g_ctx = b["m0"].bwd(g_c, a_pre=cpre, a_act=ops.ACT_GIVEN)                                # [N,F]x[F,2F]
+    g_q1 = ops.painn_mix_ctx_bwd(g_ctx, g_q, VW, g_VW, F, eps)
+    g_mu1 = b["mix"].bwd(g_VW.view(3 * N, 2 * F), addend=g_mu.view(3 * N, F)).view(N, 3, F)
+    return g_q1, g_mu1
+
+
 def painn_forward(pk: PaiNNPack, q0: Tensor, r_ij: Tensor, graph: ops.EdgeGraph, rbf_kind: int, n_rbf: int,
-                  rbf_p0: Tensor, rbf_p1: Optional[Tensor], cutoff: float, act: int, need_grad: bool,
-                  mol_ptr: Optional[Tensor] = None, n_mol: int = 0):
+                  rbf_p0: Tensor, rbf_p1: Optional[Tensor], cutoff: float, act: int, need_grad: bool):
     """Returns q [N,F], mu [N,3,F] and the tape needed by painn_backward."""
     F = pk.F
-    N = q0.shape[0]
-    if need_grad:
-        phi, dphi, geo, erec = ops.edge_geometry(r_ij, graph, rbf_kind, n_rbf, rbf_p0, rbf_p1, cutoff, True, want_rec=True)
-    else:
-        phi, dphi, geo = ops.edge_geometry(r_ij, graph, rbf_kind, n_rbf, rbf_p0, rbf_p1, cutoff, False)
-        erec = None
+    phi, dphi, geo = ops.edge_geometry(r_ij, graph, rbf_kind, n_rbf, rbf_p0, rbf_p1, cutoff, need_grad)
     q, mu = q0, None
     tape = []
     for t in range(pk.T):
         b = pk.blocks[t]
-        a, hpre = b["c0"].fwd(q, act, save_deriv=True)                                         # painn.py:54
-        x = b["c1"].fwd(a)
+        x, hpre = painn_context_fwd(b, q, act)                                               # painn.py:54
         q1, mu1 = ops.painn_edge_fwd(x, mu, q, phi, geo, graph, pk.wf[t], pk.bf[t], F, n_rbf,   # :55-65
-                                     mol_ptr=mol_ptr, n_mol=n_mol,
                                      wf_packed=_packed_filter(pk, t, n_rbf, graph.n_edges))
-        VW = b["mix"].fwd(mu1.view(3 * N, F))                                                # :103  [3N,2F]
-        ctx = ops.painn_mix_ctx(q1, VW, F, pk.eps)                                           # :104-107
-        c, cpre = b["m0"].fwd(ctx, act, save_deriv=True)                                       # :108
-        s = b["m1"].fwd(c)
-        q2, mu2 = ops.painn_mix_update(q1, mu1, s, VW, F)                                    # :110-116
+        q2, mu2, mtape = painn_mixing_fwd(b, q1, mu1, F, pk.eps, act)                        # :103-116
         if need_grad:
-            tape.append((hpre, x, mu, VW, cpre, s))
+            tape.append((hpre, x, mu, mtape))
         q, mu = q2, mu2
-    return q, mu, (phi, dphi, geo, erec, tape, mol_ptr, n_mol)
+    return q, mu, (phi, dphi, geo, tape)
 
 
 def painn_backward(pk: PaiNNPack, saved, graph: ops.EdgeGraph, n_rbf: int, act: int, g_q: Tensor,
                    g_mu: Optional[Tensor], n_edges_total: int) -> Tensor:
     """dE/dr_ij [E,3] (in the caller's edge order) from dE/dq [N,F], dE/dmu [N,3,F]."""
     F = pk.F
-    phi, dphi, geo, erec, tape, mol_ptr, n_mol = saved
+    phi, dphi, geo, tape = saved
     N = g_q.shape[0]
     dev = g_q.device
     g_rij = torch.empty((n_edges_total, 3), dtype=torch.float32, device=dev)
@@ -127,21 +150,14 @@ def painn_backward(pk: PaiNNPack, saved, graph: ops.EdgeGraph, n_rbf: int, act: 
         g_mu = torch.zeros((N, 3, F), dtype=torch.float32, device=dev)
     for t in reversed(range(pk.T)):
         b = pk.blocks[t]
-        hpre, x, mu_in, VW, cpre, s = tape[t]
-        # --- mixing (painn.py:103-116) reversed
-        g_s, g_VW = ops.painn_mix_update_bwd(g_q, g_mu, s, VW, F)
-        g_c = b["m1"].bwd(g_s)                                                               # [N,3F]x[3F,F]
-        g_ctx = b["m0"].bwd(g_c, a_pre=cpre, a_act=ops.ACT_GIVEN)                                      # [N,F]x[F,2F]
-        g_q1 = ops.painn_mix_ctx_bwd(g_ctx, g_q, VW, g_VW, F, pk.eps)
-        g_mu1 = b["mix"].bwd(g_VW.view(3 * N, 2 * F), addend=g_mu.view(3 * N, F)).view(N, 3, F)
-        # --- interaction (painn.py:54-65) reversed
+        hpre, x, mu_in, mtape = tape[t]
+        g_q1, g_mu1 = painn_mixing_bwd(b, g_q, g_mu, mtape, F, pk.eps)                       # painn.py:103-116 reversed
         g_x, g_mu0 = ops.painn_edge_bwd(x, mu_in, g_q1, g_mu1, phi, dphi, geo, graph, pk.wf[t], pk.bf[t], F, n_rbf,
-                                        g_rij, accumulate=(t != pk.T - 1), erec=erec, mol_ptr=mol_ptr, n_mol=n_mol,
+                                        g_rij, accumulate=(t != pk.T - 1),                   # :54-65 reversed
                                         wf_packed=_packed_filter(pk, t, n_rbf, graph.n_edges))
         if t == 0:
             break   # dE/dq0 would only reach the (position-independent) embedding: the first context net is not reversed
-        g_a = b["c1"].bwd(g_x)                                                               # [N,3F]x[3F,F]
-        g_q = b["c0"].bwd(g_a, a_pre=hpre, a_act=ops.ACT_GIVEN, addend=g_q1)                           # [N,F]x[F,F] + residual
+        g_q = painn_context_bwd(b, g_x, hpre, addend=g_q1)
         g_mu = g_mu0
     return g_rij
 
@@ -154,9 +170,9 @@ class PaiNNFunction(torch.autograd.Function):
         mod, graph = holder["module"], holder["graph"]
         pk = mod._pack()
         need = r_ij.requires_grad
-        q, mu, saved = painn_forward(pk, q0, r_ij.detach(), graph, mod._rbf_kind, mod._n_rbf, mod._rbf_p0,
-                                     mod._rbf_p1, mod._cutoff_value, mod._act, need,
-                                     mol_ptr=holder.get("mol_ptr"), n_mol=holder.get("n_mol", 0))
+        with ops.device_of(r_ij, q0):
+            q, mu, saved = painn_forward(pk, q0, r_ij.detach(), graph, mod._rbf_kind, mod._n_rbf, mod._rbf_p0,
+                                         mod._rbf_p1, mod._cutoff_value, mod._act, need)
         ctx.holder = dict(pk=pk, saved=saved, graph=graph, n_rbf=mod._n_rbf, act=mod._act, E=r_ij.shape[0])
         ctx.set_materialize_grads(False)
         return q, mu
@@ -165,12 +181,125 @@ class PaiNNFunction(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_q, g_mu):
         h = ctx.holder
-        g_q = g_q.contiguous() if g_q is not None else None
-        if g_q is None:
-            g_q = torch.zeros((h["graph"].n_atoms, h["pk"].F), dtype=torch.float32, device=g_mu.device)
-        g_mu = g_mu.contiguous() if g_mu is not None else None
-        g_rij = painn_backward(h["pk"], h["saved"], h["graph"], h["n_rbf"], h["act"], g_q, g_mu, h["E"])
+        some = g_q if g_q is not None else g_mu
+        with ops.device_of(some):
+            g_q = g_q.contiguous() if g_q is not None else None
+            if g_q is None:
+                g_q = torch.zeros((h["graph"].n_atoms, h["pk"].F), dtype=torch.float32, device=g_mu.device)
+            g_mu = g_mu.contiguous() if g_mu is not None else None
+            g_rij = painn_backward(h["pk"], h["saved"], h["graph"], h["n_rbf"], h["act"], g_q, g_mu, h["E"])
         return g_rij, None, None
+
+
+# ---- block-level autograd functions ---------------------------------------------------------------------------------
+# The same kernels, exposed per block: the reference's block API (PaiNNInteraction.forward / PaiNNMixing.forward,
+# painn.py:31-67,92-117) and the spatially decomposed evaluation of ONE large system (parallel.py: a halo exchange of ghost
+# rows sits between the context net and the edge kernel of every block) are compositions of these.
+class EdgeGeometry:
+    """Per-evaluation radial basis / cutoff / unit-vector records of an edge list (shared by all interaction blocks)."""
+
+    def __init__(self, mod, r_ij: Tensor, graph: ops.EdgeGraph, need_grad: bool = True):
+        self.graph, self.n_rbf, self.E = graph, mod._n_rbf, r_ij.shape[0]
+        with ops.device_of(r_ij):
+            self.phi, self.dphi, self.geo = ops.edge_geometry(r_ij.detach().contiguous(), graph, mod._rbf_kind, mod._n_rbf,
+                                                              mod._rbf_p0, mod._rbf_p1, mod._cutoff_value, need_grad)
+
+
+class PaiNNContextFunction(torch.autograd.Function):
+    """q [N,F] -> x = interatomic_context_net(q) [N,3F]."""
+
+    @staticmethod
+    def forward(ctx, q, blk, act):
+        with ops.device_of(q):
+            x, hpre = painn_context_fwd(blk, q.detach().contiguous(), act)
+        ctx.blk, ctx.hpre = blk, hpre
+        return x
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_x):
+        with ops.device_of(g_x):
+            return painn_context_bwd(ctx.blk, g_x.contiguous(), ctx.hpre), None, None
+
+
+class PaiNNEdgeFunction(torch.autograd.Function):
+    """(x [N,3F], mu [N,3,F] | None, q [N,F], r_ij [E,3]) -> (q + dq, mu + dmu) with the filter evaluated in-kernel from the
+    shared ``EdgeGeometry``; backward returns dE/dx, dE/dmu, dE/dq and this block's contribution to dE/dr_ij."""
+
+    @staticmethod
+    def forward(ctx, x, mu, q, r_ij, geom, pk, t):
+        g = geom.graph
+        xd = x.detach().contiguous()
+        mud = mu.detach().contiguous() if mu is not None else None
+        with ops.device_of(xd):
+            q1, mu1 = ops.painn_edge_fwd(xd, mud, q.detach().contiguous(), geom.phi, geom.geo, g, pk.wf[t], pk.bf[t], pk.F,
+                                         geom.n_rbf, wf_packed=_packed_filter(pk, t, geom.n_rbf, g.n_edges))
+        ctx.h = (xd, mud, geom, pk, t)
+        ctx.set_materialize_grads(False)
+        return q1, mu1
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_q1, g_mu1):
+        xd, mud, geom, pk, t = ctx.h
+        g = geom.graph
+        N, F = g.n_atoms, pk.F
+        dev = xd.device
+        with ops.device_of(xd):
+            g_q1 = g_q1.contiguous() if g_q1 is not None else torch.zeros((N, F), dtype=torch.float32, device=dev)
+            g_mu1 = g_mu1.contiguous() if g_mu1 is not None else torch.zeros((N, 3, F), dtype=torch.float32, device=dev)
+            g_rij = torch.empty((geom.E, 3), dtype=torch.float32, device=dev)
+            g_x, g_mu0 = ops.painn_edge_bwd(xd, mud, g_q1, g_mu1, geom.phi, geom.dphi, geom.geo, g, pk.wf[t], pk.bf[t], F,
+                                            geom.n_rbf, g_rij, accumulate=False,
+                                            wf_packed=_packed_filter(pk, t, geom.n_rbf, g.n_edges))
+        return g_x, g_mu0, g_q1, g_rij, None, None, None
+
+
+class PaiNNEdgeWijFunction(torch.autograd.Function):
+    """Interaction with a caller-supplied filter (painn.py:55-65): (x, mu, q, Wij [E,3F], dir_ij [E,3]) -> (q', mu')."""
+
+    @staticmethod
+    def forward(ctx, x, mu, q, Wij, dir_ij, graph, F):
+        t = [v.detach().contiguous() for v in (x, mu, q, Wij, dir_ij)]
+        with ops.device_of(*t):
+            q1, mu1 = ops.painn_edge_wij_fwd(t[0], t[1], t[2], t[3], t[4], graph, F)
+        ctx.h = (t[0], t[1], t[3], t[4], graph, F)
+        ctx.set_materialize_grads(False)
+        return q1, mu1
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_q1, g_mu1):
+        x, mu, Wij, dir_ij, graph, F = ctx.h
+        N, dev = graph.n_atoms, x.device
+        with ops.device_of(x):
+            g_q1 = g_q1.contiguous() if g_q1 is not None else torch.zeros((N, F), dtype=torch.float32, device=dev)
+            g_mu1 = g_mu1.contiguous() if g_mu1 is not None else torch.zeros((N, 3, F), dtype=torch.float32, device=dev)
+            g_x, g_mu0, g_W, g_dir = ops.painn_edge_wij_bwd(x, mu, g_q1, g_mu1, Wij, dir_ij, graph, F)
+        return g_x, g_mu0, g_q1, g_W, g_dir, None, None
+
+
+class PaiNNMixingFunction(torch.autograd.Function):
+    """PaiNNMixing.forward (painn.py:92-117): (q [N,F], mu [N,3,F]) -> (q', mu')."""
+
+    @staticmethod
+    def forward(ctx, q, mu, blk, F, eps, act):
+        with ops.device_of(q, mu):
+            q2, mu2, tape = painn_mixing_fwd(blk, q.detach().contiguous(), mu.detach().contiguous(), F, eps, act)
+        ctx.h = (blk, tape, F, eps)
+        ctx.set_materialize_grads(False)
+        return q2, mu2
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_q, g_mu):
+        blk, tape, F, eps = ctx.h
+        N, dev = tape[2].shape[0], tape[2].device
+        with ops.device_of(tape[2]):
+            g_q = g_q.contiguous() if g_q is not None else torch.zeros((N, F), dtype=torch.float32, device=dev)
+            g_mu = g_mu.contiguous() if g_mu is not None else torch.zeros((N, 3, F), dtype=torch.float32, device=dev)
+            g_q1, g_mu1 = painn_mixing_bwd(blk, g_q, g_mu, tape, F, eps)
+        return g_q1, g_mu1, None, None, None, None
 
 
 # =====================================================================================================================
@@ -179,7 +308,6 @@ class PaiNNFunction(torch.autograd.Function):
 class SchNetPack(ParamPack):
     def build(self, mod):
         self.F, self.T, self.NF = mod.n_atom_basis, len(mod.interactions), mod.n_filters
-        self.emb = _c(mod.embedding.weight)
         self.blocks = []
         for it in mod.interactions:
             f0, f1 = it.filter_network[0], it.filter_network[1]
@@ -240,8 +368,9 @@ class SchNetFunction(torch.autograd.Function):
         mod, graph = holder["module"], holder["graph"]
         pk = mod._pack()
         need = r_ij.requires_grad
-        x, saved = schnet_forward(pk, x0, r_ij.detach(), graph, mod._rbf_kind, mod._n_rbf, mod._rbf_p0, mod._rbf_p1,
-                                  mod._cutoff_value, mod._act, need)
+        with ops.device_of(r_ij, x0):
+            x, saved = schnet_forward(pk, x0, r_ij.detach(), graph, mod._rbf_kind, mod._n_rbf, mod._rbf_p0, mod._rbf_p1,
+                                      mod._cutoff_value, mod._act, need)
         ctx.holder = dict(pk=pk, saved=saved, graph=graph, n_rbf=mod._n_rbf, act=mod._act, E=r_ij.shape[0])
         return x
 
@@ -249,8 +378,37 @@ class SchNetFunction(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_x):
         h = ctx.holder
-        g_rij = schnet_backward(h["pk"], h["saved"], h["graph"], h["n_rbf"], h["act"], g_x.contiguous(), h["E"])
+        with ops.device_of(g_x):
+            g_rij = schnet_backward(h["pk"], h["saved"], h["graph"], h["n_rbf"], h["act"], g_x.contiguous(), h["E"])
         return g_rij, None, None
+
+
+class CFConvFunction(torch.autograd.Function):
+    """Continuous-filter convolution of the block-level API (schnet.py:62-67): (h [N,F], Wij [E,F], rcut [E]) ->
+    m[i] = sum_{e: idx_i[e]=i} h[idx_j[e]] * Wij[e] * rcut[e], with all three gradients.  Wij / rcut arrive in the caller's
+    edge order; the permutation to receiver-slot order is an index_select (data movement only)."""
+
+    @staticmethod
+    def forward(ctx, h, Wij, rcut, graph):
+        hd = h.detach().contiguous()
+        with ops.device_of(hd, Wij, rcut):
+            eid = graph.slot_eid[:graph.n_edges].long()
+            w_slot = Wij.detach().index_select(0, eid).contiguous()
+            geo = torch.zeros((graph.n_edges, ops.GEO_STRIDE), dtype=torch.float32, device=hd.device)
+            geo[:, 4] = rcut.detach().reshape(-1).index_select(0, eid)
+            m = ops.cfconv_fwd(hd, w_slot, geo, graph, hd.shape[1])
+        ctx.h = (hd, w_slot, geo, graph, eid, rcut.shape)
+        return m
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_m):
+        hd, w_slot, geo, graph, eid, rshape = ctx.h
+        with ops.device_of(hd):
+            g_h, g_w_slot, g_fc_slot = ops.cfconv_bwd(hd, w_slot, geo, g_m.contiguous(), graph, hd.shape[1])
+            g_W = torch.empty_like(g_w_slot).index_copy_(0, eid, g_w_slot)
+            g_rc = torch.empty_like(g_fc_slot).index_copy_(0, eid, g_fc_slot).view(rshape)
+        return g_h, g_W, g_rc, None
 
 
 # =====================================================================================================================
@@ -263,9 +421,10 @@ class AtomwiseFunction(torch.autograd.Function):
     def forward(ctx, q, holder):
         pk, idx_m, n_mol, act = holder["pack"], holder["idx_m"], holder["n_mol"], holder["act"]
         qd = q.detach().contiguous()
-        hid, hpre = pk["l0"].fwd(qd, act, save_deriv=True)
-        mol_ptr = ops.segment_ptr(idx_m, n_mol) if idx_m is not None else None
-        y, energy = ops.atomwise_out(hid, pk["w1"], pk["b1"], mol_ptr, n_mol)
+        with ops.device_of(qd):
+            hid, hpre = pk["l0"].fwd(qd, act, save_deriv=True)
+            mol_ptr = ops.segment_ptr(idx_m, n_mol) if idx_m is not None else None
+            y, energy = ops.atomwise_out(hid, pk["w1"], pk["b1"], mol_ptr, n_mol)
         ctx.holder = dict(pk=pk, hpre=hpre, idx_m=idx_m, act=act, N=q.shape[0])
         ctx.set_materialize_grads(False)
         if energy is None:
@@ -279,6 +438,7 @@ class AtomwiseFunction(torch.autograd.Function):
         pk = h["pk"]
         H = pk["w1"].shape[0]
         g_hid = None
+        torch.cuda.set_device(pk["w1"].device)       # autograd worker thread: make the parameters' device current
         if h["idx_m"] is not None and g_e is not None and g_e.numel() > 0:
             g_hid = ops.atomwise_out_bwd(g_e.contiguous(), h["idx_m"], pk["w1"], h["N"], H)
         if g_y is not None:  # per-atom output used downstream (rare): g_hid += g_y (x) w1  -- plumbing-level torch op
@@ -298,13 +458,15 @@ class PairwiseDistancesFunction(torch.autograd.Function):
         idx_i, idx_j = holder["idx_i"], holder["idx_j"]
         ctx.holder = holder
         ctx.off_grad = offsets is not None and offsets.requires_grad
-        return ops.pairwise_fwd(R.detach().contiguous(), idx_i, idx_j,
-                                offsets.detach().contiguous() if offsets is not None else None)
+        with ops.device_of(R, idx_i, idx_j):
+            return ops.pairwise_fwd(R.detach().contiguous(), idx_i, idx_j,
+                                    offsets.detach().contiguous() if offsets is not None else None)
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_rij):
         g_rij = g_rij.contiguous()
         graph = ctx.holder["graph"]
-        g_R = ops.pairwise_bwd(g_rij, graph, 1.0)
+        with ops.device_of(g_rij):
+            g_R = ops.pairwise_bwd(g_rij, graph, 1.0)
         return g_R, (g_rij if ctx.off_grad else None), None

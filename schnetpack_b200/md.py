@@ -44,6 +44,9 @@ class DeviceMD:
         self.energy: Optional[Tensor] = None
         self.forces: Optional[Tensor] = None
         self.n_pairs: Optional[Tensor] = None
+        # sticky bookkeeping of the fixed-capacity neighbour list, updated INSIDE the captured step: [0] = largest pair
+        # count seen so far, [1] = 1 if any step overflowed ``capacity`` (its list was then truncated)
+        self.nl_watch = torch.zeros(2, dtype=torch.int64, device=dev)
         self._graph = None
         self.steps_done = 0
         self._calculate()                       # forces at t = 0 (simulator.py:118)
@@ -61,6 +64,7 @@ class DeviceMD:
             self.energy.copy_(e)
             self.forces.copy_(f)
             self.n_pairs.copy_(x["_n_pairs"])
+        torch.maximum(self.nl_watch, x["_n_pairs"], out=self.nl_watch)
 
     def _step(self):
         self.momenta.add_(self.forces, alpha=0.5 * self.dt)                  # integrators.py:70   half_step
@@ -94,7 +98,18 @@ class DeviceMD:
             else:
                 self._step()
         self.steps_done += int(n_steps)
+        self.check_neighbor_list()
         return self.energy, self.forces
+
+    def check_neighbor_list(self):
+        """One host read per ``run``: raise if ANY step since the start overflowed the list capacity (the search then
+        dropped pairs and the trajectory is wrong from that step on).  ``peak_pairs`` tells how much head-room is left."""
+        peak, over = (int(v) for v in self.nl_watch.tolist())
+        self.peak_pairs = peak
+        if over:
+            raise RuntimeError(
+                f"DeviceMD: the neighbour list overflowed its capacity of {self.nl.capacity} pairs during the run (peak "
+                f"{peak}); the trajectory is invalid from that step on -- re-create DeviceMD with a larger capacity")
 
     def kinetic_energy(self) -> Tensor:
         return 0.5 * (self.momenta ** 2 / self.masses).sum()

@@ -76,7 +76,17 @@ class NeuralNetworkPotential(AtomisticModel):
         self.collect_derivatives()
         self.collect_outputs()
 
+    # set by ``convert_model`` for models that arrive in double precision (spkmd loads every model as fp64 first,
+    # md/calculators/schnetpack_calculator.py:98): floating inputs are cast to fp32 on entry, results back on exit
+    cast_inputs: bool = False
+
     def forward(self, inputs: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        out_dtype = None
+        if self.cast_inputs:
+            for k, v in list(inputs.items()):
+                if v.is_floating_point() and v.dtype != torch.float32:
+                    out_dtype = v.dtype
+                    inputs[k] = v.to(torch.float32)
         inputs = self.initialize_derivatives(inputs)
         for m in self.input_modules:
             inputs = m(inputs)
@@ -84,7 +94,10 @@ class NeuralNetworkPotential(AtomisticModel):
         for m in self.output_modules:
             inputs = m(inputs)
         inputs = self.postprocess(inputs)
-        return self.extract_outputs(inputs)
+        out = self.extract_outputs(inputs)
+        if out_dtype is not None:
+            out = {k: (v.to(out_dtype) if v.is_floating_point() else v) for k, v in out.items()}
+        return out
 
 
 # --------------------------------------------------------------------------------------------------------- conversion
@@ -156,6 +169,11 @@ def convert_model(model: nn.Module) -> NeuralNetworkPotential:
     new = NeuralNetworkPotential(_convert_representation(model.representation), in_mods, out_mods,
                                  list(model.postprocessors), getattr(model, "input_dtype_str", "float32"),
                                  getattr(model, "do_postprocessing", True))
+    was_double = any(p.dtype == torch.float64 for p in model.parameters())
+    new.float()                  # the kernels compute in fp32 (weights copied through state_dict are cast on load)
+    if was_double:
+        new.cast_inputs = True
+        new.input_dtype_str = "float32"
     new.eval()
     return new
 

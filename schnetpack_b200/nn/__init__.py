@@ -21,6 +21,16 @@ __all__ = ["GaussianRBF", "BesselRBF", "CosineCutoff", "cosine_cutoff", "gaussia
            "scatter_add", "build_mlp", "replicate_module", "activation_code"]
 
 
+def refuse_training(module: nn.Module):
+    """The CUDA path provides first-order input gradients (forces, stress); weight gradients and double backward
+    (``create_graph`` force training) are not implemented.  Instead of returning wrong or missing
+    gradients silently, a module in training mode with trainable parameters under grad mode raises."""
+    if module.training and torch.is_grad_enabled() and any(p.requires_grad for p in module.parameters()):
+        raise NotImplementedError(
+            f"schnetpack_b200.{type(module).__name__}: weight gradients / double backward (training) are not implemented "
+            "in the CUDA path (SURVEY.md section 8 f3); call model.eval() for inference, forces and MD")
+
+
 # ------------------------------------------------------------------------------------------------- activations
 class _ActFn(torch.autograd.Function):
     @staticmethod
@@ -161,13 +171,14 @@ class _DenseFn(torch.autograd.Function):
     def forward(ctx, x, weight, bias, code):
         shp = x.shape
         x2 = x.detach().reshape(-1, shp[-1]).contiguous()
-        lin = ops.Lin(weight, bias)
         need = x.requires_grad
         ctx.pre = None
-        if need:
-            y, ctx.pre = lin.fwd(x2, code, save_deriv=True)
-        else:
-            y = lin.fwd(x2, code)
+        with ops.device_of(x2, weight):
+            lin = ops.Lin(weight, bias)
+            if need:
+                y, ctx.pre = lin.fwd(x2, code, save_deriv=True)
+            else:
+                y = lin.fwd(x2, code)
         ctx.lin = lin
         ctx.code = code
         ctx.shp = shp
@@ -177,7 +188,8 @@ class _DenseFn(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, g):
         g2 = g.reshape(-1, g.shape[-1]).contiguous()
-        gx = ctx.lin.bwd(g2, a_pre=ctx.pre if ctx.code != ops.ACT_NONE else None, a_act=ops.ACT_GIVEN)
+        with ops.device_of(g2):
+            gx = ctx.lin.bwd(g2, a_pre=ctx.pre if ctx.code != ops.ACT_NONE else None, a_act=ops.ACT_GIVEN)
         return gx.view(*ctx.shp), None, None, None
 
 
@@ -200,8 +212,7 @@ class Dense(nn.Linear):
             self.bias_init(self.bias)
 
     def forward(self, input: torch.Tensor):
-        if self.training and (self.weight.requires_grad and torch.is_grad_enabled()):
-            raise NotImplementedError("schnetpack_b200: weight gradients (training) are not implemented; call .eval()")
+        refuse_training(self)
         return _DenseFn.apply(input, self.weight, self.bias, activation_code(self.activation))
 
 

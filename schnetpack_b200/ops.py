@@ -23,7 +23,25 @@ def _p(t: Optional[Tensor]):
 
 
 def _stream():
+    """Current stream of the CURRENT device; ``device_of`` makes the tensors' device current around every pipeline."""
     return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def device_of(*tensors):
+    """Context manager that makes the (single) CUDA device of ``tensors`` current, so that the stream handed to the C ABI,
+    the library's per-device launch caches and the memory all belong to the same GPU even when the caller never called
+    ``torch.cuda.set_device`` (e.g. ``model.to('cuda:1')``).  Mixed devices raise."""
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError(f"schnetpack_b200: CUDA tensors only (no CPU fallback); got {t.device}")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"schnetpack_b200: tensors on different devices ({dev} and {t.device})")
+    return torch.cuda.device(dev)
 
 
 def _chk(t: Tensor, dtype, name: str):
@@ -49,6 +67,9 @@ def kp(n_rbf: int) -> int:
 
 
 # ------------------------------------------------------------------------------------------------------------ graph
+VALIDATE_INDICES = os.environ.get("SPK_B200_VALIDATE", "1") != "0"   # host check of a NEW neighbour list (one sync per list)
+
+
 class EdgeGraph:
     """Receiver-grouped (CSR) and sender-grouped views of an (idx_i, idx_j) edge list, built on device."""
 
@@ -79,6 +100,13 @@ class EdgeGraph:
         self._ref_i = weakref.ref(idx_i)
         self._ref_j = weakref.ref(idx_j)
         self._ver = (idx_i._version, idx_j._version)
+        if VALIDATE_INDICES and E > 0 and not torch.cuda.is_current_stream_capturing():
+            # the reference raises IndexError from index_select on a bad neighbour index; here the check costs one host
+            # read per NEW neighbour list (cached graphs and captured evaluations skip it; the kernels are safe either way:
+            # a bad list is evaluated as an empty graph with NaN distances)
+            n_bad = int(self.status[1])
+            if n_bad:
+                raise IndexError(f"{n_bad} neighbour indices out of range [0, {self.n_atoms})")
 
     def matches(self, idx_i: Tensor, idx_j: Tensor, n_atoms: int) -> bool:
         return (self._ref_i() is idx_i and self._ref_j() is idx_j and self.n_atoms == n_atoms
@@ -122,7 +150,7 @@ def pairwise_fwd(R: Tensor, idx_i: Tensor, idx_j: Tensor, offsets: Optional[Tens
     E = idx_i.shape[0]
     out = torch.empty((E, 3), dtype=torch.float32, device=R.device)
     _lib.call("spk_pairwise_fwd", _p(R), _p(i64(idx_i)), _p(i64(idx_j)),
-              _p(f32(offsets, "_offsets")) if offsets is not None else None, E, _p(out), _stream())
+              _p(f32(offsets, "_offsets")) if offsets is not None else None, R.shape[0], E, _p(out), _stream())
     return out
 
 
@@ -134,12 +162,8 @@ def pairwise_bwd(g_rij: Tensor, graph: EdgeGraph, sign: float = 1.0) -> Tensor:
     return out
 
 
-def nrb(n_rbf: int) -> int:
-    return 20 if n_rbf <= 20 else 32
-
-
 def edge_geometry(r_ij: Tensor, graph: Optional[EdgeGraph], rbf_kind: int, n_rbf: int, p0: Tensor, p1: Optional[Tensor],
-                  cutoff: float, need_grad: bool = True, want_rec: bool = False):
+                  cutoff: float, need_grad: bool = True):
     f32(r_ij, "_Rij")
     E = r_ij.shape[0]
     KP = kp(n_rbf)
@@ -147,12 +171,9 @@ def edge_geometry(r_ij: Tensor, graph: Optional[EdgeGraph], rbf_kind: int, n_rbf
     phi = torch.empty((E, KP), dtype=torch.float32, device=dev)
     dphi = torch.empty((E, KP), dtype=torch.float32, device=dev) if need_grad else None
     geo = torch.empty((E, GEO_STRIDE), dtype=torch.float32, device=dev)
-    erec = torch.empty((E, 2 * nrb(n_rbf) + GEO_STRIDE), dtype=torch.float32, device=dev) if want_rec else None
     _lib.call("spk_edge_geometry", _p(r_ij), _p(graph.slot_eid) if graph is not None else None, E, rbf_kind, n_rbf,
               _p(f32(p0)), _p(f32(p1)) if p1 is not None else None, float(cutoff), _p(phi), _p(dphi), _p(geo),
-              _p(erec), _stream())
-    if want_rec:
-        return phi, dphi, geo, erec
+              _stream())
     return phi, dphi, geo
 
 
@@ -323,32 +344,14 @@ class Lin:
         return dense(G, self.w, None, ACT_NONE, **kw)
 
 
-def dense_strided(A: Tensor, k: int, B: Tensor, **kw):
-    return dense(A, B, k=k, **kw)
-
-
-def dense_into(A: Tensor, B: Tensor, out: Tensor, ldy: int, **kw):
-    assert out.shape[1] == ldy
-    return dense(A, B, out=out, **kw)
-
-
 # ------------------------------------------------------------------------------------------------------------ PaiNN
-# edge-kernel variant (r1 measurements on cfg2, fwd/bwd us per launch: tc 47/76, ldg 58/108, async 65/112, tma 71/145,
-# sys 80/170):
-#   "tc" (default)  persistent kernels with the continuous filter on the tensor cores (csrc/painn_tc.cu: tcgen05 3xTF32,
-#                   channels on TMEM lanes); F == 128, n_rbf <= 31 and >= EDGE_TC_MIN_EDGES edges, otherwise "ldg";
-#   "ldg"           streaming kernels, filter in packed FFMA2, plain register gathers (csrc/painn.cu);
-#   "async"         the same with a per-thread cp.async gather ring;
-#   "tma"           streaming kernels with a TMA bulk-copy + mbarrier producer/consumer ring (csrc/painn_tma.cu);
-#   "sys"           system-resident kernels for batches of small systems when the caller supplies mol_ptr
-#                   (csrc/painn_sys.cu).  The C library reads SPK_B200_EDGE itself for the ldg / async / tma choice.
+# edge kernels: "tc" (default) = persistent kernels with the continuous filter on the tensor cores (csrc/painn_tc.cu:
+# tcgen05 3xTF32, channels on TMEM lanes) for F == 128, n_rbf <= 31 and >= EDGE_TC_MIN_EDGES edges; everything else, and
+# SPK_B200_EDGE=ldg, runs the streaming kernels with the filter in packed FFMA2 (csrc/painn.cu).  The round-1 TMA-ring,
+# cp.async-ring and system-resident variants measured slower and live on as
+# tools/experiments/edge_variants_r1.patch.
 EDGE_IMPL = os.environ.get("SPK_B200_EDGE", "tc")
-SYS_MAX_AVG_ATOMS = 48
 EDGE_TC_MIN_EDGES = 4096
-
-
-def _use_sys(n_atoms: int, mol_ptr, n_mol: int) -> bool:
-    return (EDGE_IMPL == "sys" and mol_ptr is not None and n_mol > 0 and n_atoms / n_mol <= SYS_MAX_AVG_ATOMS)
 
 
 def edge_tc_ok(F: int, n_rbf: int, n_edges: int) -> bool:
@@ -363,17 +366,13 @@ def painn_pack_filter(wf: Tensor, bf: Tensor, F: int, n_rbf: int) -> Tensor:
     return out
 
 
-def painn_edge_fwd(x, mu, q, phi, geo, graph: EdgeGraph, wf, bf, F: int, n_rbf: int, mol_ptr=None, n_mol: int = 0,
-                   wf_packed=None):
+def painn_edge_fwd(x, mu, q, phi, geo, graph: EdgeGraph, wf, bf, F: int, n_rbf: int, wf_packed=None):
     N = graph.n_atoms
     q_out = torch.empty((N, F), dtype=torch.float32, device=x.device)
     mu_out = torch.empty((N, 3, F), dtype=torch.float32, device=x.device)
     if wf_packed is not None and edge_tc_ok(F, n_rbf, graph.n_edges):
         _lib.call("spk_painn_edge_fwd_tc", _p(x), _p(mu), _p(q), _p(phi), _p(geo), _p(graph.rowptr), _p(graph.slot_j),
                   _p(wf_packed), N, graph.n_edges, F, n_rbf, _p(q_out), _p(mu_out), _stream())
-    elif _use_sys(N, mol_ptr, n_mol):
-        _lib.call("spk_painn_edge_fwd_sys", _p(x), _p(mu), _p(q), _p(phi), _p(geo), _p(graph.rowptr), _p(graph.slot_j),
-                  _p(wf), _p(bf), _p(mol_ptr), n_mol, N, graph.n_edges, F, n_rbf, _p(q_out), _p(mu_out), _stream())
     else:
         _lib.call("spk_painn_edge_fwd", _p(x), _p(mu), _p(q), _p(phi), _p(geo), _p(graph.rowptr), _p(graph.slot_j),
                   _p(wf), _p(bf), N, graph.n_edges, F, n_rbf, _p(q_out), _p(mu_out), _stream())
@@ -381,7 +380,7 @@ def painn_edge_fwd(x, mu, q, phi, geo, graph: EdgeGraph, wf, bf, F: int, n_rbf: 
 
 
 def painn_edge_bwd(x, mu, g_q, g_mu, phi, dphi, geo, graph: EdgeGraph, wf, bf, F: int, n_rbf: int, g_rij: Tensor,
-                   accumulate: bool, erec: Optional[Tensor] = None, mol_ptr=None, n_mol: int = 0, wf_packed=None):
+                   accumulate: bool, wf_packed=None):
     N = graph.n_atoms
     g_x = torch.empty((N, 3 * F), dtype=torch.float32, device=x.device)
     g_mu_in = torch.empty((N, 3, F), dtype=torch.float32, device=x.device) if mu is not None else None
@@ -389,15 +388,33 @@ def painn_edge_bwd(x, mu, g_q, g_mu, phi, dphi, geo, graph: EdgeGraph, wf, bf, F
         _lib.call("spk_painn_edge_bwd_tc", _p(x), _p(mu), _p(g_q), _p(g_mu), _p(phi), _p(dphi), _p(geo), _p(graph.sptr),
                   _p(graph.pos_slot), _p(graph.pos_i), _p(graph.slot_eid), _p(wf_packed), N, graph.n_edges, F, n_rbf,
                   _p(g_x), _p(g_mu_in), _p(g_rij), 1 if accumulate else 0, _stream())
-    elif _use_sys(N, mol_ptr, n_mol):
-        _lib.call("spk_painn_edge_bwd_sys", _p(x), _p(mu), _p(g_q), _p(g_mu), _p(phi), _p(dphi), _p(geo),
-                  _p(graph.sptr), _p(graph.pos_slot), _p(graph.pos_i), _p(graph.slot_eid), _p(wf), _p(bf), _p(mol_ptr),
-                  n_mol, N, graph.n_edges, F, n_rbf, _p(g_x), _p(g_mu_in), _p(g_rij), 1 if accumulate else 0, _stream())
     else:
-        _lib.call("spk_painn_edge_bwd", _p(x), _p(mu), _p(g_q), _p(g_mu), _p(phi), _p(dphi), _p(geo), _p(erec),
-                  _p(graph.sptr), _p(graph.pos_slot), _p(graph.pos_i), _p(graph.slot_eid), _p(wf), _p(bf), N,
+        _lib.call("spk_painn_edge_bwd", _p(x), _p(mu), _p(g_q), _p(g_mu), _p(phi), _p(dphi), _p(geo), _p(graph.sptr), _p(graph.pos_slot), _p(graph.pos_i), _p(graph.slot_eid), _p(wf), _p(bf), N,
                   graph.n_edges, F, n_rbf, _p(g_x), _p(g_mu_in), _p(g_rij), 1 if accumulate else 0, _stream())
     return g_x, g_mu_in
+
+
+def painn_edge_wij_fwd(x, mu, q, Wij, dir_ij, graph: EdgeGraph, F: int):
+    """Block-level interaction with a materialised filter Wij [E,3F] / dir_ij [E,3] in the caller's edge order."""
+    N = graph.n_atoms
+    q_out = torch.empty((N, F), dtype=torch.float32, device=x.device)
+    mu_out = torch.empty((N, 3, F), dtype=torch.float32, device=x.device)
+    _lib.call("spk_painn_edge_wij_fwd", _p(f32(x)), _p(f32(mu)), _p(f32(q)), _p(f32(Wij, "Wij")), _p(f32(dir_ij, "dir_ij")),
+              _p(graph.rowptr), _p(graph.slot_j), _p(graph.slot_eid), N, graph.n_edges, F, _p(q_out), _p(mu_out), _stream())
+    return q_out, mu_out
+
+
+def painn_edge_wij_bwd(x, mu, g_q, g_mu, Wij, dir_ij, graph: EdgeGraph, F: int):
+    N, E = graph.n_atoms, graph.n_edges
+    dev = x.device
+    g_x = torch.empty((N, 3 * F), dtype=torch.float32, device=dev)
+    g_mu_in = torch.empty((N, 3, F), dtype=torch.float32, device=dev)
+    g_W = torch.empty((E, 3 * F), dtype=torch.float32, device=dev)
+    g_dir = torch.empty((E, 3), dtype=torch.float32, device=dev)
+    _lib.call("spk_painn_edge_wij_bwd", _p(f32(x)), _p(f32(mu)), _p(f32(g_q)), _p(f32(g_mu)), _p(f32(Wij)), _p(f32(dir_ij)),
+              _p(graph.sptr), _p(graph.pos_slot), _p(graph.pos_i), _p(graph.slot_eid), N, E, F, _p(g_x), _p(g_mu_in),
+              _p(g_W), _p(g_dir), _stream())
+    return g_x, g_mu_in, g_W, g_dir
 
 
 def painn_mix_ctx(q, VW, F: int, eps: float):

@@ -21,8 +21,9 @@ __all__ = ["PaiNN", "PaiNNInteraction", "PaiNNMixing"]
 
 
 class PaiNNInteraction(nn.Module):
-    """Parameter container of one interaction block (painn.py:14-67): interatomic_context_net = Dense(F,F,act) ->
-    Dense(F,3F).  The block is executed by the fused edge kernel inside ``PaiNN.forward``."""
+    """One interaction block (painn.py:14-67): interatomic_context_net = Dense(F,F,act) -> Dense(F,3F).  Inside
+    ``PaiNN.forward`` the block runs in the fused edge kernel (filter evaluated in-kernel); called directly with a
+    materialised filter, as the reference's block API allows, it runs on ``spk_painn_edge_wij_{fwd,bwd}``."""
 
     def __init__(self, n_atom_basis: int, activation: Callable):
         super().__init__()
@@ -33,13 +34,18 @@ class PaiNNInteraction(nn.Module):
         )
 
     def forward(self, q, mu, Wij, dir_ij, idx_i, idx_j, n_atoms: int):
-        raise NotImplementedError(
-            "PaiNNInteraction is executed inside PaiNN.forward by the fused edge kernel (spk_painn_edge_fwd); "
-            "the materialised-filter block-level call of the reference is not provided")
+        """painn.py:31-67.  q [N,1,F], mu [N,3,F], Wij [E,1,3F], dir_ij [E,3] -> (q, mu); differentiable w.r.t. q, mu, Wij
+        and dir_ij (first order)."""
+        F_ = self.n_atom_basis
+        x = self.interatomic_context_net(q)                                        # :54 (Dense kernels)
+        graph = ops.get_graph(idx_i, idx_j, int(n_atoms))
+        q1, mu1 = K.PaiNNEdgeWijFunction.apply(x.reshape(-1, 3 * F_), mu, q.reshape(-1, F_), Wij.reshape(-1, 3 * F_),
+                                               dir_ij, graph, F_)                 # :55-65
+        return q1.view(q.shape), mu1
 
 
 class PaiNNMixing(nn.Module):
-    """Parameter container of one mixing block (painn.py:70-117)."""
+    """One mixing block (painn.py:70-117); callable on its own like the reference's."""
 
     def __init__(self, n_atom_basis: int, activation: Callable, epsilon: float = 1e-8):
         super().__init__()
@@ -50,9 +56,30 @@ class PaiNNMixing(nn.Module):
         )
         self.mu_channel_mix = snn.Dense(n_atom_basis, 2 * n_atom_basis, activation=None, bias=False)
         self.epsilon = epsilon
+        self.activation = activation
+        self._blk, self._sig = None, None
+
+    def _apply(self, fn, *a, **k):
+        self._blk, self._sig = None, None
+        return super()._apply(fn, *a, **k)
+
+    def _pack(self):
+        params = list(self.parameters())
+        sig = K.ParamPack.signature(params)
+        if self._sig != sig:
+            m0, m1 = self.intraatomic_context_net[0], self.intraatomic_context_net[1]
+            self._blk = dict(mix=ops.Lin(self.mu_channel_mix.weight), m0=ops.Lin(m0.weight, m0.bias),
+                             m1=ops.Lin(m1.weight, m1.bias))
+            self._sig = sig
+        return self._blk
 
     def forward(self, q, mu):
-        raise NotImplementedError("PaiNNMixing is executed inside PaiNN.forward")
+        """painn.py:92-117.  q [N,1,F], mu [N,3,F] -> (q, mu)."""
+        snn.refuse_training(self)
+        F_ = self.n_atom_basis
+        q2, mu2 = K.PaiNNMixingFunction.apply(q.reshape(-1, F_), mu, self._pack(), F_, float(self.epsilon),
+                                              snn.activation_code(self.activation))
+        return q2.view(q.shape), mu2
 
 
 class PaiNN(nn.Module):
@@ -133,10 +160,7 @@ class PaiNN(nn.Module):
         idx_i = inputs[properties.idx_i]
         idx_j = inputs[properties.idx_j]
         n_atoms = atomic_numbers.shape[0]
-        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError(
-                "schnetpack_b200.PaiNN: weight gradients / double backward (training) are not implemented in the "
-                "CUDA path (SURVEY.md §8 f3); call model.eval() for inference, forces and MD")
+        snn.refuse_training(self)
         if not isinstance(self.radial_basis, (snn.GaussianRBF, snn.BesselRBF)) or not isinstance(
                 self.cutoff_fn, snn.CosineCutoff):
             raise NotImplementedError("fused PaiNN kernels support GaussianRBF/BesselRBF x CosineCutoff")
@@ -150,13 +174,7 @@ class PaiNN(nn.Module):
                 q0 = q0 + embedding(q0, inputs)
             q0 = q0.detach().contiguous()
 
-        # system boundaries (if the batch carries them) let the edge kernels keep a small system's rows in shared memory
         holder = dict(module=self, graph=graph)
-        if properties.idx_m in inputs and properties.n_atoms in inputs:
-            n_mol = int(inputs[properties.n_atoms].shape[0])
-            if n_mol > 0 and n_atoms / n_mol <= ops.SYS_MAX_AVG_ATOMS and ops.EDGE_IMPL == "sys":
-                holder["mol_ptr"] = ops.segment_ptr(inputs[properties.idx_m], n_mol)
-                holder["n_mol"] = n_mol
         q, mu = K.PaiNNFunction.apply(r_ij if r_ij.is_contiguous() else r_ij.contiguous(), q0, holder)
         inputs["scalar_representation"] = q
         inputs["vector_representation"] = mu

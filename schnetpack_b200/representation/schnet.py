@@ -17,8 +17,9 @@ __all__ = ["SchNet", "SchNetInteraction"]
 
 
 class SchNetInteraction(nn.Module):
-    """Parameter container of one interaction block (schnet.py:14-70): in2f (no bias), f2out = Dense(act) -> Dense,
-    filter_network = Dense(n_rbf -> n_filters, act) -> Dense(n_filters -> n_filters)."""
+    """One interaction block (schnet.py:14-70): in2f (no bias), f2out = Dense(act) -> Dense, filter_network =
+    Dense(n_rbf -> n_filters, act) -> Dense(n_filters -> n_filters).  ``SchNet.forward`` runs the block inside its own
+    kernel pipeline; called directly (the reference's block API) it runs Dense kernels + ``spk_cfconv_{fwd,bwd}``."""
 
     def __init__(self, n_atom_basis: int, n_rbf: int, n_filters: int, activation: Callable = shifted_softplus):
         super().__init__()
@@ -32,7 +33,12 @@ class SchNetInteraction(nn.Module):
         )
 
     def forward(self, x, f_ij, idx_i, idx_j, rcut_ij):
-        raise NotImplementedError("SchNetInteraction is executed inside SchNet.forward by the cfconv kernels")
+        """schnet.py:41-70.  x [N,F], f_ij [E,n_rbf], rcut_ij [E] -> v [N,F]; differentiable w.r.t. x, f_ij, rcut_ij."""
+        h = self.in2f(x)                                                           # :60
+        Wij = self.filter_network(f_ij)                                            # :61
+        graph = ops.get_graph(idx_i, idx_j, int(x.shape[0]))
+        m = K.CFConvFunction.apply(h, Wij, rcut_ij, graph)                         # :62-67
+        return self.f2out(m)                                                       # :69
 
 
 class SchNet(nn.Module):
@@ -104,10 +110,7 @@ class SchNet(nn.Module):
         idx_i = inputs[properties.idx_i]
         idx_j = inputs[properties.idx_j]
         n_atoms = atomic_numbers.shape[0]
-        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError(
-                "schnetpack_b200.SchNet: weight gradients / double backward (training) are not implemented in the "
-                "CUDA path (SURVEY.md §8 f3); call model.eval()")
+        snn.refuse_training(self)
         if not isinstance(self.radial_basis, (snn.GaussianRBF, snn.BesselRBF)) or not isinstance(
                 self.cutoff_fn, snn.CosineCutoff):
             raise NotImplementedError("fused SchNet kernels support GaussianRBF/BesselRBF x CosineCutoff")

@@ -21,42 +21,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
-import _ref_loader as rl  # noqa: E402
+from oracle import ref_loader as rl  # noqa: E402
 from schnetpack_b200 import synthetic as S  # noqa: E402
 
 
 def build_reference_model(spk, spec, params, dtype):
-    nn_ = spk.nn
-    if spec["rbf"] == "gaussian":
-        rbf = nn_.GaussianRBF(n_rbf=spec["n_rbf"], cutoff=spec["cutoff"])
-    else:
-        rbf = nn_.BesselRBF(n_rbf=spec["n_rbf"], cutoff=spec["cutoff"])
-    cut = nn_.CosineCutoff(spec["cutoff"])
-    if spec["kind"] == "painn":
-        rep = spk.representation.PaiNN(spec["n_atom_basis"], spec["n_interactions"], rbf, cut,
-                                       shared_interactions=spec["shared_interactions"],
-                                       shared_filters=spec["shared_filters"], epsilon=spec["epsilon"])
-    else:
-        rep = spk.representation.SchNet(spec["n_atom_basis"], spec["n_interactions"], rbf, cut,
-                                        n_filters=spec["n_filters"], shared_interactions=spec["shared_interactions"])
-    outs = [spk.atomistic.Atomwise(n_in=spec["n_atom_basis"], output_key="energy")]
-    if spec["forces"]:
-        outs.append(spk.atomistic.Forces(energy_key="energy", force_key="forces"))
-    model = spk.model.NeuralNetworkPotential(rep, input_modules=[spk.atomistic.PairwiseDistances()],
-                                             output_modules=outs, postprocessors=[], do_postprocessing=False)
-    sd = model.state_dict()
-    new = {}
-    for k in sd:
-        # shared_interactions replicates the same module under every index
-        kk = k
-        if k not in params and spec["shared_interactions"]:
-            import re
-            kk = re.sub(r"\.(interactions|mixing)\.\d+\.", r".\1.0.", k)
-        new[k] = torch.as_tensor(params[kk]).to(sd[k].dtype)
-    model.load_state_dict(new)
-    model = model.to(dtype)
-    model.eval()
-    return model
+    return rl.build_from_spec(spec, params, dtype)
 
 
 def run_reference(spk, model, inputs, dtype, spec):

@@ -12,7 +12,7 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
-import _ref_loader  # noqa: E402
+from oracle import ref_loader as _ref_loader  # noqa: E402
 
 from oracle import nl_oracle as NL  # noqa: E402
 

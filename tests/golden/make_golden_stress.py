@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
-import _ref_loader as rl  # noqa: E402
+from oracle import ref_loader as rl  # noqa: E402
 from make_golden import build_reference_model  # noqa: E402
 from schnetpack_b200 import synthetic as S  # noqa: E402
 

@@ -230,10 +230,7 @@ def test_painn_edge_fwd_bwd(F, n_rbf, has_mu):
     q = torch.randn(N, F, device=DEV)
     wf = torch.randn(3 * F, n_rbf, device=DEV) * 0.3
     bf = torch.randn(3 * F, device=DEV) * 0.3
-    phi, dphi, geo, erec = ops.edge_geometry(r, g, ops.RBF_GAUSSIAN, n_rbf, p0, p1, rc, True, want_rec=True)
-    NRB = ops.nrb(n_rbf)
-    assert torch.equal(erec[:, :n_rbf], phi[:, :n_rbf]) and torch.equal(erec[:, NRB:NRB + n_rbf], dphi[:, :n_rbf])
-    assert torch.equal(erec[:, 2 * NRB:], geo) and float(erec[:, n_rbf:NRB].abs().max() if n_rbf < NRB else 0.0) == 0.0
+    phi, dphi, geo = ops.edge_geometry(r, g, ops.RBF_GAUSSIAN, n_rbf, p0, p1, rc, True)
     qo, muo = ops.painn_edge_fwd(x, mu, q, phi, geo, g, wf, bf, F, n_rbf)
     # fp64 reference + autograd
     x64, q64, r64 = x.double().requires_grad_(), q.double(), r.double().requires_grad_()
@@ -244,12 +241,7 @@ def test_painn_edge_fwd_bwd(F, n_rbf, has_mu):
     g_mu = torch.randn(N, 3, F, device=DEV)
     gx_r, gmu_r, gr_r = torch.autograd.grad((qr * g_q.double()).sum() + (mur * g_mu.double()).sum(), [x64, mu64, r64])
     g_rij = torch.full((r.shape[0], 3), 7.0, device=DEV)
-    g_x, g_mu_in = ops.painn_edge_bwd(x, mu, g_q, g_mu, phi, dphi, geo, g, wf, bf, F, n_rbf, g_rij, accumulate=False,
-                                      erec=erec)
-    # the LDG variant (no combined record) must agree with the TMA variant
-    g_rij_b = torch.zeros_like(g_rij)
-    g_x_b, g_mu_b = ops.painn_edge_bwd(x, mu, g_q, g_mu, phi, dphi, geo, g, wf, bf, F, n_rbf, g_rij_b, accumulate=False)
-    assert rel(g_x_b, g_x) < 2e-6 and rel(g_rij_b, g_rij) < 5e-6
+    g_x, g_mu_in = ops.painn_edge_bwd(x, mu, g_q, g_mu, phi, dphi, geo, g, wf, bf, F, n_rbf, g_rij, accumulate=False)
     if has_mu:
         assert rel(g_x, gx_r) < 5e-6
         assert rel(g_mu_in, gmu_r) < 5e-6
@@ -257,7 +249,7 @@ def test_painn_edge_fwd_bwd(F, n_rbf, has_mu):
         assert rel(g_x[:, : 2 * F], gx_r[:, : 2 * F]) < 5e-6 and float(g_x[:, 2 * F:].abs().max()) == 0.0
     assert rel(g_rij, gr_r) < 1e-5
     # accumulate=True adds on top
-    g_x2, _ = ops.painn_edge_bwd(x, mu, g_q, g_mu, phi, dphi, geo, g, wf, bf, F, n_rbf, g_rij, accumulate=True, erec=erec)
+    g_x2, _ = ops.painn_edge_bwd(x, mu, g_q, g_mu, phi, dphi, geo, g, wf, bf, F, n_rbf, g_rij, accumulate=True)
     assert rel(g_rij, 2 * gr_r) < 1e-5
 
 
@@ -359,57 +351,6 @@ def test_atomwise_and_pairwise():
     assert rel(gR, ref) < 2e-6
 
 
-@pytest.mark.parametrize("gen", ["aspirin", "qm9like"])
-def test_painn_edge_system_resident_matches_streaming(gen):
-    """System-resident edge kernels (rows of a small system staged in shared memory) == streaming kernels; the qm9like
-    batch has systems above the shared-memory capacity chosen at launch, which exercises the in-kernel global fallback."""
-    from schnetpack_b200 import ops
-    from schnetpack_b200 import synthetic as S
-
-    monkey_impl = ops.EDGE_IMPL
-    ops.EDGE_IMPL = "sys"          # opt in to the system-resident dispatch for this comparison
-    try:
-        _sys_vs_streaming(gen)
-    finally:
-        ops.EDGE_IMPL = monkey_impl
-
-
-def _sys_vs_streaming(gen):
-    from schnetpack_b200 import ops
-    from schnetpack_b200 import synthetic as S
-
-    b = S.aspirin_batch(7, seed=11) if gen == "aspirin" else S.qm9like_batch(40, seed=12)
-    ti, tj = torch.as_tensor(b["_idx_i"], device=DEV), torch.as_tensor(b["_idx_j"], device=DEV)
-    N, B = b["_atomic_numbers"].shape[0], b["_n_atoms"].shape[0]
-    g = ops.EdgeGraph(ti, tj, N)
-    mol_ptr = ops.segment_ptr(torch.as_tensor(b["_idx_m"], device=DEV), B)
-    assert mol_ptr.tolist() == np.concatenate([[0], np.cumsum(b["_n_atoms"])]).tolist()
-    torch.manual_seed(13)
-    F, n_rbf, rc = 128, 20, 5.0
-    R = torch.as_tensor(b["_positions"], device=DEV)
-    r = (R[tj] - R[ti]).contiguous()
-    p0 = torch.linspace(0, rc, n_rbf, device=DEV)
-    p1 = torch.full((n_rbf,), float(p0[1] - p0[0]), device=DEV)
-    phi, dphi, geo, erec = ops.edge_geometry(r, g, ops.RBF_GAUSSIAN, n_rbf, p0, p1, rc, True, want_rec=True)
-    x = torch.randn(N, 3 * F, device=DEV)
-    q = torch.randn(N, F, device=DEV)
-    wf = torch.randn(3 * F, n_rbf, device=DEV) * 0.3
-    bf = torch.randn(3 * F, device=DEV) * 0.3
-    g_q = torch.randn(N, F, device=DEV)
-    g_mu = torch.randn(N, 3, F, device=DEV)
-    for mu in (torch.randn(N, 3, F, device=DEV), None):
-        qa, ma = ops.painn_edge_fwd(x, mu, q, phi, geo, g, wf, bf, F, n_rbf)          # streaming (no mol_ptr)
-        qb, mb = ops.painn_edge_fwd(x, mu, q, phi, geo, g, wf, bf, F, n_rbf, mol_ptr=mol_ptr, n_mol=B)
-        assert rel(qb, qa) < 1e-6 and rel(mb, ma) < 1e-6
-        ra, rb = torch.zeros(r.shape[0], 3, device=DEV), torch.zeros(r.shape[0], 3, device=DEV)
-        gxa, gma = ops.painn_edge_bwd(x, mu, g_q, g_mu, phi, dphi, geo, g, wf, bf, F, n_rbf, ra, False, erec=erec)
-        gxb, gmb = ops.painn_edge_bwd(x, mu, g_q, g_mu, phi, dphi, geo, g, wf, bf, F, n_rbf, rb, False, erec=erec,
-                                      mol_ptr=mol_ptr, n_mol=B)
-        assert rel(gxb, gxa) < 2e-6 and rel(rb, ra) < 5e-6
-        if mu is not None:
-            assert rel(gmb, gma) < 2e-6
-
-
 @pytest.mark.parametrize("impl", ["tc", "ffma"])
 def test_lin_saved_derivative_backward(impl):
     """Lin.fwd(save_deriv=True) stores act'(pre) (SPK_SAVE_DERIV); Lin.bwd(a_act=ACT_GIVEN) multiplies by it: together they
@@ -500,3 +441,111 @@ def test_painn_edge_tensor_core_filter_matches_streaming(gen, n_rbf):
                     assert rel(gm_tc, gm_ref.double()) < 2e-6, (gen, acc, rel(gm_tc, gm_ref.double()))
     finally:
         ops.EDGE_IMPL, ops.EDGE_TC_MIN_EDGES = saved
+
+
+@pytest.mark.parametrize("has_mu", [True, False])
+def test_painn_edge_tc_kernels_vs_fp64_restatement(has_mu):
+    """Tensor-core edge kernels (forward and reverse) held DIRECTLY against a torch fp64 restatement of painn.py:55-65 +
+    :232-236 with autograd (not only against the streaming kernels), on a graph large enough for every persistent CTA to
+    own several chunks (aspirin x 40: 12 k edges) and on a periodic box."""
+    from schnetpack_b200 import ops
+    from schnetpack_b200 import synthetic as S
+
+    saved = ops.EDGE_IMPL, ops.EDGE_TC_MIN_EDGES
+    ops.EDGE_IMPL, ops.EDGE_TC_MIN_EDGES = "tc", 1
+    try:
+        for b in (S.aspirin_batch(40, seed=5), S.periodic_box(700, seed=6)):
+            ti, tj = torch.as_tensor(b["_idx_i"], device=DEV), torch.as_tensor(b["_idx_j"], device=DEV)
+            N = b["_atomic_numbers"].shape[0]
+            g = ops.EdgeGraph(ti, tj, N)
+            torch.manual_seed(41)
+            F, n_rbf, rc = 128, 20, 5.0
+            R = torch.as_tensor(b["_positions"], device=DEV)
+            r = (R[tj] - R[ti] + torch.as_tensor(b["_offsets"], device=DEV)).contiguous()
+            p0 = torch.linspace(0, rc, n_rbf, device=DEV)
+            p1 = torch.full((n_rbf,), float(p0[1] - p0[0]), device=DEV)
+            x = torch.randn(N, 3 * F, device=DEV)
+            mu = torch.randn(N, 3, F, device=DEV) if has_mu else None
+            q = torch.randn(N, F, device=DEV)
+            wf = torch.randn(3 * F, n_rbf, device=DEV) * 0.3
+            bf = torch.randn(3 * F, device=DEV) * 0.3
+            wpk = ops.painn_pack_filter(wf, bf, F, n_rbf)
+            assert ops.edge_tc_ok(F, n_rbf, g.n_edges)
+            phi, dphi, geo = ops.edge_geometry(r, g, ops.RBF_GAUSSIAN, n_rbf, p0, p1, rc, True)
+            qo, muo = ops.painn_edge_fwd(x, mu, q, phi, geo, g, wf, bf, F, n_rbf, wf_packed=wpk)
+            x64, q64, r64 = x.double().requires_grad_(), q.double(), r.double().requires_grad_()
+            mu64 = (mu.double() if has_mu else torch.zeros(N, 3, F, device=DEV, dtype=torch.float64)).requires_grad_()
+            qr, mur = _painn_layer_ref(x64, mu64, q64, r64, ti, tj, wf.double(), bf.double(), rc, p0.double(), p1.double())
+            assert rel(qo, qr) < 3e-6 and rel(muo, mur) < 3e-6
+            g_q = torch.randn(N, F, device=DEV)
+            g_mu = torch.randn(N, 3, F, device=DEV)
+            gx_r, gmu_r, gr_r = torch.autograd.grad((qr * g_q.double()).sum() + (mur * g_mu.double()).sum(),
+                                                    [x64, mu64, r64])
+            g_rij = torch.zeros((r.shape[0], 3), device=DEV)
+            g_x, g_mu_in = ops.painn_edge_bwd(x, mu, g_q, g_mu, phi, dphi, geo, g, wf, bf, F, n_rbf, g_rij, False,
+                                              wf_packed=wpk)
+            if has_mu:
+                assert rel(g_x, gx_r) < 5e-6 and rel(g_mu_in, gmu_r + g_mu.double() * 0) < 5e-6
+            else:
+                assert rel(g_x[:, : 2 * F], gx_r[:, : 2 * F]) < 5e-6
+            assert rel(g_rij, gr_r) < 1e-5
+    finally:
+        ops.EDGE_IMPL, ops.EDGE_TC_MIN_EDGES = saved
+
+
+def test_painn_edge_wij_block_kernels():
+    """spk_painn_edge_wij_{fwd,bwd} (materialised filter, block-level API) vs a torch fp64 restatement of painn.py:55-65 with
+    autograd, on an UNSORTED edge list (Wij / dir_ij stay in the caller's order)."""
+    from schnetpack_b200 import ops
+    from schnetpack_b200 import synthetic as S
+
+    b = S.aspirin_batch(6, seed=8)
+    rng = np.random.default_rng(3)
+    perm = rng.permutation(b["_idx_i"].shape[0])
+    ti = torch.as_tensor(b["_idx_i"][perm], device=DEV)
+    tj = torch.as_tensor(b["_idx_j"][perm], device=DEV)
+    N, E, F = b["_atomic_numbers"].shape[0], perm.shape[0], 64
+    g = ops.EdgeGraph(ti, tj, N)
+    torch.manual_seed(5)
+    x, mu, q = torch.randn(N, 3 * F, device=DEV), torch.randn(N, 3, F, device=DEV), torch.randn(N, F, device=DEV)
+    W, u = torch.randn(E, 3 * F, device=DEV), torch.randn(E, 3, device=DEV)
+    qo, muo = ops.painn_edge_wij_fwd(x, mu, q, W, u, g, F)
+    x64, mu64, W64, u64 = (t.double().requires_grad_() for t in (x, mu, W, u))
+    y = W64 * x64[tj]
+    dq, dmuR, dmumu = y.split(F, dim=-1)
+    qr = q.double() + torch.zeros(N, F, device=DEV, dtype=torch.float64).index_add(0, ti, dq)
+    dmu = dmuR[:, None, :] * u64[:, :, None] + dmumu[:, None, :] * mu64[tj]
+    mur = mu64 + torch.zeros(N, 3, F, device=DEV, dtype=torch.float64).index_add(0, ti, dmu)
+    assert rel(qo, qr) < 2e-6 and rel(muo, mur) < 2e-6
+    g_q, g_mu = torch.randn(N, F, device=DEV), torch.randn(N, 3, F, device=DEV)
+    gx_r, gmu_r, gW_r, gu_r = torch.autograd.grad((qr * g_q.double()).sum() + (mur * g_mu.double()).sum(),
+                                                  [x64, mu64, W64, u64])
+    g_x, g_mu_in, g_W, g_u = ops.painn_edge_wij_bwd(x, mu, g_q, g_mu, W, u, g, F)
+    assert rel(g_x, gx_r) < 3e-6 and rel(g_mu_in, gmu_r) < 3e-6 and rel(g_W, gW_r) < 3e-6 and rel(g_u, gu_r) < 5e-6
+
+
+def test_bad_neighbor_indices_raise_and_never_gather_out_of_bounds():
+    """Reference: index_select raises IndexError on a bad index.  Here the first build of a new list raises on the host, and
+    the kernels -- which cannot raise -- treat the list as an EMPTY graph (row pointers zeroed) and poison the distances of
+    the bad edges with NaN instead of reading out of bounds."""
+    from schnetpack_b200 import ops
+
+    b, ti, tj, N = _graph_inputs(seed=1, batch=2)
+    bad_j = tj.clone()
+    bad_j[5] = N + 1000
+    with pytest.raises(IndexError):
+        ops.EdgeGraph(ti, bad_j, N)
+    old = ops.VALIDATE_INDICES
+    ops.VALIDATE_INDICES = False
+    try:
+        g = ops.EdgeGraph(ti, bad_j, N)
+        assert int(g.status[1]) == 1
+        assert int(g.rowptr.abs().max()) == 0 and int(g.sptr.abs().max()) == 0
+        R = torch.as_tensor(b["_positions"], device=DEV)
+        rij = ops.pairwise_fwd(R, ti, bad_j, None)
+        assert bool(torch.isnan(rij[5]).all()) and not bool(torch.isnan(rij[:5]).any())
+    finally:
+        ops.VALIDATE_INDICES = old
+    Z = torch.tensor([1, 6, 250, -1], device=DEV)
+    out = ops.embedding(torch.randn(100, 32, device=DEV), Z)
+    assert not bool(torch.isnan(out[:2]).any()) and bool(torch.isnan(out[2:]).all())
