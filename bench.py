@@ -4,6 +4,8 @@
     python bench.py --gpus 1 --steps 20 --warmup 5                  # CUDA path (this repo)
     python bench.py --impl reference --gpus 1 --steps 5 --warmup 1  # reference arm: CPU path on the host cores
     torchrun --nproc-per-node N ... bench.py --gpus N ...            # weak scaling: one batch per rank, no collective
+    torchrun --nproc-per-node N ... bench.py --gpus N --config cfg5  # STRONG scaling: one 262144-atom periodic box split
+                                                                     # into N slabs, NCCL halo exchange of ghost rows
 
 Workload (BASELINE.json configs[1]): MD17 aspirin x 256, PaiNN F=128 T=3 (20 Gaussian RBF, cosine cutoff 5 A),
 energy + forces.  One *step* = one full evaluation ``model(inputs)`` of the whole batch (256 molecule-evals).
@@ -112,30 +114,63 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------- reference (CPU) arm
-def oracle_eval_time(spec, params, data, steps, warmup, threads):
+def reference_engine(spec, params, data, device=None):
+    """(callable evaluating one full batch, kind).  The reference's OWN modules (oracle/ref_loader.py: /root/reference or the
+    vendored byte-identical copy oracle/_ref) when present -> kind "reference"; otherwise the restatement
+    oracle/spk_oracle.py (the same ATen op sequence) -> kind "port"."""
+    from oracle import ref_loader as rl
+
+    if rl.available():
+        model = rl.build_from_spec(spec, params, torch.float32, device)
+        x0 = {}
+        for k, v in data.items():
+            t = torch.as_tensor(v)
+            if t.is_floating_point():
+                t = t.float()
+            x0[k] = t.to(device) if device is not None else t
+        forces = bool(spec.get("forces", True))
+
+        def run():
+            x = {k: (v.detach().clone() if v.is_floating_point() else v) for k, v in x0.items()}   # fresh leaves per call
+            if "_Rij" in x:
+                x = model.representation(x)
+                return model.output_modules[0](x)
+            return model(x)
+
+        _ = forces
+        return run, "reference"
     from oracle import spk_oracle as O
 
+    if device is None:
+        return (lambda: O.energy_forces(spec, params, data, dtype=torch.float32)), "port"
+    p_dev = O.to_torch(params, torch.float32, device)
+    x_dev = O.to_torch(data, torch.float32, device)
+    return (lambda: O.energy_forces(spec, p_dev, x_dev, device=device)), "port"
+
+
+def cpu_eval_time(run, steps, warmup, threads):
     torch.set_num_threads(threads)
     ts = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
-        O.energy_forces(spec, params, data, dtype=torch.float32)
+        run()
         dt = time.perf_counter() - t0
         if it >= warmup:
             ts.append(dt)
     return ts
 
 
-def best_thread_count(spec, params, data):
-    """The reference's eager CPU path scales badly past a few dozen threads on these small ops (128 threads were 13x
-    slower than 8 on the round-1 box), so give it the thread count it is fastest with: probe 8/16/32/64/all once each
-    and keep the best.  Returns (threads, seconds_per_eval_at_that_count)."""
+def best_thread_count(run):
+    """BASELINE.md section 3 asks for torch.set_num_threads(os.cpu_count()); the reference's eager CPU path scales badly
+    past a few dozen threads on these small ops (128 threads were 13x slower than 8 on the round-1 box), so the arm is
+    given the thread count it is FASTEST with (favours the reference): probe 8/16/32/64/all once each, keep the best.
+    Returns (threads, seconds_per_eval_at_that_count)."""
     cores = os.cpu_count() or 1
     cands = sorted({c for c in (8, 16, 32, 64, cores) if c <= cores} or {cores})
     best = None
     first = True
     for c in cands:
-        t = min(oracle_eval_time(spec, params, data, 1, 1 if first else 0, c))
+        t = min(cpu_eval_time(run, 1, 1 if first else 0, c))
         first = False
         if best is None or t < best[1]:
             best = (c, t)
@@ -144,34 +179,104 @@ def best_thread_count(spec, params, data):
     return best
 
 
+def cpu_sample(args):
+    """The bounded CPU sample of a workload: (spec, data, scale, description).  cfg5's 262144-atom box does not fit a CPU
+    reference evaluation in minutes: the CPU arm evaluates a 16384-atom periodic box of the same density and model and its
+    rate is scaled by the atom ratio (labelled as such)."""
+    if args.config == "cfg5":
+        n_sub = 16384
+        spec, data = S.make_config("cfg4", n_atoms_total=n_sub)
+        n_full = args.atoms or 262144
+        return spec, data, n_sub / n_full, (f"{n_sub}-atom periodic sub-box of the same density / model, rate scaled by "
+                                            f"{n_sub}/{n_full} atoms")
+    spec, data = workload(args.config, 0, args.batch)
+    return spec, data, 1.0, "the full batch"
+
+
+def config_dict(args, world, B, N, E, F, T):
+    """ONE description of the workload, identical in both arms (the driver compares them)."""
+    spatial = args.config == "cfg5"
+    return {"workload": f"{args.config}: {S.CONFIGS[args.config]['desc']}", "systems_per_gpu": (1 if spatial else B),
+            "atoms": N, "edges": E, "n_atom_basis": F, "n_interactions": T,
+            "parallelism": (f"spatial x{world}: one periodic box in {world} slab(s), NCCL halo exchange of ghost rows"
+                            if spatial else f"batch-sharded x{world}"),
+            "weights": "seeded xavier-uniform (synthetic.init_params)",
+            "timing": {"b200": "CUDA events per step on the launch stream, 256 MiB device memset between timed steps "
+                               "(outside the event intervals); step = CUDA-graph replay of model(inputs) on the resident "
+                               "batch (cfg5: eager per-block pipeline, tables exceed L2)",
+                       "reference": "time.perf_counter per full evaluation of the reference modules on the host cores"}}
+
+
 def run_reference(args, rank, world):
-    """The reference's CPU path = the same ATen op sequence, restated in oracle/spk_oracle.py (kind 'port': the Python
-    reference cannot travel to the GPU box), timed on all host cores.  Rank 0 only."""
+    """The reference's CPU path: the UNMODIFIED reference modules (kind 'reference', oracle/_ref) -- or the oracle port if
+    they are absent -- timed on the host cores.  Rank 0 only."""
     if rank != 0:
         return
-    spec, data = workload(args.config, 0, args.batch)
+    spec, data, scale, what = cpu_sample(args)
     params = S.init_params(spec, seed=0)
-    cores, _ = best_thread_count(spec, params, data)
-    ts = oracle_eval_time(spec, params, data, args.steps, args.warmup, cores)
+    run, kind = reference_engine(spec, params, data)
+    cores, _ = best_thread_count(run)
+    ts = cpu_eval_time(run, args.steps, args.warmup, cores)
     B = n_systems(data)
-    E = int(data[S.idx_i].shape[0])
-    ms = 1e3 * float(np.mean(ts))
-    v = B / float(np.mean(ts))
+    N_s, E_s = int(data[S.Z].shape[0]), int(data[S.idx_i].shape[0])
+    if args.config == "cfg5":
+        N, E = args.atoms or 262144, int(round(E_s / scale))
+    else:
+        N, E = N_s, E_s
+    ms = 1e3 * float(np.mean(ts)) / scale
+    v = B * scale / float(np.mean(ts))
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong" if args.config == "cfg5" else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.config}: {S.CONFIGS[args.config]['desc']}", "systems": B,
-                   "atoms": int(data[S.Z].shape[0]), "edges": E},
-        "edge_msgs_per_s": E * spec["n_interactions"] / float(np.mean(ts)),
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} full-batch evals ({B} systems) after {args.warmup} warm-up, "
-                                   f"oracle/spk_oracle.py fp32 (same ATen op sequence as the reference), "
-                                   f"torch.set_num_threads({cores}) = fastest of 8/16/32/64/{os.cpu_count()} probed; median {1e3 * float(np.median(ts)):.1f} ms, "
-                                   f"min {1e3 * float(np.min(ts)):.1f} ms"},
+        "config": config_dict(args, args.gpus, B, N, E, spec["n_atom_basis"], spec["n_interactions"]),
+        "edge_msgs_per_s": E_s * spec["n_interactions"] / float(np.mean(ts)),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{args.steps} evaluations of {what} ({B} systems, {N_s} atoms, {E_s} edges) after "
+                                   f"{args.warmup} warm-up, "
+                                   + ("the reference's own modules (oracle/ref_loader.py)" if kind == "reference"
+                                      else "oracle/spk_oracle.py (same ATen op sequence as the reference)")
+                                   + f", fp32, torch.set_num_threads({cores}) = fastest of 8/16/32/64/{os.cpu_count()} "
+                                     f"probed; median {1e3 * float(np.median(ts)):.1f} ms, min {1e3 * float(np.min(ts)):.1f} ms"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_leg(args):
+    spec, data, scale, what = cpu_sample(args)
+    params = S.init_params(spec, seed=0)
+    run, kind = reference_engine(spec, params, data)
+    cores, _ = best_thread_count(run)
+    ts = cpu_eval_time(run, 3, 0, cores)
+    B = n_systems(data)
+    return {"value": B * scale / float(np.mean(ts)), "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"3 evaluations of {what} ({B} systems, {int(data[S.Z].shape[0])} atoms, "
+                      f"{int(data[S.idx_i].shape[0])} edges), "
+                      + ("the reference's own modules (oracle/ref_loader.py)" if kind == "reference"
+                         else "oracle/spk_oracle.py (the reference's ATen op sequence)")
+                      + f", fp32, {cores} threads (fastest of 8/16/32/64/{os.cpu_count()} probed on this host); "
+                        f"mean {1e3 * float(np.mean(ts)):.0f} ms"}
+
+
+def eager_gpu_leg(spec, params, data, dev, B, n_it=10):
+    """The reference's own single-GPU eager PyTorch path (modules .to(cuda), cuBLAS SGEMM, index_select / index_add_ atomics,
+    autograd backward) on the same B200, inputs resident: the denominator of the north-star's >= 5x target."""
+    try:
+        run, kind = reference_engine(spec, params, data, device=dev)
+        for _ in range(3):
+            run()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n_it):
+            run()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / n_it
+        return {"value": B / dt, "unit": UNIT, "ms_per_step": 1e3 * dt, "kind": kind,
+                "what": "the reference's modules in eager PyTorch on the same B200 (wall clock, synchronised), inputs resident"}
+    except Exception as exc:  # pragma: no cover
+        return {"error": repr(exc)[:200]}
 
 
 # ------------------------------------------------------------------------------------------------- CUDA arm
@@ -404,38 +509,15 @@ def run_cuda(args, rank, world, local_rank):
             except Exception:
                 pass
 
-    # ---- CPU baseline (bounded sample, rank 0, N=1 only) --------------------------------------------------------------
+    # ---- CPU baseline (bounded sample, rank 0, N=1 only): the reference's own modules when oracle/_ref is present ----------
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cores, _ = best_thread_count(spec, params, data)
-        ts = oracle_eval_time(spec, params, data, 3, 0, cores)
-        cpu = {"value": B / float(np.mean(ts)), "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"3 full-batch evals ({B} systems, {E} edges) of oracle/spk_oracle.py fp32 (the reference's "
-                         f"ATen op sequence) on {cores} threads (fastest of 8/16/32/64/{os.cpu_count()} probed on this "
-                         f"host); mean {1e3 * float(np.mean(ts)):.0f} ms"}
+        cpu = cpu_baseline_leg(args)
 
-    # ---- the reference's eager single-GPU path (oracle port = same ATen op sequence) on this B200, for the >=5x target ----
+    # ---- the reference's eager single-GPU path (its own modules .to(cuda)) on this B200, for the >=5x target ---------------
     eager = None
     if world == 1 and not args.no_cpu_baseline:
-        try:
-            from oracle import spk_oracle as O
-
-            p_dev = O.to_torch(params, torch.float32, dev)
-            x_dev = O.to_torch(data, torch.float32, dev)
-            for _ in range(3):
-                O.energy_forces(spec, p_dev, x_dev, device=dev)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            n_it = 10
-            for _ in range(n_it):
-                O.energy_forces(spec, p_dev, x_dev, device=dev)
-            torch.cuda.synchronize()
-            dt = (time.perf_counter() - t0) / n_it
-            eager = {"value": B / dt, "unit": UNIT, "ms_per_step": 1e3 * dt,
-                     "kind": "port: oracle/spk_oracle.py (the reference modules' eager ATen op sequence, cuBLAS SGEMM, "
-                             "index_select / index_add_ atomics, autograd backward) on the same B200, inputs resident"}
-        except Exception as exc:  # pragma: no cover
-            eager = {"error": repr(exc)[:200]}
+        eager = eager_gpu_leg(spec, params, data, dev, B)
 
     md_info = None
     if args.md and world == 1 and S.cell in data and not padded:
@@ -470,12 +552,9 @@ def run_cuda(args, rank, world, local_rank):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": f"{args.config}: {S.CONFIGS[args.config]['desc']}", "systems_per_gpu": B, "atoms": N,
-                   "edges": E, "n_atom_basis": F, "n_interactions": T, "parallelism": f"batch-sharded x{world}",
-                   "l2": "256 MiB device memset between timed steps (outside the per-step event intervals)",
-                   "step": ("CUDA-graph replay of model(inputs) on the resident batch (GraphedPotential.replay)" if use_graph
-                            else "eager model(inputs) on the resident batch"),
-                   "weights": "seeded xavier-uniform (synthetic.init_params)"},
+        "config": config_dict(args, world, B, N, E, F, T),
+        "step": ("CUDA-graph replay of model(inputs) on the resident batch (GraphedPotential.replay)" if use_graph
+                 else "eager model(inputs) on the resident batch"),
         "edge_msgs_per_s": world * E * T * args.steps / (total_ms * 1e-3),
         "wall_ms_per_step": 1e3 * t_wall / args.steps,
         "clocks": clocks,
@@ -484,10 +563,220 @@ def run_cuda(args, rank, world, local_rank):
                 "ms_per_step_median": e2e_steps_ms[len(e2e_steps_ms) // 2], "ms_per_step_max": e2e_steps_ms[-1]},
         "gpu_launches": launches,
         "roofline": roof, "roofline_all": roof_all, "cpu_baseline": cpu, "eager_gpu_baseline": eager,
+        "vs_reference_gpu_eager": (value / eager["value"] if eager and "value" in eager else None),
+        "e2e_vs_reference_gpu_eager": (e2e_value / eager["value"] if eager and "value" in eager else None),
         "impl_switches": {"dense": ops.DENSE_IMPL, "edge": ops.EDGE_IMPL},
     }
     if md_info is not None:
         line["md"] = md_info
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------- spatial (cfg5) arm
+def run_spatial(args, rank, world, local_rank):
+    """cfg5: ONE periodic box (default 262144 atoms, PaiNN 128x3, E+F) cut into `world` slabs; every rank owns a slab, holds
+    read-only ghost rows of the senders it does not own, and exchanges (x, mu) ghost rows per interaction block over NCCL
+    point-to-point (gradients back in the reverse sweep).  STRONG scaling: the box is fixed, `value` = whole-box evaluations
+    per second.  At N=1 the same pipeline runs without a halo -- the single-GPU workload whose gathered tables (400 MB per
+    [N,3F] table) exceed the 126 MB L2, where the roofline fraction of the edge kernels is an HBM statement."""
+    from schnetpack_b200 import _lib, ops, parallel as P
+    from schnetpack_b200.model import from_spec
+    from schnetpack_b200.neighbors import neighbor_list
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=dev)
+    n_total = args.atoms or 262144
+    spec = S.model_spec(**S.CONFIGS["cfg5"]["spec"])
+    box = S.periodic_box(n_total, build_list=False)
+    params = S.init_params(spec, seed=0)
+    model = from_spec(spec, params, dev)
+    F, T = spec["n_atom_basis"], spec["n_interactions"]
+    # the neighbour list of the whole box, built on the device (linked-cell kernel), then the graph partition on the host
+    R_all = torch.as_tensor(box[S.R], device=dev)
+    ii, jj, off, _ = neighbor_list(R_all, torch.as_tensor(box[S.cell], device=dev), torch.as_tensor(box[S.pbc], device=dev),
+                                   torch.as_tensor(box[S.n_atoms], device=dev), spec["cutoff"])
+    box[S.idx_i], box[S.idx_j], box[S.offsets] = ii.cpu().numpy(), jj.cpu().numpy(), off.cpu().numpy()
+    E_total = int(box[S.idx_i].shape[0])
+    del ii, jj, off, R_all
+    torch.cuda.empty_cache()
+    owner = P.slab_owners(box[S.R], world)
+    plan = P.partition_graph(owner, box[S.idx_i], box[S.idx_j], rank, world)
+    engine = P.PartitionedPotential(model, box, plan, dev, group=None)
+    E_loc, N_loc = int(plan.idx_i.shape[0]), plan.n_owned + plan.n_ghost
+    halo_rows = plan.n_ghost
+    box.pop(S.idx_i), box.pop(S.idx_j), box.pop(S.offsets)
+
+    # ---- live timing of the edge kernels (CUDA events on the launch stream, inside the timed region)
+    ev = {"fwd": [], "bwd": []}
+    orig_fwd, orig_bwd = ops.painn_edge_fwd, ops.painn_edge_bwd
+    timing = {"on": False}
+
+    def timed(kind, orig):
+        def f(x, mu, *a, **k):
+            if not timing["on"]:
+                return orig(x, mu, *a, **k)
+            s_, e_ = torch.cuda.Event(True), torch.cuda.Event(True)
+            s_.record()
+            r = orig(x, mu, *a, **k)
+            e_.record()
+            ev[kind].append((s_, e_, mu is not None))
+            return r
+        return f
+
+    ops.painn_edge_fwd, ops.painn_edge_bwd = timed("fwd", orig_fwd), timed("bwd", orig_bwd)
+    # halo share: events around every exchange (forward and reverse) on the launch stream
+    halo_ev = []
+    orig_halo_f, orig_halo_b = P.HaloExchange.forward, P.HaloExchange.backward
+
+    def halo_f(ctx, rows, plan_, group=None):
+        if not timing["on"]:
+            return orig_halo_f(ctx, rows, plan_, group)
+        s_, e_ = torch.cuda.Event(True), torch.cuda.Event(True)
+        s_.record()
+        r = orig_halo_f(ctx, rows, plan_, group)
+        e_.record()
+        halo_ev.append((s_, e_))
+        return r
+
+    def halo_b(ctx, g):
+        if not timing["on"]:
+            return orig_halo_b(ctx, g)
+        s_, e_ = torch.cuda.Event(True), torch.cuda.Event(True)
+        s_.record()
+        r = orig_halo_b(ctx, g)
+        e_.record()
+        halo_ev.append((s_, e_))
+        return r
+
+    P.HaloExchange.forward, P.HaloExchange.backward = staticmethod(halo_f), staticmethod(halo_b)
+
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    for _ in range(max(args.warmup, 3)):
+        energy, forces = engine()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    timing["on"] = True
+    c0 = _lib.launch_count
+    step_ev = []
+    torch.cuda.synchronize()
+    for _ in range(args.steps):
+        flush_buf.fill_(1)
+        s_, e_ = torch.cuda.Event(True), torch.cuda.Event(True)
+        s_.record()
+        energy, forces = engine()
+        e_.record()
+        step_ev.append((s_, e_))
+    torch.cuda.synchronize()
+    timing["on"] = False
+    launches = _lib.launch_count - c0
+    clocks = sampler.stop() if sampler is not None else None
+    dev_ms = sum(a.elapsed_time(b) for a, b in step_ev)
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    halo_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in halo_ev)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.barrier()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(halo_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = args.steps / (total_ms * 1e-3)                      # whole-box evaluations per second (all ranks together)
+
+    # ---- end to end: host positions in, energy + owned forces out
+    R_host = engine.R_own.detach().cpu().pin_memory()
+    f_host = torch.empty((plan.n_owned, 3), dtype=torch.float32).pin_memory()
+    e_host = torch.empty(1, dtype=torch.float32).pin_memory()
+    h2d, d2h = R_host.numel() * 4, f_host.numel() * 4 + 4
+
+    def e2e_step():
+        engine.set_positions(R_host.to(dev, non_blocking=True))
+        e_, f_ = engine()
+        e_host.copy_(e_, non_blocking=True)
+        f_host.copy_(f_, non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    e2e_ev = []
+    for _ in range(args.steps):
+        flush_buf.fill_(1)
+        s_, e_ = torch.cuda.Event(True), torch.cuda.Event(True)
+        s_.record()
+        e2e_step()
+        e_.record()
+        e2e_ev.append((s_, e_))
+    torch.cuda.synchronize()
+    t2 = torch.tensor([sum(a.elapsed_time(b) for a, b in e2e_ev)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.barrier()
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_value = args.steps / (float(t2.item()) * 1e-3)
+    if rank != 0:
+        return
+
+    peak, peak_src = measured_peaks()
+    roof_all = {}
+    for kind in ("fwd", "bwd"):
+        if not ev[kind]:
+            continue
+        ms_l = [(a.elapsed_time(b), hm) for a, b, hm in ev[kind]]
+        tot_ms = sum(m for m, _ in ms_l)
+        tot_bytes = sum(edge_kernel_bytes(E_loc, N_loc, F, hm, kind == "bwd") for _, hm in ms_l)
+        ach = tot_bytes / (tot_ms * 1e-3) / 1e9
+        roof_all[kind] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                          "kernel": f"k_painn_edge_{kind}_tc", "launches_timed": len(ms_l), "avg_us": 1e3 * tot_ms / len(ms_l),
+                          "algorithmic_bytes_per_launch": tot_bytes / len(ms_l), "share_of_step": tot_ms / dev_ms,
+                          "peak_source": peak_src,
+                          "model": "SURVEY 8(d) no-reuse gather model over this rank's edges / local rows; the gathered "
+                                   "tables (N_local x 1.5 KB x 2) exceed the 126 MB L2 here",
+                          "timing": "CUDA events around the kernel, inside the timed region (rank 0)"}
+    roof = None
+    if roof_all:
+        dom = max(roof_all, key=lambda k: roof_all[k]["share_of_step"])
+        roof = dict(roof_all[dom])
+        tr = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tr):
+            try:
+                roof["traffic"] = json.load(open(tr)).get(f"cfg5_n{world}_" + roof["kernel"])
+            except Exception:
+                pass
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline_leg(args)
+    line = {
+        "metric": METRIC, "value": value, "unit": "box-evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": config_dict(args, world, 1, n_total, E_total, F, T),
+        "step": "eager per-block pipeline (context net -> halo exchange -> fused edge kernel -> mixing) + autograd reverse sweep",
+        "edge_msgs_per_s": E_total * T * args.steps / (total_ms * 1e-3),
+        "atoms_per_s": n_total * args.steps / (total_ms * 1e-3),
+        "rank0": {"owned_atoms": plan.n_owned, "ghost_atoms": halo_rows, "local_edges": E_loc},
+        "halo": {"exchanges_per_step": len(halo_ev) // max(args.steps, 1), "ms_per_step_max_over_ranks": float(halo_ms.item()) / args.steps,
+                 "share_of_step": float(halo_ms.item()) / total_ms,
+                 # forward: positions (3) + x (3F) per block + mu (3F) from the second block on; the reverse sweep sends the
+                 # same volume back (gradients of the ghost rows to their owners)
+                 "bytes_sent_per_step_rank0": 2 * 4 * int(sum(len(v) for v in plan.send.values())) * (3 + 3 * F * T + 3 * F * (T - 1)),
+                 "transport": "NCCL grouped isend/irecv (torch.distributed.batch_isend_irecv), index-gather pack, receives land in the ghost block"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "box-evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "PartitionedPotential.set_positions(host) -> __call__() -> energy, forces to pinned host"},
+        "gpu_launches": launches,
+        "roofline": roof, "roofline_all": roof_all, "cpu_baseline": cpu,
+        "impl_switches": {"dense": ops.DENSE_IMPL, "edge": ops.EDGE_IMPL},
+    }
     print(json.dumps(line), flush=True)
 
 
@@ -499,6 +788,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="cfg2", choices=sorted(S.CONFIGS))
     ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--atoms", type=int, default=None, help="cfg5: atoms in the periodic box (default 262144)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--md", action="store_true", help="also time the device-resident MD step (rows f1+f2); not part of the metric")
     ap.add_argument("--no-graph", action="store_true", help="time eager model(inputs) calls (value and e2e) instead of CUDA-graph replays")
@@ -511,7 +801,10 @@ def main():
         return
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
-    run_cuda(args, rank, world, local_rank)
+    if args.config == "cfg5":
+        run_spatial(args, rank, world, local_rank)
+    else:
+        run_cuda(args, rank, world, local_rank)
     if world > 1:
         import torch.distributed as dist
 

@@ -187,6 +187,42 @@ int spk_painn_mix_ctx_bwd(const float* g_ctx, const float* g_q, const float* VW,
                           float* g_q_out, float* g_VW, spk_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Persistent per-atom stage (csrc/atom_chain.cu): all per-atom work between two edge kernels -- PaiNNMixing
+ * (painn.py:103-116) followed by the next block's interatomic_context_net (painn.py:54), or their reverses -- as ONE
+ * launch.  The caller describes the stage as up to SPK_CHAIN_MAX_STEPS steps executed in order for every 128-atom tile
+ * (step k of a tile starts when step k-1 of the SAME tile is complete; tiles are independent because every step is
+ * row-local):
+ *   SPK_CHAIN_GEMM   Y[rows, N] = act( (A[rows, K] .* a_pre) * W^T + bias ) + addend over rows_per_atom * n_atoms rows
+ *                    (the spk_dense_tc operation; a_pre != NULL multiplies A by the saved act'(pre) = SPK_ACT_GIVEN; with an
+ *                    activation, y_pre != NULL receives act'(pre)).  Wp = spk_tc_pack_weight output advanced to the
+ *                    128-column tiles: Wp + spk_tc_packed_floats_tn(N, K, 64).  Requires N % 128 == 0, K % 16 == 0.
+ *   SPK_CHAIN_MIX_CTX / MIX_UPDATE / MIX_UPDATE_BWD / MIX_CTX_BWD   the elementwise glue of spk_painn_mix_* with operands
+ *                    (g0, g1, g2, g3) -> (o0, o1) as listed in csrc/atom_chain.cu.
+ * workspace: spk_atom_chain_workspace_ints(n_steps, n_atoms) int32, zero before the FIRST use (the kernel leaves it zero);
+ * one workspace per concurrently running stream.
+ * ------------------------------------------------------------------------------------------------------------- */
+#define SPK_CHAIN_MAX_STEPS 8
+#define SPK_CHAIN_GEMM 0
+#define SPK_CHAIN_MIX_CTX 1        /* g0 = q [N,F], g1 = VW [N,3,2F]                      -> o0 = ctx [N,2F]                  */
+#define SPK_CHAIN_MIX_UPDATE 2     /* g0 = q, g1 = VW, g2 = mu [N,3,F], g3 = s [N,3F]     -> o0 = q', o1 = mu'               */
+#define SPK_CHAIN_MIX_UPDATE_BWD 3 /* g0 = g_q, g1 = VW, g2 = g_mu, g3 = s               -> o0 = g_s [N,3F], o1 = g_VW      */
+#define SPK_CHAIN_MIX_CTX_BWD 4    /* g0 = g_ctx [N,2F], g1 = VW, g2 = g_q               -> o0 = g_q', o1 = g_VW (V part +=) */
+typedef struct {
+    int32_t kind, rows_per_atom, K, N, act, F;
+    float eps;
+    int32_t reserved;
+    int64_t lda, ldy, ld_add;
+    const float *A, *a_pre, *Wp, *bias, *addend;
+    float *Y, *y_pre;
+    const float *g0, *g1, *g2, *g3;
+    float *o0, *o1;
+} spk_chain_step_t;
+size_t spk_tc_packed_floats_tn(int N, int K, int tile_n); /* floats of the tile_n-wide (64 | 128) packing of W [N,K] */
+size_t spk_atom_chain_workspace_ints(int n_steps, int64_t n_atoms);
+int spk_atom_chain(const spk_chain_step_t* steps /* host array */, int n_steps, int64_t n_atoms, int32_t* workspace,
+                   size_t workspace_ints, spk_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * SchNet.  representation/schnet.py:41-70 (SchNetInteraction.forward).
  * ------------------------------------------------------------------------------------------------------------- */
 /* continuous-filter convolution (schnet.py:62-67): m[i] = sum_{s in row i} h[j_s] * Wraw[s] * fc_s ; Wraw [E,F] is

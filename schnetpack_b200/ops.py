@@ -309,6 +309,19 @@ class Lin:
 
     __slots__ = ("w", "wt", "b", "w_pk", "wt_pk")
 
+    @staticmethod
+    def _wide(pk: Optional[Tensor], n: int, k: int) -> Optional[Tensor]:
+        """the 128-column tiles of a packed weight ([64-wide tiles | 128-wide tiles]); None if it has none"""
+        if pk is None or n % 128:
+            return None
+        return pk[_lib.lib().spk_tc_packed_floats_tn(n, k, 64):]
+
+    def fwd_wide(self):
+        return self._wide(self.w_pk, self.w.shape[0], self.w.shape[1])
+
+    def bwd_wide(self):
+        return self._wide(self.wt_pk, self.wt.shape[0], self.wt.shape[1])
+
     def __init__(self, weight: Tensor, bias: Optional[Tensor] = None):
         self.w = weight.detach().contiguous()
         self.wt = weight.detach().t().contiguous()
@@ -342,6 +355,49 @@ class Lin:
         if self.wt_pk is not None and self._tc_ok(G, self.wt.shape[0], kw):
             return dense_tc(G, self.wt_pk, self.wt.shape[0], None, ACT_NONE, **kw)
         return dense(G, self.w, None, ACT_NONE, **kw)
+
+
+# ------------------------------------------------------------------------------------------------------------ atom chain
+# persistent per-atom stage (csrc/atom_chain.cu): one launch for mixing(t) + context(t+1) (or their reverses) instead of
+# seven.  SPK_B200_CHAIN=0 restores the launch-per-layer pipeline (same kernels as round 1) for A/B measurements.
+CHAIN_IMPL = os.environ.get("SPK_B200_CHAIN", "1") != "0"
+_CHAIN_WS: "dict[tuple, Tensor]" = {}
+
+
+def chain_gemm(A: Tensor, w_wide: Tensor, n_out: int, k: int, Y: Tensor, rows_per_atom: int = 1, bias=None, act=ACT_NONE,
+               a_pre=None, addend=None, y_pre=None) -> _lib.ChainStep:
+    st = _lib.ChainStep()
+    st.kind, st.rows_per_atom, st.K, st.N, st.act = _lib.CHAIN_GEMM, rows_per_atom, int(k), int(n_out), int(act)
+    st.lda, st.ldy = int(A.shape[-1]), int(Y.shape[-1])
+    st.ld_add = int(addend.shape[-1]) if addend is not None else 0
+    st.A, st.Wp, st.Y = A.data_ptr(), w_wide.data_ptr(), Y.data_ptr()
+    st.a_pre = a_pre.data_ptr() if a_pre is not None else None
+    st.bias = bias.data_ptr() if bias is not None else None
+    st.addend = addend.data_ptr() if addend is not None else None
+    st.y_pre = y_pre.data_ptr() if y_pre is not None else None
+    return st
+
+
+def chain_glue(kind: int, F: int, eps: float, g0, g1, g2, g3, o0, o1) -> _lib.ChainStep:
+    st = _lib.ChainStep()
+    st.kind, st.F, st.eps = kind, int(F), float(eps)
+    for name, t in (("g0", g0), ("g1", g1), ("g2", g2), ("g3", g3), ("o0", o0), ("o1", o1)):
+        setattr(st, name, t.data_ptr() if t is not None else None)
+    return st
+
+
+def atom_chain(steps, n_atoms: int, device):
+    """Run a stage program (list of ChainStep) over all 128-atom tiles in ONE persistent launch."""
+    n = len(steps)
+    arr = (_lib.ChainStep * n)(*steps)
+    need = _lib.lib().spk_atom_chain_workspace_ints(n, n_atoms)
+    stream = torch.cuda.current_stream()
+    key = (device.index if device.index is not None else torch.cuda.current_device(), stream.cuda_stream)
+    ws = _CHAIN_WS.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.zeros(max(need, 4096), dtype=torch.int32, device=device)   # zero once; the kernel leaves it zero
+        _CHAIN_WS[key] = ws
+    _lib.call("spk_atom_chain", arr, n, n_atoms, _p(ws), ws.numel(), c_void_p(stream.cuda_stream))
 
 
 # ------------------------------------------------------------------------------------------------------------ PaiNN

@@ -112,6 +112,19 @@ class RankPlan:
         self.rank, self.world = rank, world
         self.owned, self.ghosts, self.edge_ids, self.idx_i, self.idx_j = owned, ghosts, edge_ids, idx_i, idx_j
         self.send, self.recv = send, recv
+        self._dev_send = {}
+
+    def to_device(self, device):
+        """Cache the per-peer send lists as index tensors on ``device`` (the exchange then never copies them again)."""
+        self._dev_send = {p: torch.as_tensor(v).to(device) for p, v in self.send.items()}
+        return self
+
+    def send_index(self, p, device):
+        t = self._dev_send.get(p)
+        if t is None or t.device != torch.device(device):
+            t = torch.as_tensor(self.send[p]).to(device)
+            self._dev_send[p] = t
+        return t
 
     @property
     def n_owned(self) -> int:
@@ -175,7 +188,17 @@ class HaloExchange(torch.autograd.Function):
 
     forward: every rank sends the rows its peers list as ghosts and receives its own ghost rows (isend/irecv);
     backward: the gradients of the ghost rows travel back to their owners and are accumulated onto the rows they came
-    from (fixed peer order: deterministic).  All ranks must call it the same number of times in the same order."""
+    from (fixed peer order: deterministic).  All ranks must call it the same number of times in the same order.
+
+    On GPUs the transport is NCCL point-to-point (grouped send/recv over NVLink; receives land directly in the ghost block,
+    one index-gather kernel per peer packs the send rows).  With the gloo backend (CPU tests, or several ranks sharing one
+    GPU in the single-GPU test of the CUDA engine) CUDA rows are staged through host memory, which gloo requires."""
+
+    @staticmethod
+    def _staged(rows, group):
+        import torch.distributed as dist
+
+        return rows.is_cuda and dist.get_backend(group) == "gloo"
 
     @staticmethod
     def forward(ctx, rows: torch.Tensor, plan: RankPlan, group=None):
@@ -183,25 +206,29 @@ class HaloExchange(torch.autograd.Function):
 
         ctx.plan, ctx.group, ctx.n_owned = plan, group, rows.shape[0]
         tail = tuple(rows.shape[1:])
-        ghost = rows.new_zeros((plan.n_ghost,) + tail)
-        ops, bufs = [], []
+        staged = HaloExchange._staged(rows, group)
+        ghost = rows.new_empty((plan.n_ghost,) + tail)
+        ops, keep, late = [], [], []
         for p in sorted(set(plan.send) | set(plan.recv)):
             if p in plan.send:
-                sb = rows.detach()[torch.as_tensor(plan.send[p], device=rows.device)].contiguous()
-                bufs.append(sb)
+                sb = rows.detach().index_select(0, plan.send_index(p, rows.device))
+                if staged:
+                    sb = sb.cpu()
+                keep.append(sb)
                 ops.append(dist.P2POp(dist.isend, sb, p, group))
             if p in plan.recv:
                 a, b = plan.recv[p]
-                rb = rows.new_empty((b - a,) + tail)
-                bufs.append((rb, a, b))
+                if staged:
+                    rb = torch.empty((b - a,) + tail, dtype=rows.dtype)
+                    late.append((rb, a, b))
+                else:
+                    rb = ghost[a:b]                                      # contiguous block of the ghost rows: no unpack
                 ops.append(dist.P2POp(dist.irecv, rb, p, group))
         if ops:
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
-        for item in bufs:
-            if isinstance(item, tuple):
-                rb, a, b = item
-                ghost[a:b] = rb
+        for rb, a, b in late:
+            ghost[a:b] = rb.to(rows.device)
         return ghost
 
     @staticmethod
@@ -210,21 +237,129 @@ class HaloExchange(torch.autograd.Function):
 
         plan, group = ctx.plan, ctx.group
         tail = tuple(g_ghost.shape[1:])
+        staged = HaloExchange._staged(g_ghost, group)
+        g_ghost = g_ghost.contiguous()
         g_rows = g_ghost.new_zeros((ctx.n_owned,) + tail)
         ops, recvs, keep = [], [], []
         for p in sorted(set(plan.send) | set(plan.recv)):
             if p in plan.recv:                               # my ghosts came from p: their gradients go back to p
                 a, b = plan.recv[p]
-                sb = g_ghost[a:b].contiguous()
+                sb = g_ghost[a:b].cpu() if staged else g_ghost[a:b]
                 keep.append(sb)
                 ops.append(dist.P2POp(dist.isend, sb, p, group))
             if p in plan.send:                               # p holds ghosts of my rows: receive their gradients
-                rb = g_ghost.new_empty((len(plan.send[p]),) + tail)
+                n = len(plan.send[p])
+                rb = torch.empty((n,) + tail, dtype=g_ghost.dtype) if staged else g_ghost.new_empty((n,) + tail)
                 recvs.append((p, rb))
                 ops.append(dist.P2POp(dist.irecv, rb, p, group))
         if ops:
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
         for p, rb in recvs:                                  # ascending peer order: deterministic accumulation
-            g_rows.index_add_(0, torch.as_tensor(plan.send[p], device=g_rows.device), rb)
+            g_rows.index_add_(0, plan.send_index(p, g_rows.device), rb.to(g_rows.device))
         return g_rows, None, None
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# The CUDA engine on a partition: per-block kernel pipelines with a halo exchange in front of every edge kernel.
+# ----------------------------------------------------------------------------------------------------------------------
+def _halo(rows: torch.Tensor, plan: RankPlan, group):
+    if plan.world == 1 or (plan.n_ghost == 0 and not plan.send):
+        return rows.new_zeros((0,) + tuple(rows.shape[1:]))
+    return HaloExchange.apply(rows, plan, group)
+
+
+class PartitionedPotential:
+    """Energy + forces of ONE large system evaluated by the ranks of a process group, every
+    rank running the sm_100a kernels on its part of the graph:
+
+        owned atoms  -> context net (dense kernels)            x [n_owned, 3F]
+        halo         -> ghost rows of (x, mu) from their owners  (HaloExchange: NCCL point-to-point, autograd-aware)
+        local edges  -> fused edge kernel (receivers owned, senders owned or ghost)
+        owned atoms  -> mixing (dense kernels + glue)
+
+    per interaction block, then the Atomwise head on the owned atoms; forces come from ``torch.autograd.grad`` exactly as
+    in the single-device model, the reverse halo (gradients of ghost rows summed into their owners, ghost position
+    gradients returned with the first exchange's backward) being HaloExchange's backward.  Each directed edge is computed
+    by exactly one rank, so owned-atom results are complete without a reduction; the only collective besides the halo is
+    the all-reduce of the per-system partial energies.
+
+    ``model`` is a ``schnetpack_b200.model.NeuralNetworkPotential`` with a PaiNN representation and an Atomwise head;
+    ``batch`` is the GLOBAL system (numpy or tensors: Z, positions, idx_i, idx_j, offsets, idx_m, n_atoms) which every rank
+    holds at set-up (only its part goes to the device).
+    """
+
+    def __init__(self, model, batch: Dict, plan: RankPlan, device, group=None):
+        from . import functional as K
+        from . import ops
+
+        self.K, self.ops = K, ops
+        self.model, self.plan, self.group, self.device = model, plan, group, torch.device(device)
+        rep = model.representation
+        if type(rep).__name__ != "PaiNN":
+            raise NotImplementedError("PartitionedPotential: PaiNN representation (the named large-system configs)")
+        self.rep = rep
+        self.head = [m for m in model.output_modules if type(m).__name__ == "Atomwise"][0]
+        dev = self.device
+
+        def take(key, sel):
+            v = batch[key]
+            v = v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
+            return torch.as_tensor(v[sel]).to(dev)
+
+        self.Z = take(properties.Z, plan.owned)
+        self.R_own = take(properties.R, plan.owned).float().contiguous()
+        self.offsets = take(properties.offsets, plan.edge_ids).float().contiguous()
+        self.idx_m = take(properties.idx_m, plan.owned)
+        self.idx_i = torch.as_tensor(plan.idx_i).to(dev)
+        self.idx_j = torch.as_tensor(plan.idx_j).to(dev)
+        self.n_sys = int(np.asarray(batch[properties.n_atoms].cpu() if isinstance(batch[properties.n_atoms], torch.Tensor)
+                                    else batch[properties.n_atoms]).shape[0])
+        self.n_local = plan.n_owned + plan.n_ghost
+        plan.to_device(dev)
+        with torch.cuda.device(dev):
+            self.graph = ops.EdgeGraph(self.idx_i, self.idx_j, self.n_local)
+
+    def set_positions(self, R_own: torch.Tensor):
+        self.R_own = R_own.to(self.device, torch.float32).contiguous()
+
+    def __call__(self):
+        """Returns (energy [n_systems] summed over ranks, forces of the OWNED atoms [n_owned, 3])."""
+        K, ops, plan, rep, group = self.K, self.ops, self.plan, self.rep, self.group
+        n_o, n_g = plan.n_owned, plan.n_ghost
+        dev = self.device
+        with torch.cuda.device(dev), torch.enable_grad():
+            pk = rep._pack()
+            F, act = pk.F, rep._act
+            R_own = self.R_own.detach().requires_grad_(True)                      # model/base.py:105-111
+            R_loc = torch.cat([R_own, _halo(R_own, plan, group)], dim=0)          # ghost positions (autograd-aware)
+            r_ij = K.PairwiseDistancesFunction.apply(R_loc, self.offsets,        # atomistic/distances.py:14-26
+                                                     dict(idx_i=self.idx_i, idx_j=self.idx_j, graph=self.graph))
+            geom = K.EdgeGeometry(rep, r_ij, self.graph)                          # painn.py:227-230, shared by the blocks
+            if isinstance(rep.embedding, torch.nn.Embedding) and len(rep.electronic_embeddings) == 0:
+                q = ops.embedding(rep.embedding.weight.detach().contiguous(), self.Z)   # painn.py:239
+            else:
+                raise NotImplementedError("PartitionedPotential: plain nn.Embedding only")
+            mu = None
+            ghost_q = q.new_zeros((n_g, F))
+            for t in range(pk.T):
+                b = pk.blocks[t]
+                x = K.PaiNNContextFunction.apply(q, b, act)                       # painn.py:54 on the owned atoms
+                x_loc = torch.cat([x, _halo(x, plan, group)], dim=0)              # senders' rows incl. ghosts
+                mu_loc = torch.cat([mu, _halo(mu, plan, group)], dim=0) if mu is not None else None
+                q_loc = torch.cat([q, ghost_q], dim=0)                            # ghost rows receive nothing
+                q1, mu1 = K.PaiNNEdgeFunction.apply(x_loc, mu_loc, q_loc, r_ij, geom, pk, t)     # :55-65
+                q, mu = K.PaiNNMixingFunction.apply(q1[:n_o], mu1[:n_o], b, F, pk.eps, act)      # :103-116
+            inputs = {"scalar_representation": q, properties.idx_m: self.idx_m,
+                      properties.n_atoms: torch.empty(self.n_sys, dtype=torch.int64, device=dev)}
+            agg = self.head.aggregation_mode
+            if agg != "sum":
+                raise NotImplementedError("PartitionedPotential: Atomwise(aggregation_mode='sum')")
+            e_part = self.head(inputs)[self.head.output_key]                      # atomwise.py:69-88 on the owned atoms
+            (g,) = torch.autograd.grad([e_part], [R_own], grad_outputs=[torch.ones_like(e_part)])   # response.py:62-68
+            energy = e_part.detach().clone()
+            if plan.world > 1:
+                import torch.distributed as dist
+
+                dist.all_reduce(energy, group=group)
+        return energy, -g.detach()

@@ -260,10 +260,12 @@ def qm9like_batch(batch: int = 1024, cutoff: float = 5.0, seed: int = 0, padded:
 
 
 def periodic_box(n_atoms_total: int = 8192, density: float = 0.1002, cutoff: float = 5.0, seed: int = 0,
-                 min_dist: float = 0.8):
+                 min_dist: float = 0.8, build_list: bool = True):
     """cfg4/cfg5: water-density periodic cubic box, Z pattern O,H,H, jittered-lattice positions.
 
     L = (N/density)^(1/3) (43.4 A at N=8192, 137.9 A at N=262144), ~52 neighbours/atom at rc=5.
+    ``build_list=False`` leaves the neighbour list out (for large boxes the caller builds it on the device with
+    ``schnetpack_b200.neighbors.neighbor_list``; the numpy sweep below needs minutes beyond ~50 k atoms).
     """
     rng = np.random.default_rng(seed)
     n = n_atoms_total
@@ -276,8 +278,11 @@ def periodic_box(n_atoms_total: int = 8192, density: float = 0.1002, cutoff: flo
     amp = max(0.0, (a - min_dist) / 2.0) * 0.98
     pos = (grid[sel] + 0.5) * a + rng.uniform(-amp, amp, (n, 3))
     zs = np.tile(np.array([8, 1, 1], dtype=np.int64), n // 3 + 1)[:n]
-    ii, jj, ss = periodic_cell_list(pos, box, cutoff)
     cellm = np.eye(3) * box
+    if not build_list:
+        return {n_atoms: np.array([n], dtype=np.int64), idx_m: np.zeros(n, dtype=np.int64), Z: zs,
+                R: pos.astype(np.float32), cell: cellm[None].astype(np.float32), pbc: np.ones(3, dtype=bool)}
+    ii, jj, ss = periodic_cell_list(pos, box, cutoff)
     out = {
         n_atoms: np.array([n], dtype=np.int64),
         idx_m: np.zeros(n, dtype=np.int64),
