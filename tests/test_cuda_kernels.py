@@ -549,3 +549,32 @@ def test_bad_neighbor_indices_raise_and_never_gather_out_of_bounds():
     Z = torch.tensor([1, 6, 250, -1], device=DEV)
     out = ops.embedding(torch.randn(100, 32, device=DEV), Z)
     assert not bool(torch.isnan(out[:2]).any()) and bool(torch.isnan(out[2:]).all())
+
+
+@pytest.mark.parametrize("batch", [1, 7, 40])
+def test_atom_chain_matches_per_layer_pipeline(batch):
+    """Persistent per-atom stage (csrc/atom_chain.cu: mixing + next context net, and their reverses, as one launch with
+    tile-level dependency counters) == the launch-per-layer pipeline of the same kernels, for atom counts below one tile
+    (21), with a partial last tile (147) and several tiles (840); energies / forces also against the fp64 oracle.  Repeated
+    calls reuse the self-resetting dependency workspace."""
+    from oracle import spk_oracle as O
+    from schnetpack_b200 import ops
+    from schnetpack_b200 import synthetic as S
+    from schnetpack_b200.model import batch_to_device, from_spec
+
+    spec, data = S.make_config("cfg2", batch=batch)
+    params = S.init_params(spec, seed=17)
+    model = from_spec(spec, params, DEV)
+    old = ops.CHAIN_IMPL
+    try:
+        ops.CHAIN_IMPL = False
+        ref = model(batch_to_device(data, DEV))
+        ops.CHAIN_IMPL = True
+        for _ in range(3):
+            out = model(batch_to_device(data, DEV))
+        torch.cuda.synchronize()
+    finally:
+        ops.CHAIN_IMPL = old
+    assert rel(out["energy"], ref["energy"]) < 2e-6 and rel(out["forces"], ref["forces"]) < 2e-6
+    o = O.energy_forces(spec, params, data, dtype=torch.float64)
+    assert rel(out["energy"].cpu(), o["energy"]) < 1e-5 and rel(out["forces"].cpu(), o["forces"]) < 1e-5
