@@ -64,6 +64,15 @@ int spk_graph_build(const int64_t* idx_i, const int64_t* idx_j, int64_t n_atoms,
                     int32_t* slot_j, int32_t* slot_eid, int32_t* sptr, int32_t* pos_slot, int32_t* pos_i,
                     int32_t* status, void* workspace, size_t workspace_bytes, spk_stream_t stream);
 
+/* The same views over the ACTIVE edges only: an edge is kept iff |r_ij[e]| < cutoff, i.e. iff the cosine cutoff does not
+ * zero its message (nn/cutoff.py:30-32) -- padded neighbour lists (slots at distance >= cutoff) then cost nothing in the
+ * edge kernels.  rowptr[n_atoms] (device) is the number of kept edges; slot arrays are filled for [0, rowptr[n_atoms]) and
+ * slot_eid still points into the caller's full edge arrays.  r_ij [E,3] fp32. */
+int spk_graph_build_active(const int64_t* idx_i, const int64_t* idx_j, const float* r_ij, float cutoff, int64_t n_atoms,
+                           int64_t n_edges, int32_t* rowptr, int32_t* slot_j, int32_t* slot_eid, int32_t* sptr,
+                           int32_t* pos_slot, int32_t* pos_i, int32_t* status, void* workspace, size_t workspace_bytes,
+                           spk_stream_t stream);
+
 /* mol_ptr[B+1] from the sorted system index idx_m (atomistic/atomwise.py:79-81 uses idx_m with index_add). */
 int spk_segment_ptr(const int64_t* idx_m, int64_t n_atoms, int64_t n_mol, int32_t* mol_ptr, spk_stream_t stream);
 
@@ -78,10 +87,12 @@ int spk_pairwise_fwd(const float* R, const int64_t* idx_i, const int64_t* idx_j,
 int spk_pairwise_bwd(const float* g_rij, const int32_t* rowptr, const int32_t* slot_eid, const int32_t* sptr,
                      const int32_t* pos_slot, int64_t n_atoms, float sign, float* g_R, spk_stream_t stream);
 /* per CSR slot s (edge slot_eid[s]): phi[s,0:n_rbf] radial basis (zero padded to KP), dphi = d phi/dd,
- * geo[s] = (ux, uy, uz, d, fc, dfc/dd, 1/d, 0).  rbf_p0/p1 = offsets/widths (gaussian) or freqs/NULL (bessel). */
+ * geo[s] = (ux, uy, uz, d, fc, dfc/dd, 1/d, 0).  rbf_p0/p1 = offsets/widths (gaussian) or freqs/NULL (bessel).
+ * n_active (nullable, device): number of slots that exist (rowptr[n_atoms] of spk_graph_build_active); slots past it are
+ * left untouched. */
 int spk_edge_geometry(const float* r_ij, const int32_t* slot_eid, int64_t n_edges, int rbf_kind, int n_rbf,
-                      const float* rbf_p0, const float* rbf_p1, float cutoff, float* phi, float* dphi, float* geo,
-                      spk_stream_t stream);
+                      const float* rbf_p0, const float* rbf_p1, float cutoff, const int32_t* n_active, float* phi,
+                      float* dphi, float* geo, spk_stream_t stream);
 /* standalone radial basis / cutoff / activation (nn.GaussianRBF, nn.BesselRBF, nn.CosineCutoff, shifted_softplus
  * forward + derivative, used by the nn.* module mirrors).  d: [n]; out: [n, n_rbf]; dout nullable */
 int spk_rbf_fwd(const float* d, int64_t n, int rbf_kind, int n_rbf, const float* rbf_p0, const float* rbf_p1,
@@ -229,6 +240,18 @@ int spk_atom_chain(const spk_chain_step_t* steps /* host array */, int n_steps, 
  * the filter-network output per CSR slot. */
 int spk_cfconv_fwd(const float* h, const float* w_raw, const float* geo, const int32_t* rowptr, const int32_t* slot_j,
                    int64_t n_atoms, int64_t n_edges, int F, float* m, spk_stream_t stream);
+/* The whole interaction-block forward edge pipeline fused, filter network on tcgen05 (csrc/schnet_tc.cu):
+ *   m[i] = sum_{s in row i} h[j_s] * ( W1 act(W0 phi_s + b0) + b1 ) * fc_s          schnet.py:61-67
+ * filter_packed = spk_schnet_pack_filter(filter_network.0.{weight,bias}, filter_network.1.weight) (hi|lo operand tiles,
+ * spk_schnet_filter_packed_floats() floats); b1 = filter_network.1.bias; act = SPK_ACT_SSP | SPK_ACT_SILU | SPK_ACT_NONE.
+ * rowptr may come from spk_graph_build_active (rowptr[n_atoms] slots exist; n_edges is only the capacity of the arrays).
+ * F == n_filters == 128 and n_rbf <= 31, otherwise SPK_ERR_UNSUPPORTED (the caller runs the materialised pipeline). */
+size_t spk_schnet_filter_packed_floats(void);
+int spk_schnet_pack_filter(const float* w0, const float* b0, const float* w1, int F, int n_rbf, float* packed,
+                           spk_stream_t stream);
+int spk_schnet_cfconv_fwd_tc(const float* h, const float* phi, const float* geo, const int32_t* rowptr,
+                             const int32_t* slot_j, const float* filter_packed, const float* b1, int act, int64_t n_atoms,
+                             int64_t n_edges, int F, int n_rbf, float* m, spk_stream_t stream);
 /* reverse grouped by sender: g_h[j] = sum W fc g_m[i];  g_wraw[s] = h[j] g_m[i] fc_s;
  * g_fc[s] = sum_c h[j,c] g_m[i,c] Wraw[s,c] */
 int spk_cfconv_bwd(const float* h, const float* w_raw, const float* geo, const float* g_m, const int32_t* sptr,

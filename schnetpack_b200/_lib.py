@@ -38,10 +38,11 @@ SIGNATURES = {
     "spk_version": [],
     "spk_graph_workspace_bytes": [c_int64, c_int64],
     "spk_graph_build": [P, P, c_int64, c_int64, P, P, P, P, P, P, P, P, c_size_t, P],
+    "spk_graph_build_active": [P, P, P, c_float, c_int64, c_int64, P, P, P, P, P, P, P, P, c_size_t, P],
     "spk_segment_ptr": [P, c_int64, c_int64, P, P],
     "spk_pairwise_fwd": [P, P, P, P, c_int64, c_int64, P, P],
     "spk_pairwise_bwd": [P, P, P, P, P, c_int64, c_float, P, P],
-    "spk_edge_geometry": [P, P, c_int64, c_int, c_int, P, P, c_float, P, P, P, P],
+    "spk_edge_geometry": [P, P, c_int64, c_int, c_int, P, P, c_float, P, P, P, P, P],
     "spk_rbf_fwd": [P, c_int64, c_int, c_int, P, P, P, P, P],
     "spk_cosine_cutoff_fwd": [P, c_int64, c_float, P, P, P],
     "spk_act_fwd": [P, c_int64, c_int, P, P, P],
@@ -67,6 +68,9 @@ SIGNATURES = {
     "spk_painn_mix_update_bwd": [P, P, P, P, c_int64, c_int, P, P, P],
     "spk_painn_mix_ctx_bwd": [P, P, P, c_int64, c_int, c_float, P, P, P],
     "spk_cfconv_fwd": [P, P, P, P, P, c_int64, c_int64, c_int, P, P],
+    "spk_schnet_filter_packed_floats": [],
+    "spk_schnet_pack_filter": [P, P, P, c_int, c_int, P, P],
+    "spk_schnet_cfconv_fwd_tc": [P, P, P, P, P, P, P, c_int, c_int64, c_int64, c_int, c_int, P, P],
     "spk_cfconv_bwd": [P, P, P, P, P, P, P, c_int64, c_int64, c_int, P, P, P, P],
     "spk_radial_bwd": [P, P, P, P, P, c_int64, c_int, P, c_int, P],
     "spk_atomwise_out": [P, P, P, P, c_int64, c_int64, c_int, P, P, P],
@@ -77,6 +81,7 @@ SIGNATURES = {
 }
 _RESTYPE = {"spk_graph_workspace_bytes": c_size_t, "spk_tc_packed_floats": c_size_t,
             "spk_tc_packed_floats_tn": c_size_t, "spk_atom_chain_workspace_ints": c_size_t,
+            "spk_schnet_filter_packed_floats": c_size_t,
             "spk_painn_filter_packed_floats": c_size_t, "spk_neighbor_list_workspace_bytes": c_size_t}
 
 _lib = None
@@ -116,7 +121,7 @@ def check(rc: int, name: str):
 
 
 # kernels launched per C-ABI call (default 1); bench.py reports the running total as ``gpu_launches``
-LAUNCHES = {"spk_graph_build": 8, "spk_atomwise_out": 2, "spk_neighbor_list": 6}
+LAUNCHES = {"spk_graph_build": 8, "spk_graph_build_active": 8, "spk_atomwise_out": 2, "spk_neighbor_list": 6}
 launch_count = 0
 
 

@@ -76,12 +76,14 @@ __global__ void k_pairwise_bwd(const float* __restrict__ g, const int* __restric
 // one thread per slot computes the geometry record, then KP threads-worth of radial values are produced by a loop
 __global__ void k_edge_geometry(const float* __restrict__ r_ij, const int* __restrict__ slot_eid, int64_t n_edges,
                                 int kind, int n_rbf, int KP, const float* __restrict__ p0, const float* __restrict__ p1,
-                                float rc, float* __restrict__ phi, float* __restrict__ dphi, float* __restrict__ geo) {
+                                float rc, const int* __restrict__ n_active, float* __restrict__ phi, float* __restrict__ dphi,
+                                float* __restrict__ geo) {
     SPK_PDL_ENTER();
     // thread (s, k): k in [0, KP)
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= n_edges * KP) return;
     int64_t s = t / KP;
+    if (n_active && s >= *n_active) return;      // CSR built from the active edges only: slots past its end do not exist
     int k = (int)(t - s * KP);
     int64_t e = slot_eid ? (int64_t)slot_eid[s] : s;
     float x = r_ij[e * 3 + 0], y = r_ij[e * 3 + 1], z = r_ij[e * 3 + 2];
@@ -198,8 +200,8 @@ extern "C" int spk_pairwise_bwd(const float* g_rij, const int32_t* rowptr, const
 }
 
 extern "C" int spk_edge_geometry(const float* r_ij, const int32_t* slot_eid, int64_t n_edges, int rbf_kind, int n_rbf,
-                                 const float* rbf_p0, const float* rbf_p1, float cutoff, float* phi, float* dphi,
-                                 float* geo, spk_stream_t stream) {
+                                 const float* rbf_p0, const float* rbf_p1, float cutoff, const int32_t* n_active,
+                                 float* phi, float* dphi, float* geo, spk_stream_t stream) {
     if (n_edges < 0 || n_rbf <= 0) return SPK_ERR_ARG;
     if (n_rbf > 32) return SPK_ERR_UNSUPPORTED;
     if (rbf_kind != SPK_RBF_GAUSSIAN && rbf_kind != SPK_RBF_BESSEL) return SPK_ERR_ARG;
@@ -208,7 +210,7 @@ extern "C" int spk_edge_geometry(const float* r_ij, const int32_t* slot_eid, int
     if (rbf_kind == SPK_RBF_GAUSSIAN && !rbf_p1) return SPK_ERR_ARG;
     int KP = spk_kp(n_rbf);
     spk_launch(k_edge_geometry, GRID1D(n_edges * KP, 256), r_ij, slot_eid, n_edges, rbf_kind, n_rbf, KP, rbf_p0, rbf_p1,
-                                                   cutoff, phi, dphi, geo);
+                                                   cutoff, n_active, phi, dphi, geo);
     SPK_LAUNCH_CHECK();
     return SPK_OK;
 }

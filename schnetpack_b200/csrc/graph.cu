@@ -5,16 +5,28 @@
 
 namespace {
 
-__global__ void k_init_status(int* __restrict__ status) {
+// sorted_hint = 0 forces the general (cursor + stable rank) fill: used when edges are filtered, because the identity
+// mapping slot == edge position of the sorted fast path no longer holds
+__global__ void k_init_status(int* __restrict__ status, int sorted_hint) {
     SPK_PDL_ENTER();
-    if (threadIdx.x < 4) status[threadIdx.x] = (threadIdx.x == 0) ? 1 : 0;
+    if (threadIdx.x < 4) status[threadIdx.x] = (threadIdx.x == 0) ? sorted_hint : 0;
+}
+
+// edge filter of spk_graph_build_active: keep the edges the cosine cutoff does not zero (nn/cutoff.py:30-32: d < rc), with
+// the distance expression of k_edge_geometry
+__device__ __forceinline__ bool edge_kept(const float* __restrict__ r_ij, int64_t e, float rc) {
+    if (!r_ij) return true;
+    const float x = r_ij[e * 3 + 0], y = r_ij[e * 3 + 1], z = r_ij[e * 3 + 2];
+    return sqrtf(x * x + y * y + z * z) < rc;
 }
 
 __global__ void k_count(const int64_t* __restrict__ idx_i, const int64_t* __restrict__ idx_j, int64_t n_atoms,
-                        int64_t n_edges, int* __restrict__ deg_i, int* __restrict__ deg_j, int* __restrict__ status) {
+                        int64_t n_edges, const float* __restrict__ r_ij, float rc, int* __restrict__ deg_i,
+                        int* __restrict__ deg_j, int* __restrict__ status) {
     SPK_PDL_ENTER();
     int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (e >= n_edges) return;
+    if (!edge_kept(r_ij, e, rc)) return;
     int64_t i = idx_i[e], j = idx_j[e];
     if (i < 0 || i >= n_atoms || j < 0 || j >= n_atoms) {
         atomicAdd(&status[1], 1);
@@ -71,12 +83,14 @@ __global__ void __launch_bounds__(1024) k_scan2(const int* __restrict__ deg_a, i
 
 // CSR fill.  Sorted input: identity.  Otherwise atomic cursors into tmp (ordered later by k_rank_rows).
 __global__ void k_fill_csr(const int64_t* __restrict__ idx_i, const int64_t* __restrict__ idx_j, int64_t n_edges,
-                           const int* __restrict__ rowptr, int* __restrict__ cursor, const int* __restrict__ status,
-                           int* __restrict__ slot_j, int* __restrict__ slot_eid, int* __restrict__ tmp_eid) {
+                           const float* __restrict__ r_ij, float rc, const int* __restrict__ rowptr,
+                           int* __restrict__ cursor, const int* __restrict__ status, int* __restrict__ slot_j,
+                           int* __restrict__ slot_eid, int* __restrict__ tmp_eid) {
     SPK_PDL_ENTER();
     int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (e >= n_edges) return;
     if (status[1] != 0) return;
+    if (!edge_kept(r_ij, e, rc)) return;
     if (status[0] != 0) {
         slot_j[e] = (int)idx_j[e];
         slot_eid[e] = (int)e;
@@ -110,12 +124,14 @@ __global__ void k_rank_rows(const int* __restrict__ ptr, int n_rows, const int* 
     }
 }
 
-__global__ void k_fill_csc(const int* __restrict__ slot_j, int64_t n_edges, const int* __restrict__ sptr,
-                           int* __restrict__ cursor, const int* __restrict__ status, int* __restrict__ tmp_slot) {
+__global__ void k_fill_csc(const int* __restrict__ slot_j, int64_t n_edges, int n_atoms, const int* __restrict__ rowptr,
+                           const int* __restrict__ sptr, int* __restrict__ cursor, const int* __restrict__ status,
+                           int* __restrict__ tmp_slot) {
     SPK_PDL_ENTER();
     int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (s >= n_edges) return;
     if (status[1] != 0) return;
+    if (s >= rowptr[n_atoms]) return;            // filtered build: only the first rowptr[N] slots exist
     int j = slot_j[s];
     int p = sptr[j] + atomicAdd(&cursor[j], 1);
     tmp_slot[p] = (int)s;
@@ -156,10 +172,10 @@ extern "C" size_t spk_graph_workspace_bytes(int64_t n_atoms, int64_t n_edges) {
     return sizeof(int) * (4 * n + 2 * e) + 256;
 }
 
-extern "C" int spk_graph_build(const int64_t* idx_i, const int64_t* idx_j, int64_t n_atoms, int64_t n_edges,
-                               int32_t* rowptr, int32_t* slot_j, int32_t* slot_eid, int32_t* sptr, int32_t* pos_slot,
-                               int32_t* pos_i, int32_t* status, void* workspace, size_t workspace_bytes,
-                               spk_stream_t stream) {
+static int graph_build_impl(const int64_t* idx_i, const int64_t* idx_j, const float* r_ij, float cutoff, int64_t n_atoms,
+                            int64_t n_edges, int32_t* rowptr, int32_t* slot_j, int32_t* slot_eid, int32_t* sptr,
+                            int32_t* pos_slot, int32_t* pos_i, int32_t* status, void* workspace, size_t workspace_bytes,
+                            spk_stream_t stream) {
     if (n_atoms < 0 || n_edges < 0 || n_atoms >= (1ll << 31) - 1 || n_edges >= (1ll << 31) - 1) return SPK_ERR_ARG;
     if (!rowptr || !sptr || !status || !workspace) return SPK_ERR_ARG;
     if (workspace_bytes < spk_graph_workspace_bytes(n_atoms, n_edges)) return SPK_ERR_ARG;
@@ -177,22 +193,41 @@ extern "C" int spk_graph_build(const int64_t* idx_i, const int64_t* idx_j, int64
     if (err != cudaSuccess) return SPK_CUDA_ERR(err);
     const int T = 256;
     int n_int = (int)n_atoms;
-    spk_launch(k_init_status, 1, 32, 0, st, status);
+    spk_launch(k_init_status, 1, 32, 0, st, status, r_ij ? 0 : 1);
     if (n_edges > 0) {
-        spk_launch(k_count, (unsigned)spk_cdiv(n_edges, T), T, 0, st, idx_i, idx_j, n_atoms, n_edges, deg_i, deg_j, status);
+        spk_launch(k_count, (unsigned)spk_cdiv(n_edges, T), T, 0, st, idx_i, idx_j, n_atoms, n_edges, r_ij, cutoff, deg_i,
+                   deg_j, status);
     }
     spk_launch(k_scan2, 2, 1024, 0, st, deg_i, rowptr, deg_j, sptr, n_int, status);
     if (n_edges > 0) {
         unsigned ge = (unsigned)spk_cdiv(n_edges, T);
         unsigned gw = (unsigned)spk_cdiv(n_atoms * 32, T);
-        spk_launch(k_fill_csr, ge, T, 0, st, idx_i, idx_j, n_edges, rowptr, cur_i, status, slot_j, slot_eid, tmp_a);
+        spk_launch(k_fill_csr, ge, T, 0, st, idx_i, idx_j, n_edges, r_ij, cutoff, rowptr, cur_i, status, slot_j, slot_eid,
+                   tmp_a);
         spk_launch(k_rank_rows, gw, T, 0, st, rowptr, n_int, tmp_a, idx_j, nullptr, 0, status, slot_eid, slot_j);
-        spk_launch(k_fill_csc, ge, T, 0, st, slot_j, n_edges, sptr, cur_j, status, tmp_a);
+        spk_launch(k_fill_csc, ge, T, 0, st, slot_j, n_edges, n_int, rowptr, sptr, cur_j, status, tmp_a);
         spk_launch(k_rank_rows, gw, T, 0, st, sptr, n_int, tmp_a, idx_i, slot_eid, 1, status, pos_slot, pos_i);
         spk_launch(k_guard, (unsigned)(n_atoms / 256 + 1 < 64 ? n_atoms / 256 + 1 : 64), 256, 0, st, rowptr, sptr, n_int, status);
     }
     SPK_LAUNCH_CHECK();
     return SPK_OK;
+}
+
+extern "C" int spk_graph_build(const int64_t* idx_i, const int64_t* idx_j, int64_t n_atoms, int64_t n_edges,
+                               int32_t* rowptr, int32_t* slot_j, int32_t* slot_eid, int32_t* sptr, int32_t* pos_slot,
+                               int32_t* pos_i, int32_t* status, void* workspace, size_t workspace_bytes,
+                               spk_stream_t stream) {
+    return graph_build_impl(idx_i, idx_j, nullptr, 0.f, n_atoms, n_edges, rowptr, slot_j, slot_eid, sptr, pos_slot, pos_i,
+                            status, workspace, workspace_bytes, stream);
+}
+
+extern "C" int spk_graph_build_active(const int64_t* idx_i, const int64_t* idx_j, const float* r_ij, float cutoff,
+                                      int64_t n_atoms, int64_t n_edges, int32_t* rowptr, int32_t* slot_j,
+                                      int32_t* slot_eid, int32_t* sptr, int32_t* pos_slot, int32_t* pos_i, int32_t* status,
+                                      void* workspace, size_t workspace_bytes, spk_stream_t stream) {
+    if (n_edges > 0 && !r_ij) return SPK_ERR_ARG;
+    return graph_build_impl(idx_i, idx_j, r_ij, cutoff, n_atoms, n_edges, rowptr, slot_j, slot_eid, sptr, pos_slot, pos_i,
+                            status, workspace, workspace_bytes, stream);
 }
 
 extern "C" int spk_segment_ptr(const int64_t* idx_m, int64_t n_atoms, int64_t n_mol, int32_t* mol_ptr,

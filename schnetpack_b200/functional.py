@@ -427,8 +427,51 @@ class SchNetPack(ParamPack):
             o0, o1 = it.f2out[0], it.f2out[1]
             self.blocks.append(dict(
                 in2f=ops.Lin(it.in2f.weight), f0=ops.Lin(f0.weight, f0.bias), f1=ops.Lin(f1.weight, f1.bias),
-                o0=ops.Lin(o0.weight, o0.bias), o1=ops.Lin(o1.weight, o1.bias),
+                o0=ops.Lin(o0.weight, o0.bias), o1=ops.Lin(o1.weight, o1.bias), fpk=None,
             ))
+
+
+def _schnet_filter_packed(b, n_rbf: int):
+    if b["fpk"] is None:      # tensor-core operand tiles of the block's filter network, built on first use
+        b["fpk"] = ops.schnet_pack_filter(b["f0"].w, b["f0"].b, b["f1"].w, n_rbf)
+    return b["fpk"]
+
+
+def schnet_forward_fused(pk: SchNetPack, x0: Tensor, r_ij: Tensor, idx_i: Tensor, idx_j: Tensor, rbf_kind: int, n_rbf: int,
+                         rbf_p0, rbf_p1, cutoff: float, act: int) -> Tensor:
+    """Inference forward (no tape) with ONE fused edge kernel per interaction block (filter network on tcgen05 inside it,
+    csrc/schnet_tc.cu) over the ACTIVE edges only (d < cutoff: padding slots of a padded neighbour list are dropped when the
+    receiver CSR is built), and the per-atom layers f2out + residual + the next block's in2f as one persistent launch
+    (csrc/atom_chain.cu).  schnet.py:56-70,160-171."""
+    F, N, dev = pk.F, x0.shape[0], x0.device
+    graph = ops.EdgeGraph(idx_i, idx_j, N, r_ij=r_ij, cutoff=cutoff)
+    phi, _, geo = ops.edge_geometry(r_ij, graph, rbf_kind, n_rbf, rbf_p0, rbf_p1, cutoff, False, active_only=True)
+    f32 = dict(dtype=torch.float32, device=dev)
+    use_chain = ops.CHAIN_IMPL and all(b[k].w_pk is not None for b in pk.blocks for k in ("in2f", "o0", "o1"))
+    x = x0
+    h = pk.blocks[0]["in2f"].fwd(x)                                                          # schnet.py:60
+    for t in range(pk.T):
+        b = pk.blocks[t]
+        m = ops.schnet_cfconv_fwd_tc(h, phi, geo, graph, _schnet_filter_packed(b, n_rbf), b["f1"].b, act, n_rbf)   # :61-67
+        if use_chain:
+            v0 = torch.empty((N, F), **f32)
+            x_new = torch.empty((N, F), **f32)
+            steps = [ops.chain_gemm(m, b["o0"].fwd_wide(), F, pk.NF, v0, bias=b["o0"].b, act=act),      # :69
+                     ops.chain_gemm(v0, b["o1"].fwd_wide(), F, F, x_new, bias=b["o1"].b, addend=x)]     # :69 + :168
+            if t + 1 < pk.T:
+                h_next = torch.empty((N, pk.NF), **f32)
+                steps.append(ops.chain_gemm(x_new, pk.blocks[t + 1]["in2f"].fwd_wide(), pk.NF, F, h_next))
+            ops.atom_chain(steps, N, dev)
+            keep = (m, v0, x)   # noqa: F841
+            x = x_new
+            if t + 1 < pk.T:
+                h = h_next
+        else:
+            v0 = b["o0"].fwd(m, act)
+            x = b["o1"].fwd(v0, addend=x)
+            if t + 1 < pk.T:
+                h = pk.blocks[t + 1]["in2f"].fwd(x)
+    return x
 
 
 def schnet_forward(pk: SchNetPack, x0: Tensor, r_ij: Tensor, graph: ops.EdgeGraph, rbf_kind: int, n_rbf: int,
@@ -482,8 +525,13 @@ class SchNetFunction(torch.autograd.Function):
         pk = mod._pack()
         need = r_ij.requires_grad
         with ops.device_of(r_ij, x0):
-            x, saved = schnet_forward(pk, x0, r_ij.detach(), graph, mod._rbf_kind, mod._n_rbf, mod._rbf_p0, mod._rbf_p1,
-                                      mod._cutoff_value, mod._act, need)
+            if graph is None:
+                x = schnet_forward_fused(pk, x0, r_ij.detach(), holder["idx_i"], holder["idx_j"], mod._rbf_kind, mod._n_rbf,
+                                         mod._rbf_p0, mod._rbf_p1, mod._cutoff_value, mod._act)
+                saved = None
+            else:
+                x, saved = schnet_forward(pk, x0, r_ij.detach(), graph, mod._rbf_kind, mod._n_rbf, mod._rbf_p0,
+                                          mod._rbf_p1, mod._cutoff_value, mod._act, need)
         ctx.holder = dict(pk=pk, saved=saved, graph=graph, n_rbf=mod._n_rbf, act=mod._act, E=r_ij.shape[0])
         return x
 

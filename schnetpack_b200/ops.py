@@ -76,7 +76,10 @@ class EdgeGraph:
     __slots__ = ("n_atoms", "n_edges", "rowptr", "slot_j", "slot_eid", "sptr", "pos_slot", "pos_i", "status",
                  "_ref_i", "_ref_j", "_ver", "__weakref__")
 
-    def __init__(self, idx_i: Tensor, idx_j: Tensor, n_atoms: int):
+    def __init__(self, idx_i: Tensor, idx_j: Tensor, n_atoms: int, r_ij: Optional[Tensor] = None,
+                 cutoff: Optional[float] = None):
+        """With ``r_ij`` / ``cutoff`` the views cover the ACTIVE edges only (|r_ij| < cutoff, spk_graph_build_active):
+        ``rowptr[-1]`` on the device is their number, ``n_edges`` stays the capacity of the slot arrays."""
         i64(idx_i, "_idx_i")
         i64(idx_j, "_idx_j")
         if idx_i.shape != idx_j.shape or idx_i.dim() != 1:
@@ -94,9 +97,14 @@ class EdgeGraph:
         self.status = torch.empty(4, **i32)
         nbytes = _lib.lib().spk_graph_workspace_bytes(n_atoms, E)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        _lib.call("spk_graph_build", _p(idx_i), _p(idx_j), n_atoms, E, _p(self.rowptr), _p(self.slot_j),
-                  _p(self.slot_eid), _p(self.sptr), _p(self.pos_slot), _p(self.pos_i), _p(self.status), _p(ws),
-                  nbytes, _stream())
+        if r_ij is None:
+            _lib.call("spk_graph_build", _p(idx_i), _p(idx_j), n_atoms, E, _p(self.rowptr), _p(self.slot_j),
+                      _p(self.slot_eid), _p(self.sptr), _p(self.pos_slot), _p(self.pos_i), _p(self.status), _p(ws),
+                      nbytes, _stream())
+        else:
+            _lib.call("spk_graph_build_active", _p(idx_i), _p(idx_j), _p(f32(r_ij, "_Rij")), float(cutoff), n_atoms, E,
+                      _p(self.rowptr), _p(self.slot_j), _p(self.slot_eid), _p(self.sptr), _p(self.pos_slot),
+                      _p(self.pos_i), _p(self.status), _p(ws), nbytes, _stream())
         self._ref_i = weakref.ref(idx_i)
         self._ref_j = weakref.ref(idx_j)
         self._ver = (idx_i._version, idx_j._version)
@@ -163,7 +171,9 @@ def pairwise_bwd(g_rij: Tensor, graph: EdgeGraph, sign: float = 1.0) -> Tensor:
 
 
 def edge_geometry(r_ij: Tensor, graph: Optional[EdgeGraph], rbf_kind: int, n_rbf: int, p0: Tensor, p1: Optional[Tensor],
-                  cutoff: float, need_grad: bool = True):
+                  cutoff: float, need_grad: bool = True, active_only: bool = False):
+    """``active_only``: ``graph`` was built from the active edges (EdgeGraph(..., r_ij, cutoff)); only its
+    ``rowptr[-1]`` slots are filled."""
     f32(r_ij, "_Rij")
     E = r_ij.shape[0]
     KP = kp(n_rbf)
@@ -172,8 +182,8 @@ def edge_geometry(r_ij: Tensor, graph: Optional[EdgeGraph], rbf_kind: int, n_rbf
     dphi = torch.empty((E, KP), dtype=torch.float32, device=dev) if need_grad else None
     geo = torch.empty((E, GEO_STRIDE), dtype=torch.float32, device=dev)
     _lib.call("spk_edge_geometry", _p(r_ij), _p(graph.slot_eid) if graph is not None else None, E, rbf_kind, n_rbf,
-              _p(f32(p0)), _p(f32(p1)) if p1 is not None else None, float(cutoff), _p(phi), _p(dphi), _p(geo),
-              _stream())
+              _p(f32(p0)), _p(f32(p1)) if p1 is not None else None, float(cutoff),
+              _p(graph.rowptr[graph.n_atoms:]) if active_only else None, _p(phi), _p(dphi), _p(geo), _stream())
     return phi, dphi, geo
 
 
@@ -509,6 +519,30 @@ def cfconv_fwd(h, w_raw, geo, graph: EdgeGraph, F: int):
     m = torch.empty((N, F), dtype=torch.float32, device=h.device)
     _lib.call("spk_cfconv_fwd", _p(h), _p(w_raw), _p(geo), _p(graph.rowptr), _p(graph.slot_j), N, graph.n_edges, F,
               _p(m), _stream())
+    return m
+
+
+# fused forward block (csrc/schnet_tc.cu): filter network on tcgen05 inside the edge kernel; F == n_filters == 128, n_rbf <= 31.
+# SPK_B200_CFCONV=mat restores the materialised-filter pipeline (two dense kernels over [E, .] + spk_cfconv_fwd).
+CFCONV_IMPL = os.environ.get("SPK_B200_CFCONV", "tc")
+CFCONV_TC_MIN_EDGES = 2048
+
+
+def cfconv_tc_ok(F: int, n_filters: int, n_rbf: int, n_edges: int) -> bool:
+    return CFCONV_IMPL == "tc" and F == 128 and n_filters == 128 and n_rbf <= 31 and n_edges >= CFCONV_TC_MIN_EDGES
+
+
+def schnet_pack_filter(w0: Tensor, b0: Tensor, w1: Tensor, n_rbf: int) -> Tensor:
+    out = torch.empty(_lib.lib().spk_schnet_filter_packed_floats(), dtype=torch.float32, device=w0.device)
+    _lib.call("spk_schnet_pack_filter", _p(f32(w0)), _p(f32(b0)), _p(f32(w1)), w1.shape[0], n_rbf, _p(out), _stream())
+    return out
+
+
+def schnet_cfconv_fwd_tc(h, phi, geo, graph: EdgeGraph, filter_packed, b1, act: int, n_rbf: int):
+    N, F = graph.n_atoms, h.shape[1]
+    m = torch.empty((N, F), dtype=torch.float32, device=h.device)
+    _lib.call("spk_schnet_cfconv_fwd_tc", _p(f32(h)), _p(phi), _p(geo), _p(graph.rowptr), _p(graph.slot_j),
+              _p(filter_packed), _p(b1), act, N, graph.n_edges, F, n_rbf, _p(m), _stream())
     return m
 
 

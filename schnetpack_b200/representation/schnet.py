@@ -114,7 +114,10 @@ class SchNet(nn.Module):
         if not isinstance(self.radial_basis, (snn.GaussianRBF, snn.BesselRBF)) or not isinstance(
                 self.cutoff_fn, snn.CosineCutoff):
             raise NotImplementedError("fused SchNet kernels support GaussianRBF/BesselRBF x CosineCutoff")
-        graph = ops.get_graph(idx_i, idx_j, n_atoms)
+        # inference on the fused forward kernels builds its own receiver view over the ACTIVE edges (d < cutoff) from r_ij
+        fused = (not (r_ij.requires_grad and torch.is_grad_enabled())
+                 and ops.cfconv_tc_ok(self.n_atom_basis, self.n_filters, self.radial_basis.n_rbf, r_ij.shape[0]))
+        graph = None if fused else ops.get_graph(idx_i, idx_j, n_atoms)
         if isinstance(self.embedding, nn.Embedding) and len(self.electronic_embeddings) == 0:
             x0 = ops.embedding(self.embedding.weight.detach().contiguous(), atomic_numbers)   # schnet.py:161
         else:
@@ -123,6 +126,6 @@ class SchNet(nn.Module):
                 x0 = x0 + embedding(x0, inputs)
             x0 = x0.detach().contiguous()
         x = K.SchNetFunction.apply(r_ij if r_ij.is_contiguous() else r_ij.contiguous(), x0,
-                                   dict(module=self, graph=graph))
+                                   dict(module=self, graph=graph, idx_i=idx_i, idx_j=idx_j))
         inputs["scalar_representation"] = x
         return inputs

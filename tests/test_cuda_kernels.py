@@ -578,3 +578,50 @@ def test_atom_chain_matches_per_layer_pipeline(batch):
     assert rel(out["energy"], ref["energy"]) < 2e-6 and rel(out["forces"], ref["forces"]) < 2e-6
     o = O.energy_forces(spec, params, data, dtype=torch.float64)
     assert rel(out["energy"].cpu(), o["energy"]) < 1e-5 and rel(out["forces"].cpu(), o["forces"]) < 1e-5
+
+
+@pytest.mark.parametrize("case", ["qm9", "qm9_padded", "box", "bessel18"])
+def test_schnet_fused_forward_block_vs_fp64(case):
+    """csrc/schnet_tc.cu (filter network on tcgen05 inside the edge kernel, CSR over the active edges only) against a torch
+    fp64 restatement of schnet.py:56-67 for one block, incl. a padded neighbour list (padding slots at d == cutoff are
+    dropped by spk_graph_build_active), a periodic box, and n_rbf % 4 != 0 with the Bessel basis."""
+    from schnetpack_b200 import ops
+    from schnetpack_b200 import synthetic as S
+
+    torch.manual_seed(9)
+    F, rc = 128, 5.0
+    n_rbf = 18 if case == "bessel18" else 20
+    if case == "box":
+        b = S.periodic_box(500, seed=4)
+    else:
+        b = S.qm9like_batch(48, seed=5, padded=(case == "qm9_padded"))
+    ti, tj = torch.as_tensor(b["_idx_i"], device=DEV), torch.as_tensor(b["_idx_j"], device=DEV)
+    N = b["_atomic_numbers"].shape[0]
+    if "_Rij" in b:
+        r = torch.as_tensor(b["_Rij"], device=DEV)
+    else:
+        R = torch.as_tensor(b["_positions"], device=DEV)
+        r = (R[tj] - R[ti] + torch.as_tensor(b["_offsets"], device=DEV)).contiguous()
+    if case == "bessel18":
+        kind, p0, p1 = ops.RBF_BESSEL, (torch.arange(1, n_rbf + 1, device=DEV) * math.pi / rc).float(), None
+    else:
+        kind, p0 = ops.RBF_GAUSSIAN, torch.linspace(0, rc, n_rbf, device=DEV)
+        p1 = torch.full((n_rbf,), float(p0[1] - p0[0]), device=DEV)
+    g = ops.EdgeGraph(ti, tj, N, r_ij=r, cutoff=rc)
+    d64 = r.double().norm(dim=1)
+    n_act = int(g.rowptr[-1])
+    assert n_act == int((r.norm(dim=1) < rc).sum()) and (case != "qm9_padded" or n_act < ti.shape[0])
+    phi, _, geo = ops.edge_geometry(r, g, kind, n_rbf, p0, p1, rc, False, active_only=True)
+    w0, b0 = torch.randn(F, n_rbf, device=DEV) * 0.3, torch.randn(F, device=DEV) * 0.3
+    w1, b1 = torch.randn(F, F, device=DEV) * 0.1, torch.randn(F, device=DEV) * 0.1
+    h = torch.randn(N, F, device=DEV)
+    m = ops.schnet_cfconv_fwd_tc(h, phi, geo, g, ops.schnet_pack_filter(w0, b0, w1, n_rbf), b1, ops.ACT_SSP, n_rbf)
+    if kind == ops.RBF_GAUSSIAN:
+        f = torch.exp(-0.5 / p1.double() ** 2 * (d64[:, None] - p0.double()) ** 2)
+    else:
+        f = torch.sin(d64[:, None] * p0.double()) / d64[:, None]
+    fc = 0.5 * (torch.cos(d64 * math.pi / rc) + 1) * (d64 < rc)
+    hid = torch.nn.functional.softplus(f @ w0.double().t() + b0.double()) - math.log(2.0)
+    W = (hid @ w1.double().t() + b1.double()) * fc[:, None]
+    ref = torch.zeros(N, F, device=DEV, dtype=torch.float64).index_add(0, ti, h.double()[tj] * W)
+    assert rel(m, ref) < 3e-6, rel(m, ref)
