@@ -23,6 +23,10 @@ class PairwiseDistances(nn.Module):
     receiver- and sender-grouped edge views (deterministic; the reference uses index_put atomics)."""
 
     def forward(self, inputs: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        if self.training and torch.is_grad_enabled():     # training graph: differentiable twice (functional_torch)
+            from .. import functional_torch as T
+
+            return T.pairwise(inputs)
         R = inputs[properties.R]
         offsets = inputs[properties.offsets]
         idx_i = inputs[properties.idx_i].long()
@@ -70,10 +74,12 @@ class Atomwise(nn.Module):
         return self._pk
 
     def forward(self, inputs: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        if snn.use_training_path(self):           # training: differentiable ATen path (functional_torch), SURVEY 8 f3
+            from .. import functional_torch as T
+
+            return T.atomwise(self, inputs)
         if self.n_out != 1 or len(self.outnet) != 2:
             raise NotImplementedError("schnetpack_b200.Atomwise: fused head covers n_out=1, n_layers=2")
-        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("schnetpack_b200.Atomwise: training is not implemented; call model.eval()")
         q = inputs["scalar_representation"]
         idx_m, n_mol = None, 0
         if self.aggregation_mode is not None:

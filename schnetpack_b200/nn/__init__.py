@@ -18,17 +18,15 @@ from torch.nn.init import xavier_uniform_, zeros_
 from .. import ops
 
 __all__ = ["GaussianRBF", "BesselRBF", "CosineCutoff", "cosine_cutoff", "gaussian_rbf", "Dense", "shifted_softplus",
-           "scatter_add", "build_mlp", "replicate_module", "activation_code"]
+           "scatter_add", "build_mlp", "replicate_module", "activation_code", "use_training_path"]
 
 
-def refuse_training(module: nn.Module):
-    """The CUDA path provides first-order input gradients (forces, stress); weight gradients and double backward
-    (``create_graph`` force training) are not implemented.  Instead of returning wrong or missing
-    gradients silently, a module in training mode with trainable parameters under grad mode raises."""
-    if module.training and torch.is_grad_enabled() and any(p.requires_grad for p in module.parameters()):
-        raise NotImplementedError(
-            f"schnetpack_b200.{type(module).__name__}: weight gradients / double backward (training) are not implemented "
-            "in the CUDA path (SURVEY.md section 8 f3); call model.eval() for inference, forces and MD")
+def use_training_path(module: nn.Module) -> bool:
+    """True when ``module`` must take the differentiable ATen path of ``functional_torch`` instead of the kernels: it is in
+    ``train()`` mode, grad mode is on and it has trainable parameters.  The CUDA path provides first-order input gradients
+    (forces, stress) only; weight gradients and the double backward of force training (``create_graph``, SURVEY.md section 8
+    f3) come from that path -- never silently from the kernels."""
+    return module.training and torch.is_grad_enabled() and any(p.requires_grad for p in module.parameters())
 
 
 # ------------------------------------------------------------------------------------------------- activations
@@ -212,7 +210,10 @@ class Dense(nn.Linear):
             self.bias_init(self.bias)
 
     def forward(self, input: torch.Tensor):
-        refuse_training(self)
+        if use_training_path(self):               # training: differentiable ATen path (functional_torch)
+            from .. import functional_torch as T
+
+            return T.dense(input, self, T._activation(self.activation))
         return _DenseFn.apply(input, self.weight, self.bias, activation_code(self.activation))
 
 

@@ -75,8 +75,10 @@ class PaiNNMixing(nn.Module):
 
     def forward(self, q, mu):
         """painn.py:92-117.  q [N,1,F], mu [N,3,F] -> (q, mu)."""
-        snn.refuse_training(self)
         F_ = self.n_atom_basis
+        if snn.use_training_path(self):
+            raise NotImplementedError("PaiNNMixing called on its own in training mode: train through PaiNN.forward "
+                                      "(functional_torch) or call .eval()")
         q2, mu2 = K.PaiNNMixingFunction.apply(q.reshape(-1, F_), mu, self._pack(), F_, float(self.epsilon),
                                               snn.activation_code(self.activation))
         return q2.view(q.shape), mu2
@@ -160,7 +162,10 @@ class PaiNN(nn.Module):
         idx_i = inputs[properties.idx_i]
         idx_j = inputs[properties.idx_j]
         n_atoms = atomic_numbers.shape[0]
-        snn.refuse_training(self)
+        if snn.use_training_path(self):           # training (weight gradients, double backward): ATen path, SURVEY 8 f3
+            from .. import functional_torch as T
+
+            return T.painn(self, inputs)
         if not isinstance(self.radial_basis, (snn.GaussianRBF, snn.BesselRBF)) or not isinstance(
                 self.cutoff_fn, snn.CosineCutoff):
             raise NotImplementedError("fused PaiNN kernels support GaussianRBF/BesselRBF x CosineCutoff")

@@ -110,7 +110,10 @@ class SchNet(nn.Module):
         idx_i = inputs[properties.idx_i]
         idx_j = inputs[properties.idx_j]
         n_atoms = atomic_numbers.shape[0]
-        snn.refuse_training(self)
+        if snn.use_training_path(self):           # training (weight gradients, double backward): ATen path, SURVEY 8 f3
+            from .. import functional_torch as T
+
+            return T.schnet(self, inputs)
         if not isinstance(self.radial_basis, (snn.GaussianRBF, snn.BesselRBF)) or not isinstance(
                 self.cutoff_fn, snn.CosineCutoff):
             raise NotImplementedError("fused SchNet kernels support GaussianRBF/BesselRBF x CosineCutoff")

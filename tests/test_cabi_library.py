@@ -62,7 +62,10 @@ def test_no_cpu_fallback():
         model(x)
 
 
-def test_training_mode_refused():
+def test_training_mode_is_the_only_way_onto_the_aten_path():
+    """train() mode with trainable weights evaluates the differentiable ATen formulas (functional_torch, row f3 --
+    tests/test_training_path.py pins it to the reference's weight gradients); the moment the model is in eval() mode, or no
+    parameter is trainable, or grad mode is off, the kernels are the only path and CPU tensors raise."""
     import torch
 
     from schnetpack_b200 import synthetic as S
@@ -70,10 +73,20 @@ def test_training_mode_refused():
 
     spec, inputs = S.make_config("cfg1")
     model = from_spec(spec, S.init_params(spec, 0))
+    x = lambda: {k: (torch.as_tensor(v).float() if v.dtype.kind == "f" else torch.as_tensor(v)) for k, v in inputs.items()}  # noqa: E731
     model.train()
-    x = {k: torch.as_tensor(v) for k, v in inputs.items()}
-    with pytest.raises((NotImplementedError, RuntimeError)):
-        model(x)
+    out = model(x())
+    assert out["forces"].requires_grad                   # create_graph=self.training: differentiable forces
+    with torch.no_grad():
+        with pytest.raises(RuntimeError):                # grad mode off (and no forces possible): kernels only
+            model.representation(dict(x(), _Rij=torch.zeros((inputs["_idx_i"].shape[0], 3))))
+    for p in model.parameters():
+        p.requires_grad_(False)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        model(x())
+    model.eval()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        model(x())
 
 
 def test_product_does_not_import_oracle():

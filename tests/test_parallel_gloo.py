@@ -100,7 +100,7 @@ def test_bench_reference_arm_prints_one_json_line():
               "e2e"):
         assert k in d, k
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1    # "reference" when oracle/_ref or /root/reference is present
 
 
 # ------------------------------------------------------------------------------------ one large system over several ranks
