@@ -294,6 +294,14 @@ int spk_neighbor_list(const float* R, const float* cell, const uint8_t* pbc, con
                       float* offsets, int32_t* shifts, int64_t* n_pairs, void* workspace, size_t workspace_bytes,
                       spk_stream_t stream);
 
+/* ---- "next" row f2: velocity-Verlet update of the device-resident MD state (md/integrators.py:59-70,97-110;
+ * unit handling of md/calculators/base_calculator.py:96,120-152).  momenta [N,3] += 1/2 dt * forces * force_conversion; with
+ * drift != 0 also positions [N,3] += dt * momenta / masses [N] and, if given, model_positions = positions *
+ * position_conversion (the array the next force evaluation reads).  All in place, enqueue-only. */
+int spk_md_velocity_verlet(float* momenta, float* positions, float* model_positions, const float* forces,
+                           const float* masses, int64_t n_atoms, float dt, float force_conversion,
+                           float position_conversion, int drift, spk_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -175,6 +175,26 @@ __global__ void k_add(const float* __restrict__ a, const float* __restrict__ b, 
     out[t] = b ? a[t] + b[t] : a[t];
 }
 
+// velocity Verlet (md/integrators.py:59-70 half_step, :97-110 main_step) on the device-resident state: one thread per
+// (atom, component).  forces arrive in MODEL units and are converted on the fly (md/calculators/base_calculator.py:96,
+// force_conversion = energy_conversion / position_conversion); model_positions = positions * position_conversion is what the
+// next force evaluation reads (base_calculator.py:_get_system_molecules).
+__global__ void k_velocity_verlet(float* __restrict__ momenta, float* __restrict__ positions,
+                                  float* __restrict__ model_positions, const float* __restrict__ forces,
+                                  const float* __restrict__ masses, int64_t n_atoms, float dt, float f_conv, float p_conv,
+                                  int drift) {
+    SPK_PDL_ENTER();
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n_atoms * 3) return;
+    const float p = fmaf(0.5f * dt, forces[t] * f_conv, momenta[t]);                 // p += 1/2 F dt
+    momenta[t] = p;
+    if (drift) {
+        const float x = positions[t] + dt * p / masses[t / 3];                       // q += p / m dt
+        positions[t] = x;
+        if (model_positions) model_positions[t] = x * p_conv;
+    }
+}
+
 }  // namespace
 
 #define GRID1D(n, T) (unsigned)spk_cdiv((n), (T)), (T), 0, spk_st(stream)
@@ -270,6 +290,18 @@ extern "C" int spk_add(const float* a, const float* b, int64_t n, float* out, sp
     if (n == 0) return SPK_OK;
     if (!a || !out) return SPK_ERR_ARG;
     spk_launch(k_add, GRID1D(n, 256), a, b, n, out);
+    SPK_LAUNCH_CHECK();
+    return SPK_OK;
+}
+
+extern "C" int spk_md_velocity_verlet(float* momenta, float* positions, float* model_positions, const float* forces,
+                                      const float* masses, int64_t n_atoms, float dt, float force_conversion,
+                                      float position_conversion, int drift, spk_stream_t stream) {
+    if (n_atoms < 0) return SPK_ERR_ARG;
+    if (n_atoms == 0) return SPK_OK;
+    if (!momenta || !forces || (drift && (!positions || !masses))) return SPK_ERR_ARG;
+    spk_launch(k_velocity_verlet, GRID1D(n_atoms * 3, 256), momenta, positions, model_positions, forces, masses, n_atoms, dt,
+               force_conversion, position_conversion, drift);
     SPK_LAUNCH_CHECK();
     return SPK_OK;
 }

@@ -9,8 +9,14 @@ velocity-Verlet integrator of md/integrators.py:59-70,97-110) with NOTHING leavi
     replayed; the host only counts steps.  ``n_pairs`` (true pair count, overflow flag) stays on the device for the caller
     to poll when it wants to.
 
-Units are the caller's: forces = -dE/dR in the model's energy / length units, ``masses`` and ``time_step`` consistent with
-them (the reference converts to its internal MD units in md/system.py; that bookkeeping is outside the hot path).
+Units follow the reference's calculator (md/calculators/base_calculator.py:85-98,120-152): the MD state (positions, momenta,
+masses, time step) lives in the caller's MD units; ``position_conversion`` turns MD positions into the model's length unit
+before every evaluation and ``energy_conversion`` turns the model's energies into MD energy units, so forces are scaled by
+``energy_conversion / position_conversion``.  Both default to 1 (MD units == model units).  The integrator is the
+velocity-Verlet of md/integrators.py:59-70,97-110 as one kernel per half step (``spk_md_velocity_verlet``).  No Verlet skin
+is kept (md/neighborlist_md.py:55-98 rebuilds when an atom moved more than skin / 2): rebuilding the exact-cutoff list on the
+device every step costs less than the bookkeeping (0.22 ms at 8192 atoms) and gives the same forces, since the model's
+cutoff function removes every pair beyond the cutoff either way.
 """
 from __future__ import annotations
 
@@ -18,7 +24,7 @@ from typing import Dict, Optional
 
 import torch
 
-from . import ops
+from . import _lib, ops
 from . import properties as P
 from .neighbors import CellListNeighborList
 
@@ -29,15 +35,22 @@ Tensor = torch.Tensor
 
 class DeviceMD:
     def __init__(self, model: torch.nn.Module, batch: Dict[str, Tensor], masses: Tensor, time_step: float, cutoff: float,
-                 capacity: int, momenta: Optional[Tensor] = None, use_graph: bool = True):
+                 capacity: int, momenta: Optional[Tensor] = None, use_graph: bool = True,
+                 position_conversion: float = 1.0, energy_conversion: float = 1.0):
+        """``batch[_positions]`` (and ``_cell``) are in MODEL units as everywhere in this package; ``self.positions`` is the
+        MD-unit state (= model positions / position_conversion)."""
         dev = batch[P.R].device
         if dev.type != "cuda":
             raise ValueError("DeviceMD needs a CUDA batch (no CPU fallback)")
         self.model = model
         self.dt = float(time_step)
+        self.p_conv = float(position_conversion)
+        self.e_conv = float(energy_conversion)
+        self.f_conv = self.e_conv / self.p_conv                                   # base_calculator.py:96
         self.static = {k: v.detach().clone() for k, v in batch.items() if k not in (P.idx_i, P.idx_j, P.offsets)}
-        self.positions = self.static[P.R]
-        self.masses = masses.to(dev, torch.float32).reshape(-1, 1).clone()
+        self.model_positions = self.static[P.R]                                   # what the model reads
+        self.positions = self.model_positions if self.p_conv == 1.0 else self.model_positions / self.p_conv
+        self.masses = masses.to(dev, torch.float32).reshape(-1).contiguous().clone()
         self.momenta = torch.zeros_like(self.positions) if momenta is None else momenta.to(dev, torch.float32).clone()
         self.nl = CellListNeighborList(cutoff, capacity=int(capacity), pad=True)
         self.use_graph = use_graph
@@ -66,16 +79,24 @@ class DeviceMD:
             self.n_pairs.copy_(x["_n_pairs"])
         torch.maximum(self.nl_watch, x["_n_pairs"], out=self.nl_watch)
 
+    def _verlet(self, drift: bool):
+        n = self.positions.shape[0]
+        mp = self.model_positions if self.model_positions is not self.positions else None
+        _lib.call("spk_md_velocity_verlet", ops._p(self.momenta), ops._p(self.positions), ops._p(mp), ops._p(self.forces),
+                  ops._p(self.masses), n, self.dt, self.f_conv, self.p_conv, 1 if drift else 0, ops._stream())
+
     def _step(self):
-        self.momenta.add_(self.forces, alpha=0.5 * self.dt)                  # integrators.py:70   half_step
-        self.positions.addcdiv_(self.momenta, self.masses, value=self.dt)    # integrators.py:108  main_step
-        self._calculate()                                                    # simulator.py:137
-        self.momenta.add_(self.forces, alpha=0.5 * self.dt)                  # simulator.py:144    half_step
+        self._verlet(True)        # integrators.py:70 half_step + :108 main_step (momenta, then positions with the new momenta)
+        self._calculate()         # simulator.py:137
+        self._verlet(False)       # simulator.py:144 half_step
 
     def _capture(self):
         dev = self.positions.device
         # capture works on copies of the state so that warm-up iterations do not advance the trajectory
-        saved = (self.positions.clone(), self.momenta.clone(), self.forces.clone(), self.energy.clone())
+        state = [self.positions, self.momenta, self.forces, self.energy]
+        if self.model_positions is not self.positions:
+            state.append(self.model_positions)
+        saved = [t.clone() for t in state]
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
@@ -84,7 +105,7 @@ class DeviceMD:
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             self._step()
-        for dst, src in zip((self.positions, self.momenta, self.forces, self.energy), saved):
+        for dst, src in zip(state, saved):
             dst.copy_(src)
         self._graph = graph
 
@@ -112,4 +133,8 @@ class DeviceMD:
                 f"{peak}); the trajectory is invalid from that step on -- re-create DeviceMD with a larger capacity")
 
     def kinetic_energy(self) -> Tensor:
-        return 0.5 * (self.momenta ** 2 / self.masses).sum()
+        return 0.5 * (self.momenta ** 2 / self.masses[:, None]).sum()
+
+    def potential_energy(self) -> Tensor:
+        """model energy in MD units (base_calculator.py: property_conversion of the energy key)"""
+        return self.energy * self.e_conv
