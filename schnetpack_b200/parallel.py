@@ -345,8 +345,13 @@ class PartitionedPotential:
             for t in range(pk.T):
                 b = pk.blocks[t]
                 x = K.PaiNNContextFunction.apply(q, b, act)                       # painn.py:54 on the owned atoms
-                x_loc = torch.cat([x, _halo(x, plan, group)], dim=0)              # senders' rows incl. ghosts
-                mu_loc = torch.cat([mu, _halo(mu, plan, group)], dim=0) if mu is not None else None
+                if mu is None:                                                    # first block: mu == 0 everywhere
+                    x_loc = torch.cat([x, _halo(x, plan, group)], dim=0)          # senders' rows incl. ghosts
+                    mu_loc = None
+                else:                                                             # ONE exchange of the 6F-float rows (x | mu)
+                    gh = _halo(torch.cat([x, mu.reshape(n_o, 3 * F)], dim=1), plan, group)
+                    x_loc = torch.cat([x, gh[:, :3 * F]], dim=0)
+                    mu_loc = torch.cat([mu, gh[:, 3 * F:].reshape(n_g, 3, F)], dim=0)
                 q_loc = torch.cat([q, ghost_q], dim=0)                            # ghost rows receive nothing
                 q1, mu1 = K.PaiNNEdgeFunction.apply(x_loc, mu_loc, q_loc, r_ij, geom, pk, t)     # :55-65
                 q, mu = K.PaiNNMixingFunction.apply(q1[:n_o], mu1[:n_o], b, F, pk.eps, act)      # :103-116
