@@ -294,6 +294,18 @@ int spk_neighbor_list(const float* R, const float* cell, const uint8_t* pbc, con
                       float* offsets, int32_t* shifts, int64_t* n_pairs, void* workspace, size_t workspace_bytes,
                       spk_stream_t stream);
 
+/* ---- row e: halo exchange of ghost-atom rows over NVLink peer memory (csrc/halo.cu).  peer_base[world] (device array) holds
+ * every rank's symmetric buffer address as mapped into THIS process (CUDA IPC / torch symmetric memory); the caller has
+ * enqueued a cross-rank barrier after the owners wrote their rows.
+ *   spk_halo_pull      ghost[k, :] = peer[ghost_rank[k]][ghost_row[k], :]          rows of row_floats floats
+ *   spk_halo_pull_add  g_rows[rows[k], :] += sum_{e in [entry_ptr[k], entry_ptr[k+1])} peer[entry_rank[e]][entry_pos[e], :]
+ *                      (entries of a row in ascending peer order: deterministic reverse halo, no atomics) */
+int spk_halo_pull(float* ghost, const uint64_t* peer_base, const int32_t* ghost_rank, const int32_t* ghost_row,
+                  int64_t n_ghost, int row_floats, spk_stream_t stream);
+int spk_halo_pull_add(float* g_rows, const uint64_t* peer_base, const int32_t* rows, const int32_t* entry_ptr,
+                      const int32_t* entry_rank, const int32_t* entry_pos, int64_t n_listed, int row_floats,
+                      spk_stream_t stream);
+
 /* ---- "next" row f2: velocity-Verlet update of the device-resident MD state (md/integrators.py:59-70,97-110;
  * unit handling of md/calculators/base_calculator.py:96,120-152).  momenta [N,3] += 1/2 dt * forces * force_conversion; with
  * drift != 0 also positions [N,3] += dt * momenta / masses [N] and, if given, model_positions = positions *

@@ -76,6 +76,8 @@ SIGNATURES = {
     "spk_atomwise_out": [P, P, P, P, c_int64, c_int64, c_int, P, P, P],
     "spk_atomwise_out_bwd": [P, P, P, c_int64, c_int, P, P],
     "spk_add": [P, P, c_int64, P, P],
+    "spk_halo_pull": [P, P, P, P, c_int64, c_int, P],
+    "spk_halo_pull_add": [P, P, P, P, P, P, c_int64, c_int, P],
     "spk_md_velocity_verlet": [P, P, P, P, P, c_int64, c_float, c_float, c_float, c_int, P],
     "spk_neighbor_list_workspace_bytes": [c_int64, c_int64],
     "spk_neighbor_list": [P, P, P, P, c_int64, c_int64, c_float, c_int64, c_int, P, P, P, P, P, P, c_size_t, P],

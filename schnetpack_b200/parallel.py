@@ -8,7 +8,8 @@ A single large periodic system does not shard this way (it needs spatial bricks 
 """
 from __future__ import annotations
 
-from typing import Dict, List, Tuple
+import os
+from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 import torch
@@ -108,10 +109,14 @@ class RankPlan:
     recv[p]    (start, stop) slice of this rank's ghost block filled by peer p
     """
 
-    def __init__(self, rank, world, owned, ghosts, edge_ids, idx_i, idx_j, send, recv):
+    def __init__(self, rank, world, owned, ghosts, edge_ids, idx_i, idx_j, send, recv, ghost_rank=None, ghost_row=None,
+                 send_pos=None):
         self.rank, self.world = rank, world
         self.owned, self.ghosts, self.edge_ids, self.idx_i, self.idx_j = owned, ghosts, edge_ids, idx_i, idx_j
         self.send, self.recv = send, recv
+        # for the peer-memory halo: owner rank of every ghost and its row index in the owner's local table; and, per peer
+        # p, where in p's ghost block the rows of send[p] start
+        self.ghost_rank, self.ghost_row, self.send_pos = ghost_rank, ghost_row, (send_pos or {})
         self._dev_send = {}
 
     def to_device(self, device):
@@ -167,7 +172,11 @@ def partition_graph(owner: np.ndarray, idx_i: np.ndarray, idx_j: np.ndarray, ran
     local = np.full(n, -1, dtype=np.int64)
     local[owned] = np.arange(owned.shape[0])
     local[ghosts] = owned.shape[0] + np.arange(ghosts.shape[0])
-    recv, send = {}, {}
+    row_on_owner = np.empty(n, dtype=np.int64)         # index of every atom in its OWNER's local table (owned ids ascending)
+    for p in range(world):
+        sel = np.nonzero(owner == p)[0]
+        row_on_owner[sel] = np.arange(sel.shape[0])
+    recv, send, send_pos = {}, {}, {}
     for p in range(world):
         if p == rank:
             continue
@@ -180,7 +189,10 @@ def partition_graph(owner: np.ndarray, idx_i: np.ndarray, idx_j: np.ndarray, ran
         mine = gp[owner[gp] == rank]
         if mine.size:
             send[p] = local[mine]
-    return RankPlan(rank, world, owned, ghosts, edge_ids, local[idx_i[edge_ids]], local[idx_j[edge_ids]], send, recv)
+            send_pos[p] = int(np.count_nonzero(owner[gp] < rank))      # p's ghost block is ordered by owner rank
+    return RankPlan(rank, world, owned, ghosts, edge_ids, local[idx_i[edge_ids]], local[idx_j[edge_ids]], send, recv,
+                    ghost_rank=owner[ghosts].astype(np.int32), ghost_row=row_on_owner[ghosts].astype(np.int32),
+                    send_pos=send_pos)
 
 
 class HaloExchange(torch.autograd.Function):
@@ -261,10 +273,114 @@ class HaloExchange(torch.autograd.Function):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+# Halo over NVLink peer memory (csrc/halo.cu): every rank READS the rows of its ghosts out of their owners' buffers -- the
+# gather that a send-side pack would do, the transfer and the unpack are one hand-written kernel; NCCL is not involved.
+# The buffers are torch symmetric memory (CUDA IPC mappings of every rank's allocation into every process); the only
+# synchronisation is its device-side barrier between "owners have written" and "peers pull".
+# ----------------------------------------------------------------------------------------------------------------------
+class PeerHalo:
+    """State of the peer-memory halo for one ``RankPlan``: two generations of a symmetric buffer (so that one barrier per
+    exchange suffices: a buffer is rewritten only after the NEXT exchange's barrier, which every peer reaches after its
+    pull from this one), the peer address tables and the index lists of the two kernels."""
+
+    def __init__(self, plan: RankPlan, device, max_row_floats: int, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+
+        self.plan, self.device, self.group = plan, torch.device(device), group if group is not None else dist.group.WORLD
+        cap = torch.tensor([max(plan.n_owned, plan.n_ghost, 1)], dtype=torch.int64, device=device)
+        dist.all_reduce(cap, op=dist.ReduceOp.MAX, group=group)
+        self.cap_rows, self.row_floats = int(cap.item()), int(max_row_floats)
+        self.bufs, self.hdls, self.ptrs = [], [], []
+        for _ in range(2):
+            b = symm.empty(self.cap_rows * self.row_floats, dtype=torch.float32, device=self.device)
+            h = symm.rendezvous(b, self.group)
+            self.bufs.append(b)
+            self.hdls.append(h)
+            self.ptrs.append(torch.tensor([int(v) for v in h.buffer_ptrs], dtype=torch.int64, device=self.device))
+        self.gen = 0
+        i32 = dict(dtype=torch.int32, device=self.device)
+        self.g_rank = torch.as_tensor(plan.ghost_rank, **i32)
+        self.g_row = torch.as_tensor(plan.ghost_row, **i32)
+        # reverse: entries (owned row, peer, position in the peer's ghost block), grouped by row, peers ascending
+        rows, ranks, pos = [], [], []
+        for p in sorted(plan.send):
+            k = np.arange(len(plan.send[p]), dtype=np.int64)
+            rows.append(np.asarray(plan.send[p], dtype=np.int64))
+            ranks.append(np.full(k.shape[0], p, dtype=np.int64))
+            pos.append(plan.send_pos[p] + k)
+        if rows:
+            rows, ranks, pos = np.concatenate(rows), np.concatenate(ranks), np.concatenate(pos)
+            order = np.lexsort((ranks, rows))
+            rows, ranks, pos = rows[order], ranks[order], pos[order]
+            uniq, start = np.unique(rows, return_index=True)
+            ptr = np.concatenate([start, [rows.shape[0]]])
+        else:
+            uniq, ptr, ranks, pos = (np.zeros(0, dtype=np.int64), np.zeros(1, dtype=np.int64), np.zeros(0, dtype=np.int64),
+                                     np.zeros(0, dtype=np.int64))
+        self.r_rows, self.r_ptr = torch.as_tensor(uniq, **i32), torch.as_tensor(ptr, **i32)
+        self.r_rank, self.r_pos = torch.as_tensor(ranks, **i32), torch.as_tensor(pos, **i32)
+
+    def publish(self, rows2d: torch.Tensor) -> int:
+        """Copy ``rows2d`` [n, C] to the front of the next buffer generation and run the cross-rank barrier; returns the
+        generation to pull from."""
+        n, C = rows2d.shape
+        if C > self.row_floats or n > self.cap_rows:
+            raise ValueError("PeerHalo: rows exceed the symmetric buffer")
+        g = self.gen
+        self.gen ^= 1
+        self.bufs[g][: n * C].copy_(rows2d.reshape(-1))
+        self.hdls[g].barrier()
+        return g
+
+
+class PeerHaloExchange(torch.autograd.Function):
+    """``HaloExchange`` over NVLink peer memory: same contract (owned rows -> ghost rows; backward sums the ghost-row
+    gradients into their owners in ascending peer order), transport = ``spk_halo_pull`` / ``spk_halo_pull_add``."""
+
+    @staticmethod
+    def forward(ctx, rows: torch.Tensor, halo: PeerHalo):
+        from . import _lib, ops
+
+        ctx.halo, ctx.shape = halo, tuple(rows.shape)
+        tail = tuple(rows.shape[1:])
+        C = 1
+        for d in tail:
+            C *= int(d)
+        plan = halo.plan
+        with torch.cuda.device(halo.device):
+            g = halo.publish(rows.detach().reshape(rows.shape[0], C))
+            ghost = torch.empty((plan.n_ghost,) + tail, dtype=torch.float32, device=halo.device)
+            _lib.call("spk_halo_pull", ops._p(ghost), ops._p(halo.ptrs[g]), ops._p(halo.g_rank), ops._p(halo.g_row),
+                      plan.n_ghost, C, ops._stream())
+        return ghost
+
+    @staticmethod
+    def backward(ctx, g_ghost: torch.Tensor):
+        from . import _lib, ops
+
+        halo = ctx.halo
+        tail = ctx.shape[1:]
+        C = 1
+        for d in tail:
+            C *= int(d)
+        with torch.cuda.device(halo.device):
+            g = halo.publish(g_ghost.contiguous().reshape(g_ghost.shape[0], C))
+            g_rows = torch.zeros(ctx.shape, dtype=torch.float32, device=halo.device)
+            _lib.call("spk_halo_pull_add", ops._p(g_rows), ops._p(halo.ptrs[g]), ops._p(halo.r_rows), ops._p(halo.r_ptr),
+                      ops._p(halo.r_rank), ops._p(halo.r_pos), int(halo.r_rows.shape[0]), C, ops._stream())
+        return g_rows, None
+
+
+# ----------------------------------------------------------------------------------------------------------------------
 # The CUDA engine on a partition: per-block kernel pipelines with a halo exchange in front of every edge kernel.
 # ----------------------------------------------------------------------------------------------------------------------
-def _halo(rows: torch.Tensor, plan: RankPlan, group):
-    if plan.world == 1 or (plan.n_ghost == 0 and not plan.send):
+def _halo(rows: torch.Tensor, plan: RankPlan, group, peer: Optional["PeerHalo"] = None):
+    if plan.world == 1:
+        return rows.new_zeros((0,) + tuple(rows.shape[1:]))
+    if peer is not None:
+        return PeerHaloExchange.apply(rows, peer)          # collective (barrier): every rank calls it, ghosts or not
+    if plan.n_ghost == 0 and not plan.send:
         return rows.new_zeros((0,) + tuple(rows.shape[1:]))
     return HaloExchange.apply(rows, plan, group)
 
@@ -319,6 +435,16 @@ class PartitionedPotential:
         plan.to_device(dev)
         with torch.cuda.device(dev):
             self.graph = ops.EdgeGraph(self.idx_i, self.idx_j, self.n_local)
+        # transport of the halo: NVLink peer memory (hand-written pull kernels over torch symmetric memory) when the ranks
+        # talk NCCL on one node, torch.distributed point-to-point otherwise (gloo tests) or with SPK_B200_HALO=nccl
+        self.peer: Optional[PeerHalo] = None
+        self.transport = "none" if plan.world == 1 else "p2p"
+        if plan.world > 1 and os.environ.get("SPK_B200_HALO", "peer") == "peer":
+            import torch.distributed as dist
+
+            if dist.get_backend(group) == "nccl":
+                self.peer = PeerHalo(plan, dev, 6 * int(rep.n_atom_basis), group)
+                self.transport = "peer"
 
     def set_positions(self, R_own: torch.Tensor):
         self.R_own = R_own.to(self.device, torch.float32).contiguous()
@@ -332,7 +458,7 @@ class PartitionedPotential:
             pk = rep._pack()
             F, act = pk.F, rep._act
             R_own = self.R_own.detach().requires_grad_(True)                      # model/base.py:105-111
-            R_loc = torch.cat([R_own, _halo(R_own, plan, group)], dim=0)          # ghost positions (autograd-aware)
+            R_loc = torch.cat([R_own, _halo(R_own, plan, group, self.peer)], dim=0)          # ghost positions (autograd-aware)
             r_ij = K.PairwiseDistancesFunction.apply(R_loc, self.offsets,        # atomistic/distances.py:14-26
                                                      dict(idx_i=self.idx_i, idx_j=self.idx_j, graph=self.graph))
             geom = K.EdgeGeometry(rep, r_ij, self.graph)                          # painn.py:227-230, shared by the blocks
@@ -346,10 +472,10 @@ class PartitionedPotential:
                 b = pk.blocks[t]
                 x = K.PaiNNContextFunction.apply(q, b, act)                       # painn.py:54 on the owned atoms
                 if mu is None:                                                    # first block: mu == 0 everywhere
-                    x_loc = torch.cat([x, _halo(x, plan, group)], dim=0)          # senders' rows incl. ghosts
+                    x_loc = torch.cat([x, _halo(x, plan, group, self.peer)], dim=0)          # senders' rows incl. ghosts
                     mu_loc = None
                 else:                                                             # ONE exchange of the 6F-float rows (x | mu)
-                    gh = _halo(torch.cat([x, mu.reshape(n_o, 3 * F)], dim=1), plan, group)
+                    gh = _halo(torch.cat([x, mu.reshape(n_o, 3 * F)], dim=1), plan, group, self.peer)
                     x_loc = torch.cat([x, gh[:, :3 * F]], dim=0)
                     mu_loc = torch.cat([mu, gh[:, 3 * F:].reshape(n_g, 3, F)], dim=0)
                 q_loc = torch.cat([q, ghost_q], dim=0)                            # ghost rows receive nothing

@@ -97,9 +97,13 @@ def test_two_ranks_one_gpu(tmp_path, world):
 
 
 @pytest.mark.timeout(600)
-def test_ranks_over_nccl(tmp_path):
+@pytest.mark.parametrize("transport", ["peer", "nccl"])
+def test_ranks_over_nccl(tmp_path, transport, monkeypatch):
+    """one process per GPU: halo over NVLink peer memory (default: hand-written pull kernels over symmetric memory) and over
+    NCCL point-to-point (SPK_B200_HALO=nccl)"""
     import torch.multiprocessing as mp
 
+    monkeypatch.setenv("SPK_B200_HALO", transport)
     world = min(torch.cuda.device_count(), 4)
     if world < 2:
         pytest.skip("needs >= 2 GPUs (NCCL cannot put two ranks on one device); covered by the 2-GPU gpurun of tools/gpu_r2_halo.sh")

@@ -179,3 +179,35 @@ def test_one_system_over_several_ranks_with_halo_exchange(tmp_path, world):
     assert int(z["n_ghost"]) > 0
     np.testing.assert_allclose(z["e"], z["e_ref"], rtol=1e-11, atol=1e-11)
     np.testing.assert_allclose(z["f"], z["f_ref"], rtol=1e-9, atol=1e-11)
+
+
+def test_peer_halo_index_lists_address_the_right_rows():
+    """The peer-memory halo (csrc/halo.cu) reads ghost rows out of their owners' tables: ``ghost_rank`` / ``ghost_row`` must
+    address exactly the global rows ``ghosts``, and the reverse lists (``send``, ``send_pos``) must address, in every peer's
+    ghost block, exactly the copies of this rank's rows.  Emulated with numpy over all ranks of 2-, 3- and 5-way partitions."""
+    sys.path.insert(0, ROOT)
+    from schnetpack_b200 import parallel as P
+    from schnetpack_b200 import synthetic as S
+
+    box = S.periodic_box(400, seed=31)
+    n = box["_positions"].shape[0]
+    X = np.random.default_rng(0).normal(size=(n, 5))
+    for world in (2, 3, 5):
+        owner = P.slab_owners(box["_positions"], world)
+        plans = [P.partition_graph(owner, box["_idx_i"], box["_idx_j"], r, world) for r in range(world)]
+        tables = [X[pl.owned] for pl in plans]                                    # every rank's owned rows, local order
+        for r, pl in enumerate(plans):
+            pulled = np.stack([tables[p][row] for p, row in zip(pl.ghost_rank, pl.ghost_row)]) if pl.n_ghost else np.zeros((0, 5))
+            assert np.array_equal(pulled, X[pl.ghosts])                           # forward pull
+            # reverse: the gradient of my owned row = sum over the peers' ghost copies, located by (send[p], send_pos[p])
+            G = [np.random.default_rng(10 + q).normal(size=(plans[q].n_ghost, 5)) for q in range(world)]
+            acc = np.zeros((pl.n_owned, 5))
+            for p in sorted(pl.send):
+                k = np.arange(len(pl.send[p]))
+                assert np.array_equal(plans[p].ghosts[pl.send_pos[p] + k], pl.owned[pl.send[p]])   # same atoms
+                np.add.at(acc, pl.send[p], G[p][pl.send_pos[p] + k])
+            want = np.zeros((n, 5))
+            for q in range(world):
+                if q != r and plans[q].n_ghost:
+                    np.add.at(want, plans[q].ghosts, G[q])
+            assert np.allclose(acc, want[pl.owned])
