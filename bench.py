@@ -569,11 +569,11 @@ def run_cuda(args, rank, world, local_rank):
     }
     if md_info is not None:
         line["md"] = md_info
-    print(json.dumps(line), flush=True)
+    return line
 
 
 # ------------------------------------------------------------------------------------------------- spatial (cfg5) arm
-def run_spatial(args, rank, world, local_rank):
+def run_spatial(args, rank, world, local_rank, steps=None, warmup=None, cpu_leg=True):
     """cfg5: ONE periodic box (default 262144 atoms, PaiNN 128x3, E+F) cut into `world` slabs; every rank owns a slab, holds
     read-only ghost rows of the senders it does not own, and exchanges (x, mu) ghost rows per interaction block over NCCL
     point-to-point (gradients back in the reverse sweep).  STRONG scaling: the box is fixed, `value` = whole-box evaluations
@@ -594,6 +594,8 @@ def run_spatial(args, rank, world, local_rank):
             os.environ["NCCL_DEBUG"] = "WARN"
         if not dist.is_initialized():
             dist.init_process_group("nccl", device_id=dev)
+    steps = steps or args.steps
+    warmup = args.warmup if warmup is None else warmup
     n_total = args.atoms or 262144
     spec = S.model_spec(**S.CONFIGS["cfg5"]["spec"])
     box = S.periodic_box(n_total, build_list=False)
@@ -658,10 +660,33 @@ def run_spatial(args, rank, world, local_rank):
         return r
 
     P.HaloExchange.forward, P.HaloExchange.backward = staticmethod(halo_f), staticmethod(halo_b)
+    orig_peer_f, orig_peer_b = P.PeerHaloExchange.forward, P.PeerHaloExchange.backward
+
+    def peer_f(ctx, rows, halo):
+        if not timing["on"]:
+            return orig_peer_f(ctx, rows, halo)
+        s_, e_ = torch.cuda.Event(True), torch.cuda.Event(True)
+        s_.record()
+        r = orig_peer_f(ctx, rows, halo)
+        e_.record()
+        halo_ev.append((s_, e_))
+        return r
+
+    def peer_b(ctx, g):
+        if not timing["on"]:
+            return orig_peer_b(ctx, g)
+        s_, e_ = torch.cuda.Event(True), torch.cuda.Event(True)
+        s_.record()
+        r = orig_peer_b(ctx, g)
+        e_.record()
+        halo_ev.append((s_, e_))
+        return r
+
+    P.PeerHaloExchange.forward, P.PeerHaloExchange.backward = staticmethod(peer_f), staticmethod(peer_b)
 
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         energy, forces = engine()
     torch.cuda.synchronize()
     if dist is not None:
@@ -670,7 +695,7 @@ def run_spatial(args, rank, world, local_rank):
     c0 = _lib.launch_count
     step_ev = []
     torch.cuda.synchronize()
-    for _ in range(args.steps):
+    for _ in range(steps):
         flush_buf.fill_(1)
         s_, e_ = torch.cuda.Event(True), torch.cuda.Event(True)
         s_.record()
@@ -689,8 +714,8 @@ def run_spatial(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(halo_ms, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
-    ms_per_step = total_ms / args.steps
-    value = args.steps / (total_ms * 1e-3)                      # whole-box evaluations per second (all ranks together)
+    ms_per_step = total_ms / steps
+    value = steps / (total_ms * 1e-3)                      # whole-box evaluations per second (all ranks together)
 
     # ---- end to end: host positions in, energy + owned forces out
     R_host = engine.R_own.detach().cpu().pin_memory()
@@ -710,7 +735,7 @@ def run_spatial(args, rank, world, local_rank):
     if dist is not None:
         dist.barrier()
     e2e_ev = []
-    for _ in range(args.steps):
+    for _ in range(steps):
         flush_buf.fill_(1)
         s_, e_ = torch.cuda.Event(True), torch.cuda.Event(True)
         s_.record()
@@ -722,9 +747,14 @@ def run_spatial(args, rank, world, local_rank):
     if dist is not None:
         dist.barrier()
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-    e2e_value = args.steps / (float(t2.item()) * 1e-3)
+    e2e_value = steps / (float(t2.item()) * 1e-3)
+    ops.painn_edge_fwd, ops.painn_edge_bwd = orig_fwd, orig_bwd
+    P.HaloExchange.forward, P.HaloExchange.backward = staticmethod(orig_halo_f), staticmethod(orig_halo_b)
+    P.PeerHaloExchange.forward, P.PeerHaloExchange.backward = staticmethod(orig_peer_f), staticmethod(orig_peer_b)
+    del engine
+    torch.cuda.empty_cache()
     if rank != 0:
-        return
+        return None
 
     peak, peak_src = measured_peaks()
     roof_all = {}
@@ -753,23 +783,25 @@ def run_spatial(args, rank, world, local_rank):
             except Exception:
                 pass
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and cpu_leg:
         cpu = cpu_baseline_leg(args)
     line = {
-        "metric": METRIC, "value": value, "unit": "box-evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC, "value": value, "unit": "box-evals/s", "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": config_dict(args, world, 1, n_total, E_total, F, T),
         "step": "eager per-block pipeline (context net -> halo exchange -> fused edge kernel -> mixing) + autograd reverse sweep",
-        "edge_msgs_per_s": E_total * T * args.steps / (total_ms * 1e-3),
-        "atoms_per_s": n_total * args.steps / (total_ms * 1e-3),
+        "edge_msgs_per_s": E_total * T * steps / (total_ms * 1e-3),
+        "atoms_per_s": n_total * steps / (total_ms * 1e-3),
         "rank0": {"owned_atoms": plan.n_owned, "ghost_atoms": halo_rows, "local_edges": E_loc},
-        "halo": {"exchanges_per_step": len(halo_ev) // max(args.steps, 1), "ms_per_step_max_over_ranks": float(halo_ms.item()) / args.steps,
+        "halo": {"exchanges_per_step": len(halo_ev) // max(steps, 1), "ms_per_step_max_over_ranks": float(halo_ms.item()) / steps,
                  "share_of_step": float(halo_ms.item()) / total_ms,
                  # forward: positions (3) + x (3F) per block + mu (3F) from the second block on; the reverse sweep sends the
                  # same volume back (gradients of the ghost rows to their owners)
                  "bytes_sent_per_step_rank0": 2 * 4 * int(sum(len(v) for v in plan.send.values())) * (3 + 3 * F * T + 3 * F * (T - 1)),
-                 "transport": "NCCL grouped isend/irecv (torch.distributed.batch_isend_irecv), index-gather pack, receives land in the ghost block"},
+                 "transport": {"peer": "NVLink peer memory: spk_halo_pull / spk_halo_pull_add over torch symmetric memory, one device-side barrier per exchange",
+                               "p2p": "NCCL grouped isend/irecv (torch.distributed.batch_isend_irecv), index-gather pack, receives land in the ghost block",
+                               "none": "single rank"}[engine.transport]},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "box-evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "PartitionedPotential.set_positions(host) -> __call__() -> energy, forces to pinned host"},
@@ -777,7 +809,7 @@ def run_spatial(args, rank, world, local_rank):
         "roofline": roof, "roofline_all": roof_all, "cpu_baseline": cpu,
         "impl_switches": {"dense": ops.DENSE_IMPL, "edge": ops.EDGE_IMPL},
     }
-    print(json.dumps(line), flush=True)
+    return line
 
 
 def main():
@@ -790,6 +822,8 @@ def main():
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--atoms", type=int, default=None, help="cfg5: atoms in the periodic box (default 262144)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-spatial", action="store_true", help="skip the cfg5 strong-scaling leg appended to the default run")
+    ap.add_argument("--spatial-steps", type=int, default=8)
     ap.add_argument("--md", action="store_true", help="also time the device-resident MD step (rows f1+f2); not part of the metric")
     ap.add_argument("--no-graph", action="store_true", help="time eager model(inputs) calls (value and e2e) instead of CUDA-graph replays")
     args = ap.parse_args()
@@ -802,9 +836,20 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
     if args.config == "cfg5":
-        run_spatial(args, rank, world, local_rank)
+        line = run_spatial(args, rank, world, local_rank)
     else:
-        run_cuda(args, rank, world, local_rank)
+        line = run_cuda(args, rank, world, local_rank)
+        if not args.no_spatial:
+            # second leg, same run: STRONG scaling of the one-box workload (cfg5) on the same N GPUs, so that a 1/2/4/8-GPU
+            # sweep of the default command also yields a curve with a real collective (the halo) in the data path
+            try:
+                sp = run_spatial(args, rank, world, local_rank, steps=args.spatial_steps, warmup=3, cpu_leg=False)
+            except Exception as exc:  # pragma: no cover
+                sp = {"error": repr(exc)[:300]}
+            if line is not None:
+                line["spatial"] = sp
+    if line is not None:
+        print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist
 

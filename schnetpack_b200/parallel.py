@@ -292,6 +292,10 @@ class PeerHalo:
         dist.all_reduce(cap, op=dist.ReduceOp.MAX, group=group)
         self.cap_rows, self.row_floats = int(cap.item()), int(max_row_floats)
         self.bufs, self.hdls, self.ptrs = [], [], []
+        try:
+            symm.enable_symm_mem_for_group(self.group.group_name)      # idempotent; newer torch enables it implicitly
+        except Exception:
+            pass
         for _ in range(2):
             b = symm.empty(self.cap_rows * self.row_floats, dtype=torch.float32, device=self.device)
             h = symm.rendezvous(b, self.group)
@@ -443,8 +447,18 @@ class PartitionedPotential:
             import torch.distributed as dist
 
             if dist.get_backend(group) == "nccl":
-                self.peer = PeerHalo(plan, dev, 6 * int(rep.n_atom_basis), group)
-                self.transport = "peer"
+                # every rank must take the same branch: agree on success with an all-reduce
+                ok = torch.ones(1, dtype=torch.int32, device=dev)
+                try:
+                    self.peer = PeerHalo(plan, dev, 6 * int(rep.n_atom_basis), group)
+                except Exception as exc:          # symmetric memory unavailable (no P2P / IPC): NCCL point-to-point
+                    self.peer_error = repr(exc)[:200]
+                    ok.zero_()
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+                if int(ok.item()) == 1:
+                    self.transport = "peer"
+                else:
+                    self.peer = None
 
     def set_positions(self, R_own: torch.Tensor):
         self.R_own = R_own.to(self.device, torch.float32).contiguous()
