@@ -6,12 +6,12 @@
 //
 // Every operation of the stage is ROW-LOCAL: the rows of a 128-atom tile produced by step k are all that step k+1 needs
 // for the same tile.  So the stage is a static list of STEPS (GEMM or elementwise glue, given by the host as plain structs)
-// cut into WORK ITEMS (step, atom tile, sub-tile).  Items are numbered step-major and dealt round-robin to one persistent
-// CTA per SM; item (k, r, *) may start when the counter done[k-1][r] has reached the number of items of step k-1 for tile r
-// (spin on ld.acquire, published with __threadfence + atomicAdd after the item's epilogue).  Because every CTA walks its
-// items in increasing order and an item only waits for lower-numbered ones, the schedule cannot deadlock as long as all
-// CTAs are resident (grid <= #SMs, one CTA per SM).  Data between steps goes through global memory (L2-resident, read with
-// ld.global.cg): what is saved is the launch boundary, not the bytes.
+// cut into WORK ITEMS (step, atom tile, sub-tile).  Items are numbered step-major and CLAIMED in increasing order from a
+// global counter by one persistent CTA per SM; item (k, r, *) may start when the counter done[k-1][r] has reached the number
+// of items of step k-1 for tile r (spin on ld.acquire, published with __threadfence + atomicAdd after the item's
+// epilogue).  An item only waits for lower-numbered ones, and those are held by CTAs that are already running, so the
+// schedule cannot deadlock however many CTAs are co-resident.  Data between steps goes through global memory (L2-resident,
+// read with ld.global.cg): what is saved is the launch boundary, not the bytes.
 //
 // A GEMM item is one 128 x 128 output tile computed by the warp-specialised tcgen05 pipeline of gemm_tc.cu (3xTF32 with
 // split accumulators and per-K-tile draining, see there), kept WARM across items: TMEM is allocated once, the mbarrier
@@ -43,7 +43,7 @@ struct ChainArgs {
     int n_steps;
     int n_tiles;            // ceil(n_atoms / 128)
     int64_t n_atoms;
-    int* ws;                // [n_steps * n_tiles] done counters, then [1] finished-CTA counter
+    int* ws;                // [n_steps * n_tiles] done counters, then [1] finished-CTA counter, [1] next-item counter
 };
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -208,7 +208,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_atom_chain(const __grid_constan
     const int total = base[g.n_steps];
 
     uint32_t ktg = 0;            // K-tiles this CTA has pushed through the pipeline so far (same value in every warp)
-    for (int item = blockIdx.x; item < total; item += gridDim.x) {
+    __shared__ int s_item;
+    int* const next_item = g.ws + g.n_steps * g.n_tiles + 1;
+    for (;;) {
+        // ---- claim the next item (dynamic, in increasing order: the lowest unfinished item is always held by a RESIDENT
+        // CTA, so the dependency spin below cannot deadlock even if fewer CTAs than launched are co-resident) and wait
+        // until every item of the previous step for its atom tile has been published
+        if (tid == 0) {
+            const int it = atomicAdd(next_item, 1);
+            if (it < total) {
+                int sj = 0;
+                while (it >= base[sj + 1]) ++sj;
+                if (sj > 0) {
+                    const int ipt_prev = items_per_tile(g.step[sj - 1]);
+                    const int tile_j = (it - base[sj]) / items_per_tile(g.step[sj]);
+                    const int* flag = g.ws + (sj - 1) * g.n_tiles + tile_j;
+                    while (ld_acquire(flag) < ipt_prev) __nanosleep(20);
+                }
+            }
+            s_item = it;
+        }
+        __syncthreads();
+        const int item = s_item;
+        if (item >= total) break;
         int si = 0;
         while (item >= base[si + 1]) ++si;
         const spk_chain_step_t& st = g.step[si];
@@ -217,14 +239,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_atom_chain(const __grid_constan
         const int tile = local / ipt, sub = local - tile * ipt;
         const int64_t a0 = (int64_t)tile * TM;
         const int64_t a1 = min(a0 + TM, g.n_atoms);
-
-        // ---- dependency: every item of the previous step for this atom tile has been published
-        if (si > 0 && tid == 0) {
-            const int need = items_per_tile(g.step[si - 1]);
-            const int* flag = g.ws + (si - 1) * g.n_tiles + tile;
-            while (ld_acquire(flag) < need) __nanosleep(20);
-        }
-        __syncthreads();
 
         if (st.kind != SPK_CHAIN_GEMM) {
             glue_item(st, a0, a1, tid);
@@ -402,6 +416,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_atom_chain(const __grid_constan
         if (prev == (int)gridDim.x - 1) {
             for (int i = 0; i < g.n_steps * g.n_tiles; ++i) g.ws[i] = 0;
             *fin = 0;
+            *next_item = 0;
             __threadfence();
         }
     }
@@ -414,7 +429,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_atom_chain(const __grid_constan
 }  // namespace
 
 extern "C" size_t spk_atom_chain_workspace_ints(int n_steps, int64_t n_atoms) {
-    return (size_t)n_steps * (size_t)spk_cdiv(n_atoms, TM) + 1;
+    return (size_t)n_steps * (size_t)spk_cdiv(n_atoms, TM) + 2;
 }
 
 extern "C" int spk_atom_chain(const spk_chain_step_t* steps, int n_steps, int64_t n_atoms, int32_t* workspace,
