@@ -360,6 +360,20 @@ def run_cuda(args, rank, world, local_rank):
         return r
 
     ops.painn_edge_fwd, ops.painn_edge_bwd = timed_fwd, timed_bwd
+    cf_ev = []                                   # (start, end, graph) per timed launch of the fused SchNet block kernel
+    orig_cf = ops.schnet_cfconv_fwd_tc
+
+    def timed_cf(h, phi, geo, graph, *a, **k):
+        if not timing["on"]:
+            return orig_cf(h, phi, geo, graph, *a, **k)
+        s, e = torch.cuda.Event(True), torch.cuda.Event(True)
+        s.record()
+        r = orig_cf(h, phi, geo, graph, *a, **k)
+        e.record()
+        cf_ev.append((s, e, graph))
+        return r
+
+    ops.schnet_cfconv_fwd_tc = timed_cf
 
     # ---- device-resident timing -----------------------------------------------------------------------------------
     # One step = one E+F evaluation of the resident batch, graph-view build included.  Default: replay of the captured
@@ -368,7 +382,7 @@ def run_cuda(args, rank, world, local_rank):
     kernel_ms = {"fwd": [], "bwd": []}          # (ms, has_mu) per timed edge-kernel launch
     evaluate(fresh(resident))                   # one-time work (weight packing, kernel attributes) outside the counts
     torch.cuda.synchronize()
-    timing["on"] = spec["kind"] == "painn"
+    timing["on"] = spec["kind"] == "painn" or not use_graph
     if use_graph:
         g_res = GraphedPotential(model)
         c0 = _lib.launch_count
@@ -393,6 +407,7 @@ def run_cuda(args, rank, world, local_rank):
     torch.cuda.synchronize()
     ev["fwd"].clear()
     ev["bwd"].clear()
+    cf_ev.clear()
     if dist is not None:
         dist.barrier()
     launches0 = _lib.launch_count
@@ -509,6 +524,22 @@ def run_cuda(args, rank, world, local_rank):
             except Exception:
                 pass
 
+    if cf_ev:      # fused SchNet block kernel: tensor-pipe bound (2(R F + F^2) = 37.9 kFLOP per edge and layer)
+        d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        tpeak = float(d.get("bf16_tflops", 1750.0))
+        n_act = int(cf_ev[0][2].rowptr[-1])
+        ms_l = [a.elapsed_time(b) for a, b, _ in cf_ev]
+        flops = n_act * 2.0 * (spec.get("n_rbf", 20) * F + F * F)
+        ach = flops * len(ms_l) / (sum(ms_l) * 1e-3) / 1e12
+        roof = {"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak, "traffic": None,
+                "kernel": "k_schnet_cfconv_fwd_tc", "launches_timed": len(ms_l), "avg_us": 1e3 * sum(ms_l) / len(ms_l),
+                "active_edges": n_act, "edge_slots": E, "share_of_step": sum(ms_l) / dev_ms,
+                "peak_source": "MEASURED_PEAKS.json bf16 dense burst" if d else "fallback (B200_PROFILING.md)",
+                "model": "algorithmic fp32 FLOPs of the filter network over the ACTIVE edges (padding slots dropped); the kernel "
+                         "computes in 3xTF32 (3 MMAs per product, TF32 = 1/2 of the bf16 rate): its own ceiling is peak / 6",
+                "timing": "CUDA events around the kernel, inside the timed region"}
+        roof_all = {"cfconv_fwd": roof}
+
     # ---- CPU baseline (bounded sample, rank 0, N=1 only): the reference's own modules when oracle/_ref is present ----------
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -565,8 +596,9 @@ def run_cuda(args, rank, world, local_rank):
         "roofline": roof, "roofline_all": roof_all, "cpu_baseline": cpu, "eager_gpu_baseline": eager,
         "vs_reference_gpu_eager": (value / eager["value"] if eager and "value" in eager else None),
         "e2e_vs_reference_gpu_eager": (e2e_value / eager["value"] if eager and "value" in eager else None),
-        "impl_switches": {"dense": ops.DENSE_IMPL, "edge": ops.EDGE_IMPL},
+        "impl_switches": {"dense": ops.DENSE_IMPL, "edge": ops.EDGE_IMPL, "chain": ops.CHAIN_IMPL, "cfconv": ops.CFCONV_IMPL},
     }
+    ops.painn_edge_fwd, ops.painn_edge_bwd, ops.schnet_cfconv_fwd_tc = orig_fwd, orig_bwd, orig_cf
     if md_info is not None:
         line["md"] = md_info
     return line
