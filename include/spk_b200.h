@@ -230,8 +230,9 @@ typedef struct {
 } spk_chain_step_t;
 size_t spk_tc_packed_floats_tn(int N, int K, int tile_n); /* floats of the tile_n-wide (64 | 128) packing of W [N,K] */
 size_t spk_atom_chain_workspace_ints(int n_steps, int64_t n_atoms);
+#define SPK_CHAIN_FLAG_NFOLD 1 /* 2 MMAs per k-step: [W_hi ; W_lo] as one 256-row operand (see csrc/atom_chain.cu) */
 int spk_atom_chain(const spk_chain_step_t* steps /* host array */, int n_steps, int64_t n_atoms, int32_t* workspace,
-                   size_t workspace_ints, spk_stream_t stream);
+                   size_t workspace_ints, int flags, spk_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * SchNet.  representation/schnet.py:41-70 (SchNetInteraction.forward).

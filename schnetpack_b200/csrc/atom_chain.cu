@@ -26,7 +26,7 @@ namespace {
 
 constexpr int TM = 128, TN = 128, TK = 16;
 constexpr int N_DRAIN = 8, W_MMA = 8, W_PROD0 = 9;
-constexpr int NST = 6, NPROD = 6, NBUF = 3;
+constexpr int NST = 6, NPROD = 6;
 constexpr int OPER_A = TM * TK * 4, OPER_B = TN * TK * 4;
 constexpr int STAGE_BYTES = 2 * OPER_A + 2 * OPER_B;        // A_hi, A_lo, W_hi, W_lo
 constexpr int EP_LD = TN + 4;
@@ -36,7 +36,18 @@ constexpr int TMEM_COLS = 512;                              // main[0..2] | corr
 constexpr int CW = TN / 2;
 static_assert(NST * STAGE_BYTES >= TM * EP_LD * 4, "epilogue staging tile reuses the pipeline stages");
 static_assert(NST % NPROD == 0, "a stage must be owned by exactly one producer warp");
-static_assert((NBUF + 1) * TN <= TMEM_COLS, "accumulators exceed TMEM");
+// Two accumulation schemes for the 3xTF32 products of a K-tile (A = Ah + Al, W = Wh + Wl):
+//   NFOLD = false   3 MMAs per k-step: Ah*Wh -> main[buf] (fresh per K-tile, 3 buffers), Al*Wh and Ah*Wl -> corr (over all K);
+//   NFOLD = true    2 MMAs per k-step: the packed tile [W_hi ; W_lo] is ONE operand of 256 rows, so Ah*[Wh;Wl]^T gives the main
+//                   product and the Ah*Wl terms in one N = 256 instruction (an MMA costs about the same for any N <= 256) and
+//                   Al*Wh accumulates onto the correction columns; [main | corr] = 256 columns per buffer, 2 buffers, both
+//                   halves fresh per K-tile and drained into fp32 registers (round-1 experiment gemm_tc_nfold, now selectable).
+template <bool NFOLD>
+struct Acc {
+    static constexpr int NBUF = NFOLD ? 2 : 3;
+    static constexpr int BUF_COLS = NFOLD ? 2 * TN : TN;
+};
+static_assert(3 * TN + TN <= TMEM_COLS && 2 * 2 * TN <= TMEM_COLS, "accumulators exceed TMEM");
 
 struct ChainArgs {
     spk_chain_step_t step[SPK_CHAIN_MAX_STEPS];
@@ -164,13 +175,15 @@ __device__ void glue_item(const spk_chain_step_t& s, int64_t a0, int64_t a1, int
     }
 }
 
+template <bool NFOLD>
 __global__ void __launch_bounds__(NTHREADS, 1) k_atom_chain(const __grid_constant__ ChainArgs g) {
+    constexpr int NBUF = Acc<NFOLD>::NBUF, BUF_COLS = Acc<NFOLD>::BUF_COLS;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     __shared__ __align__(8) uint64_t full_bar[NST];
     __shared__ __align__(8) uint64_t empty_bar[NST];
-    __shared__ __align__(8) uint64_t acc_full[NBUF];
-    __shared__ __align__(8) uint64_t acc_empty[NBUF];
+    __shared__ __align__(8) uint64_t acc_full[3];
+    __shared__ __align__(8) uint64_t acc_empty[3];
     __shared__ uint32_t s_tmem;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -309,17 +322,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_atom_chain(const __grid_constan
                             if (gk >= NBUF) mbar_wait(&acc_empty[buf], ((gk / NBUF) - 1) & 1);
                             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                             const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-                            const uint32_t d_main = tmem_base + (uint32_t)(buf * TN);
-                            const uint32_t d_corr = tmem_base + (uint32_t)(NBUF * TN);
+                            const uint32_t d_main = tmem_base + (uint32_t)(buf * BUF_COLS);
+                            const uint32_t d_corr = tmem_base + (uint32_t)(NBUF * TN);           // !NFOLD only
+                            const uint32_t idesc_w = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * TN) >> 3) << 17) |
+                                                     ((uint32_t)(TM >> 4) << 24);
 #pragma unroll
                             for (int ks = 0; ks < TK / 8; ++ks) {
                                 const uint64_t ah = make_desc(sa + 32 * ks);
                                 const uint64_t al = make_desc(sa + OPER_A + 32 * ks);
-                                const uint64_t bh = make_desc(sa + 2 * OPER_A + 32 * ks);
-                                const uint64_t bl = make_desc(sa + 2 * OPER_A + OPER_B + 32 * ks);
-                                umma_tf32(d_corr, al, bh, idesc, (kt | ks) ? 1u : 0u);   // small terms: over all of K
-                                umma_tf32(d_corr, ah, bl, idesc, 1u);
-                                umma_tf32(d_main, ah, bh, idesc, ks ? 1u : 0u);          // fresh accumulator per K-tile
+                                const uint64_t bh = make_desc(sa + 2 * OPER_A + 32 * ks);        // W_hi tile; W_lo follows it
+                                if (NFOLD) {
+                                    umma_tf32(d_main, ah, bh, idesc_w, ks ? 1u : 0u);            // [Ah Wh | Ah Wl], fresh per K-tile
+                                    umma_tf32(d_main + (uint32_t)TN, al, bh, idesc, 1u);         // Al Wh onto the correction half
+                                } else {
+                                    const uint64_t bl = make_desc(sa + 2 * OPER_A + OPER_B + 32 * ks);
+                                    umma_tf32(d_corr, al, bh, idesc, (kt | ks) ? 1u : 0u);       // small terms: over all of K
+                                    umma_tf32(d_corr, ah, bl, idesc, 1u);
+                                    umma_tf32(d_main, ah, bh, idesc, ks ? 1u : 0u);              // fresh accumulator per K-tile
+                                }
                             }
                             umma_commit(&empty_bar[s]);
                             umma_commit(&acc_full[buf]);
@@ -341,7 +361,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_atom_chain(const __grid_constan
 #pragma unroll
                         for (int c0 = 0; c0 < CW; c0 += 32) {
                             uint32_t r[32];
-                            tmem_ld32(lane_addr + (uint32_t)(buf * TN + c0), r);
+                            if (NFOLD) {                                      // corrections of this K-tile first (small)
+                                tmem_ld32(lane_addr + (uint32_t)(buf * BUF_COLS + TN + c0), r);
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) accr[c0 + j] += __uint_as_float(r[j]);
+                            }
+                            tmem_ld32(lane_addr + (uint32_t)(buf * BUF_COLS + c0), r);
 #pragma unroll
                             for (int j = 0; j < 32; ++j) accr[c0 + j] += __uint_as_float(r[j]);
                         }
@@ -352,15 +377,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_atom_chain(const __grid_constan
                     // the last acc_full commit also covers every correction MMA, and all MMAs have finished reading the
                     // stages: their memory now stages the raw fp32 tile for the CTA-wide epilogue
                     float* ep = reinterpret_cast<float*>(smem) + row * EP_LD + ch * CW;
+                    if (NFOLD) {
 #pragma unroll
-                    for (int c0 = 0; c0 < CW; c0 += 32) {
-                        uint32_t r[32];
-                        tmem_ld32(lane_addr + (uint32_t)(NBUF * TN + c0), r);
+                        for (int c0 = 0; c0 < CW; c0 += 4)
+                            *reinterpret_cast<float4*>(ep + c0) = make_float4(accr[c0], accr[c0 + 1], accr[c0 + 2], accr[c0 + 3]);
+                    } else {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            *reinterpret_cast<float4*>(ep + c0 + j) = make_float4(
-                                accr[c0 + j + 0] + __uint_as_float(r[j + 0]), accr[c0 + j + 1] + __uint_as_float(r[j + 1]),
-                                accr[c0 + j + 2] + __uint_as_float(r[j + 2]), accr[c0 + j + 3] + __uint_as_float(r[j + 3]));
+                        for (int c0 = 0; c0 < CW; c0 += 32) {
+                            uint32_t r[32];
+                            tmem_ld32(lane_addr + (uint32_t)(NBUF * TN + c0), r);
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4)
+                                *reinterpret_cast<float4*>(ep + c0 + j) = make_float4(
+                                    accr[c0 + j + 0] + __uint_as_float(r[j + 0]), accr[c0 + j + 1] + __uint_as_float(r[j + 1]),
+                                    accr[c0 + j + 2] + __uint_as_float(r[j + 2]), accr[c0 + j + 3] + __uint_as_float(r[j + 3]));
+                        }
                     }
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 }
@@ -433,7 +464,7 @@ extern "C" size_t spk_atom_chain_workspace_ints(int n_steps, int64_t n_atoms) {
 }
 
 extern "C" int spk_atom_chain(const spk_chain_step_t* steps, int n_steps, int64_t n_atoms, int32_t* workspace,
-                              size_t workspace_ints, spk_stream_t stream) {
+                              size_t workspace_ints, int flags, spk_stream_t stream) {
     if (!steps || n_steps <= 0 || n_steps > SPK_CHAIN_MAX_STEPS || n_atoms < 0 || !workspace) return SPK_ERR_ARG;
     if (n_atoms == 0) return SPK_OK;
     if (n_atoms > (1ll << 31) - 256) return SPK_ERR_UNSUPPORTED;
@@ -467,11 +498,15 @@ extern "C" int spk_atom_chain(const spk_chain_step_t* steps, int n_steps, int64_
         }
     }
     if (items >= (1ll << 31)) return SPK_ERR_UNSUPPORTED;
-    static SpkSmemOnce once;
-    if (cudaError_t e = once.set(k_atom_chain, SMEM_BYTES); e != cudaSuccess) return SPK_CUDA_ERR(e);
-    int64_t nb = spk_num_sms();                       // one persistent CTA per SM: all CTAs resident (the dependency spin needs it)
+    static SpkSmemOnce once_a, once_b;
+    if (cudaError_t e = once_a.set(k_atom_chain<false>, SMEM_BYTES); e != cudaSuccess) return SPK_CUDA_ERR(e);
+    if (cudaError_t e = once_b.set(k_atom_chain<true>, SMEM_BYTES); e != cudaSuccess) return SPK_CUDA_ERR(e);
+    int64_t nb = spk_num_sms();                       // one persistent CTA per SM
     if (nb > items) nb = items;
-    spk_launch(k_atom_chain, (unsigned)nb, NTHREADS, SMEM_BYTES, spk_st(stream), g);
+    if (flags & SPK_CHAIN_FLAG_NFOLD)
+        spk_launch(k_atom_chain<true>, (unsigned)nb, NTHREADS, SMEM_BYTES, spk_st(stream), g);
+    else
+        spk_launch(k_atom_chain<false>, (unsigned)nb, NTHREADS, SMEM_BYTES, spk_st(stream), g);
     SPK_LAUNCH_CHECK();
     return SPK_OK;
 }

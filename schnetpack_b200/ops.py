@@ -371,6 +371,7 @@ class Lin:
 # persistent per-atom stage (csrc/atom_chain.cu): one launch for mixing(t) + context(t+1) (or their reverses) instead of
 # seven.  SPK_B200_CHAIN=0 restores the launch-per-layer pipeline (same kernels as round 1) for A/B measurements.
 CHAIN_IMPL = os.environ.get("SPK_B200_CHAIN", "0") != "0"      # TODO(default on once validated on the GPU in this round)
+CHAIN_NFOLD = os.environ.get("SPK_B200_CHAIN_NFOLD", "0") != "0"    # 2 MMAs per k-step ([W_hi;W_lo] as one operand)
 _CHAIN_WS: "dict[tuple, Tensor]" = {}
 
 
@@ -407,7 +408,7 @@ def atom_chain(steps, n_atoms: int, device):
     if ws is None or ws.numel() < need:
         ws = torch.zeros(max(need, 4096), dtype=torch.int32, device=device)   # zero once; the kernel leaves it zero
         _CHAIN_WS[key] = ws
-    _lib.call("spk_atom_chain", arr, n, n_atoms, _p(ws), ws.numel(), c_void_p(stream.cuda_stream))
+    _lib.call("spk_atom_chain", arr, n, n_atoms, _p(ws), ws.numel(), 1 if CHAIN_NFOLD else 0, c_void_p(stream.cuda_stream))
 
 
 # ------------------------------------------------------------------------------------------------------------ PaiNN

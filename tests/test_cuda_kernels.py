@@ -551,8 +551,9 @@ def test_bad_neighbor_indices_raise_and_never_gather_out_of_bounds():
     assert not bool(torch.isnan(out[:2]).any()) and bool(torch.isnan(out[2:]).all())
 
 
+@pytest.mark.parametrize("nfold", [False, True])
 @pytest.mark.parametrize("batch", [1, 7, 40])
-def test_atom_chain_matches_per_layer_pipeline(batch):
+def test_atom_chain_matches_per_layer_pipeline(batch, nfold):
     """Persistent per-atom stage (csrc/atom_chain.cu: mixing + next context net, and their reverses, as one launch with
     tile-level dependency counters) == the launch-per-layer pipeline of the same kernels, for atom counts below one tile
     (21), with a partial last tile (147) and several tiles (840); energies / forces also against the fp64 oracle.  Repeated
@@ -565,16 +566,16 @@ def test_atom_chain_matches_per_layer_pipeline(batch):
     spec, data = S.make_config("cfg2", batch=batch)
     params = S.init_params(spec, seed=17)
     model = from_spec(spec, params, DEV)
-    old = ops.CHAIN_IMPL
+    old = ops.CHAIN_IMPL, ops.CHAIN_NFOLD
     try:
         ops.CHAIN_IMPL = False
         ref = model(batch_to_device(data, DEV))
-        ops.CHAIN_IMPL = True
+        ops.CHAIN_IMPL, ops.CHAIN_NFOLD = True, nfold          # both accumulation schemes of the 3xTF32 K-tiles
         for _ in range(3):
             out = model(batch_to_device(data, DEV))
         torch.cuda.synchronize()
     finally:
-        ops.CHAIN_IMPL = old
+        ops.CHAIN_IMPL, ops.CHAIN_NFOLD = old
     assert rel(out["energy"], ref["energy"]) < 2e-6 and rel(out["forces"], ref["forces"]) < 2e-6
     o = O.energy_forces(spec, params, data, dtype=torch.float64)
     assert rel(out["energy"].cpu(), o["energy"]) < 1e-5 and rel(out["forces"].cpu(), o["forces"]) < 1e-5

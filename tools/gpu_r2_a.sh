@@ -12,9 +12,9 @@ if [ $rc -eq 0 ]; then export SPK_B200_CFCONV=tc; else export SPK_B200_CFCONV=ma
 echo "switches: CHAIN=$SPK_B200_CHAIN CFCONV=$SPK_B200_CFCONV" | tee gpurun_out/r2a_switches.txt
 timeout 1500 python -m pytest tests -q -m gpu --timeout=300 --durations=8 > gpurun_out/r2a_gpu_tests.log 2>&1; echo "gpu tests rc=$?"; tail -40 gpurun_out/r2a_gpu_tests.log | cut -c1-220
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
-timeout 300 python bench.py --steps 50 --warmup 5 > gpurun_out/r2a_bench_cfg2.json 2> gpurun_out/r2a_bench_cfg2.err; echo "bench rc=$?"; cut -c1-300 gpurun_out/r2a_bench_cfg2.json; tail -3 gpurun_out/r2a_bench_cfg2.err
-SPK_B200_CHAIN=0 timeout 300 python bench.py --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/r2a_bench_cfg2_nochain.json 2> gpurun_out/r2a_bench_cfg2_nochain.err; echo "bench(no chain) rc=$?"; cut -c1-300 gpurun_out/r2a_bench_cfg2_nochain.json
-timeout 300 python bench.py --config cfg3 --steps 10 --warmup 3 > gpurun_out/r2a_bench_cfg3.json 2> gpurun_out/r2a_bench_cfg3.err; echo "cfg3 rc=$?"; cut -c1-300 gpurun_out/r2a_bench_cfg3.json; tail -3 gpurun_out/r2a_bench_cfg3.err
-SPK_B200_CFCONV=mat timeout 300 python bench.py --config cfg3 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2a_bench_cfg3_mat.json 2> gpurun_out/r2a_bench_cfg3_mat.err; echo "cfg3(mat) rc=$?"; cut -c1-300 gpurun_out/r2a_bench_cfg3_mat.json
-timeout 300 python bench.py --config cfg1 --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/r2a_bench_cfg1.json 2> gpurun_out/r2a_bench_cfg1.err; echo "cfg1 rc=$?"; cut -c1-300 gpurun_out/r2a_bench_cfg1.json
-timeout 400 python bench.py --config cfg5 --atoms 65536 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r2a_bench_cfg5_64k.json 2> gpurun_out/r2a_bench_cfg5_64k.err; echo "cfg5(64k) rc=$?"; cut -c1-400 gpurun_out/r2a_bench_cfg5_64k.json; tail -5 gpurun_out/r2a_bench_cfg5_64k.err
+timeout 500 python bench.py --steps 50 --warmup 5 > gpurun_out/r2a_bench_cfg2.json 2> gpurun_out/r2a_bench_cfg2.err; echo "bench rc=$?"; cut -c1-300 gpurun_out/r2a_bench_cfg2.json; tail -3 gpurun_out/r2a_bench_cfg2.err
+SPK_B200_CHAIN_NFOLD=1 timeout 300 python bench.py --steps 50 --warmup 5 --no-cpu-baseline --no-spatial > gpurun_out/r2a_bench_cfg2_nfold.json 2> gpurun_out/r2a_bench_cfg2_nfold.err; echo "bench(nfold) rc=$?"; cut -c1-300 gpurun_out/r2a_bench_cfg2_nfold.json
+SPK_B200_CHAIN=0 timeout 300 python bench.py --steps 50 --warmup 5 --no-cpu-baseline --no-spatial > gpurun_out/r2a_bench_cfg2_nochain.json 2> gpurun_out/r2a_bench_cfg2_nochain.err; echo "bench(no chain) rc=$?"; cut -c1-300 gpurun_out/r2a_bench_cfg2_nochain.json
+timeout 300 python bench.py --config cfg3 --steps 10 --warmup 3 --no-spatial > gpurun_out/r2a_bench_cfg3.json 2> gpurun_out/r2a_bench_cfg3.err; echo "cfg3 rc=$?"; cut -c1-300 gpurun_out/r2a_bench_cfg3.json; tail -3 gpurun_out/r2a_bench_cfg3.err
+SPK_B200_CFCONV=mat timeout 300 python bench.py --config cfg3 --steps 10 --warmup 3 --no-cpu-baseline --no-spatial > gpurun_out/r2a_bench_cfg3_mat.json 2> gpurun_out/r2a_bench_cfg3_mat.err; echo "cfg3(mat) rc=$?"; cut -c1-300 gpurun_out/r2a_bench_cfg3_mat.json
+timeout 300 python bench.py --config cfg1 --steps 50 --warmup 5 --no-cpu-baseline --no-spatial > gpurun_out/r2a_bench_cfg1.json 2> gpurun_out/r2a_bench_cfg1.err; echo "cfg1 rc=$?"; cut -c1-300 gpurun_out/r2a_bench_cfg1.json
