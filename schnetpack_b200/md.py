@@ -61,6 +61,7 @@ class DeviceMD:
         # count seen so far, [1] = 1 if any step overflowed ``capacity`` (its list was then truncated)
         self.nl_watch = torch.zeros(2, dtype=torch.int64, device=dev)
         self._graph = None
+        self._chain_ws = ops.ChainWorkspace()      # dependency counters of the persistent per-atom stages, owned here
         self.steps_done = 0
         self._calculate()                       # forces at t = 0 (simulator.py:118)
 
@@ -99,12 +100,13 @@ class DeviceMD:
         saved = [t.clone() for t in state]
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            self._step()
-        torch.cuda.current_stream(dev).wait_stream(side)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            self._step()
+        with self._chain_ws:
+            with torch.cuda.stream(side):
+                self._step()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._step()
         for dst, src in zip(state, saved):
             dst.copy_(src)
         self._graph = graph

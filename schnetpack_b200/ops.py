@@ -397,17 +397,46 @@ def chain_glue(kind: int, F: int, eps: float, g0, g1, g2, g3, o0, o1) -> _lib.Ch
     return st
 
 
+class ChainWorkspace:
+    """Dependency-counter workspace owned by a caller that captures evaluations into CUDA graphs (``GraphedPotential``,
+    ``DeviceMD``): allocated OUTSIDE the capture (during the eager warm-up) and alive as long as its owner, so a captured
+    graph never refers to memory of the allocator's per-stream cache or of another graph's private pool."""
+
+    def __init__(self):
+        self.ws: Optional[Tensor] = None
+
+    def __enter__(self):
+        self._prev = _CHAIN_OWNER[0]
+        _CHAIN_OWNER[0] = self
+        return self
+
+    def __exit__(self, *exc):
+        _CHAIN_OWNER[0] = self._prev
+        return False
+
+
+_CHAIN_OWNER = [None]
+
+
 def atom_chain(steps, n_atoms: int, device):
     """Run a stage program (list of ChainStep) over all 128-atom tiles in ONE persistent launch."""
     n = len(steps)
     arr = (_lib.ChainStep * n)(*steps)
     need = _lib.lib().spk_atom_chain_workspace_ints(n, n_atoms)
     stream = torch.cuda.current_stream()
-    key = (device.index if device.index is not None else torch.cuda.current_device(), stream.cuda_stream)
-    ws = _CHAIN_WS.get(key)
-    if ws is None or ws.numel() < need:
-        ws = torch.zeros(max(need, 4096), dtype=torch.int32, device=device)   # zero once; the kernel leaves it zero
-        _CHAIN_WS[key] = ws
+    owner = _CHAIN_OWNER[0]
+    if owner is not None:
+        if owner.ws is None or owner.ws.numel() < need or owner.ws.device != device:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("atom_chain: the owner's workspace must be sized by an eager warm-up before graph capture")
+            owner.ws = torch.zeros(max(need, 4096), dtype=torch.int32, device=device)
+        ws = owner.ws
+    else:
+        key = (device.index if device.index is not None else torch.cuda.current_device(), stream.cuda_stream)
+        ws = _CHAIN_WS.get(key)
+        if ws is None or ws.numel() < need:
+            ws = torch.zeros(max(need, 4096), dtype=torch.int32, device=device)   # zero once; the kernel leaves it zero
+            _CHAIN_WS[key] = ws
     _lib.call("spk_atom_chain", arr, n, n_atoms, _p(ws), ws.numel(), 1 if CHAIN_NFOLD else 0, c_void_p(stream.cuda_stream))
 
 
