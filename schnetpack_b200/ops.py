@@ -404,6 +404,7 @@ class ChainWorkspace:
 
     def __init__(self):
         self.ws: Optional[Tensor] = None
+        self.retired = []          # outgrown workspaces stay alive: graphs captured earlier still write to them
 
     def __enter__(self):
         self._prev = _CHAIN_OWNER[0]
@@ -429,6 +430,8 @@ def atom_chain(steps, n_atoms: int, device):
         if owner.ws is None or owner.ws.numel() < need or owner.ws.device != device:
             if torch.cuda.is_current_stream_capturing():
                 raise RuntimeError("atom_chain: the owner's workspace must be sized by an eager warm-up before graph capture")
+            if owner.ws is not None:
+                owner.retired.append(owner.ws)
             owner.ws = torch.zeros(max(need, 4096), dtype=torch.int32, device=device)
         ws = owner.ws
     else:
