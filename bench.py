@@ -783,6 +783,7 @@ def run_spatial(args, rank, world, local_rank, steps=None, warmup=None, cpu_leg=
     ops.painn_edge_fwd, ops.painn_edge_bwd = orig_fwd, orig_bwd
     P.HaloExchange.forward, P.HaloExchange.backward = staticmethod(orig_halo_f), staticmethod(orig_halo_b)
     P.PeerHaloExchange.forward, P.PeerHaloExchange.backward = staticmethod(orig_peer_f), staticmethod(orig_peer_b)
+    transport = engine.transport
     del engine
     torch.cuda.empty_cache()
     if rank != 0:
@@ -833,7 +834,7 @@ def run_spatial(args, rank, world, local_rank, steps=None, warmup=None, cpu_leg=
                  "bytes_sent_per_step_rank0": 2 * 4 * int(sum(len(v) for v in plan.send.values())) * (3 + 3 * F * T + 3 * F * (T - 1)),
                  "transport": {"peer": "NVLink peer memory: spk_halo_pull / spk_halo_pull_add over torch symmetric memory, one device-side barrier per exchange",
                                "p2p": "NCCL grouped isend/irecv (torch.distributed.batch_isend_irecv), index-gather pack, receives land in the ghost block",
-                               "none": "single rank"}[engine.transport]},
+                               "none": "single rank"}[transport]},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "box-evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "PartitionedPotential.set_positions(host) -> __call__() -> energy, forces to pinned host"},

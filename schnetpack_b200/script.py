@@ -58,15 +58,15 @@ def _module_for(kind: str, weights: List[Tensor], ip: List[int], fp: List[float]
         return mod
     n_atom_basis, n_interactions, n_rbf, rbf_kind, act, shared, shared_filters, n_filters = ip[:8]
     cutoff, eps = fp[0], fp[1]
-    with torch.device(weights[0].device):
-        rbf = snn.GaussianRBF(n_rbf, cutoff) if rbf_kind == ops.RBF_GAUSSIAN else snn.BesselRBF(n_rbf, cutoff)
-        cut = snn.CosineCutoff(cutoff)
-        if kind == "painn":
-            mod = representation.PaiNN(n_atom_basis, n_interactions, rbf, cut, activation=_ACTS[act],
-                                       shared_interactions=bool(shared), shared_filters=bool(shared_filters), epsilon=eps)
-        else:
-            mod = representation.SchNet(n_atom_basis, n_interactions, rbf, cut, n_filters=n_filters,
-                                        shared_interactions=bool(shared), activation=_ACTS[act])
+    # skeleton on the CPU (tiny); load_state_dict(assign=True) below swaps in the caller's (device) tensors without a copy
+    rbf = snn.GaussianRBF(n_rbf, cutoff) if rbf_kind == ops.RBF_GAUSSIAN else snn.BesselRBF(n_rbf, cutoff)
+    cut = snn.CosineCutoff(cutoff)
+    if kind == "painn":
+        mod = representation.PaiNN(n_atom_basis, n_interactions, rbf, cut, activation=_ACTS[act],
+                                   shared_interactions=bool(shared), shared_filters=bool(shared_filters), epsilon=eps)
+    else:
+        mod = representation.SchNet(n_atom_basis, n_interactions, rbf, cut, n_filters=n_filters,
+                                    shared_interactions=bool(shared), activation=_ACTS[act])
     keys = list(mod.state_dict().keys())
     if len(keys) != len(weights):
         raise RuntimeError(f"spk_b200::representation: expected {len(keys)} weight tensors, got {len(weights)}")

@@ -6,6 +6,8 @@ import numpy as np
 import pytest
 import torch
 
+from conftest import rel_err  # noqa: F401
+
 from oracle import nl_oracle as NL
 
 pytestmark = pytest.mark.gpu

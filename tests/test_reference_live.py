@@ -171,6 +171,7 @@ def test_convert_model_custom_embeddings_on_gpu():
                                                              spk.atomistic.Forces()]).eval()
     data = S.aspirin_batch(5, seed=1)
     data["total_charge"] = np.array([0.0, 1.0, -1.0, 2.0, 0.0], dtype=np.float32)
+    data["_idx"] = np.arange(5, dtype=np.int64)              # read by ElectronicEmbedding (nn/embedding.py:311)
     new = convert_model(model).to(dev)
     got = new(batch_to_device(data, dev))
     ref = model.double().to(dev)
