@@ -233,6 +233,10 @@ size_t spk_atom_chain_workspace_ints(int n_steps, int64_t n_atoms);
 #define SPK_CHAIN_FLAG_NFOLD 1 /* 2 MMAs per k-step: [W_hi ; W_lo] as one 256-row operand (see csrc/atom_chain.cu) */
 int spk_atom_chain(const spk_chain_step_t* steps /* host array */, int n_steps, int64_t n_atoms, int32_t* workspace,
                    size_t workspace_ints, int flags, spk_stream_t stream);
+/* development aid: the same launch writing 8 int64 stamps per work item (claimed, dependencies satisfied, K-loop done,
+ * published in ns of %globaltimer; CTA; step; atom tile; unused) to trace[8 * items] (tools/chain_trace.py) */
+int spk_atom_chain_debug(const spk_chain_step_t* steps, int n_steps, int64_t n_atoms, int32_t* workspace,
+                         size_t workspace_ints, int flags, long long* trace, spk_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * SchNet.  representation/schnet.py:41-70 (SchNetInteraction.forward).

@@ -53,6 +53,7 @@ SIGNATURES = {
     "spk_tc_packed_floats_tn": [c_int, c_int, c_int],
     "spk_atom_chain_workspace_ints": [c_int, c_int64],
     "spk_atom_chain": [POINTER(ChainStep), c_int, c_int64, P, c_size_t, c_int, P],
+    "spk_atom_chain_debug": [POINTER(ChainStep), c_int, c_int64, P, c_size_t, c_int, P, P],
     "spk_tc_pack_weight": [P, c_int, c_int, P, P],
     "spk_dense_tc": [P, c_int64, c_int, c_int64, P, c_int, P, c_int, P, c_int, P, c_int64, P, c_int64, P, P],
     "spk_painn_edge_fwd": [P, P, P, P, P, P, P, P, P, c_int64, c_int64, c_int, c_int, P, P, P],

@@ -55,7 +55,18 @@ struct ChainArgs {
     int n_tiles;            // ceil(n_atoms / 128)
     int64_t n_atoms;
     int* ws;                // [n_steps * n_tiles] done counters, then [1] finished-CTA counter, [1] next-item counter
+    long long* trace;       // optional (spk_atom_chain_debug): 8 stamps per item, see tools/chain_trace.py
 };
+
+__device__ __forceinline__ long long gtime() {
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define CTRACE(slot, val)                                                        \
+    do {                                                                         \
+        if (g.trace && tid == 0) g.trace[(int64_t)item * 8 + (slot)] = (val);    \
+    } while (0)
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -229,6 +240,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_atom_chain(const __grid_constan
         // until every item of the previous step for its atom tile has been published
         if (tid == 0) {
             const int it = atomicAdd(next_item, 1);
+            if (g.trace && it < total) g.trace[(int64_t)it * 8 + 0] = gtime();      // claimed
             if (it < total) {
                 int sj = 0;
                 while (it >= base[sj + 1]) ++sj;
@@ -252,6 +264,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_atom_chain(const __grid_constan
         const int tile = local / ipt, sub = local - tile * ipt;
         const int64_t a0 = (int64_t)tile * TM;
         const int64_t a1 = min(a0 + TM, g.n_atoms);
+        CTRACE(1, gtime());                                                          // dependencies satisfied
+        CTRACE(4, (long long)blockIdx.x);
+        CTRACE(5, (long long)si);
+        CTRACE(6, (long long)tile);
 
         if (st.kind != SPK_CHAIN_GEMM) {
             glue_item(st, a0, a1, tid);
@@ -399,6 +415,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_atom_chain(const __grid_constan
             }
             __syncthreads();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            CTRACE(2, gtime());                                                      // K-loop done, tile staged
             if (live) {
                 // =========================================== epilogue: all warps, coalesced ===========================================
                 const float* ept = reinterpret_cast<const float*>(smem);
@@ -436,6 +453,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_atom_chain(const __grid_constan
             __threadfence();
             atomicAdd(g.ws + si * g.n_tiles + tile, 1);
         }
+        CTRACE(3, gtime());                                                          // published
     }
 
     // ---- the last CTA to finish resets the counters for the next launch (the workspace has to be zero only once)
@@ -463,8 +481,18 @@ extern "C" size_t spk_atom_chain_workspace_ints(int n_steps, int64_t n_atoms) {
     return (size_t)n_steps * (size_t)spk_cdiv(n_atoms, TM) + 2;
 }
 
+extern "C" int spk_atom_chain_debug(const spk_chain_step_t* steps, int n_steps, int64_t n_atoms, int32_t* workspace,
+                                    size_t workspace_ints, int flags, long long* trace, spk_stream_t stream);
+
 extern "C" int spk_atom_chain(const spk_chain_step_t* steps, int n_steps, int64_t n_atoms, int32_t* workspace,
                               size_t workspace_ints, int flags, spk_stream_t stream) {
+    return spk_atom_chain_debug(steps, n_steps, n_atoms, workspace, workspace_ints, flags, nullptr, stream);
+}
+
+// same launch with per-item time stamps (8 x int64 per item: claimed, dependencies satisfied, K-loop done, published [ns,
+// %globaltimer], CTA, step, atom tile, -) written to `trace` (device, >= 8 * items int64) -- development aid
+extern "C" int spk_atom_chain_debug(const spk_chain_step_t* steps, int n_steps, int64_t n_atoms, int32_t* workspace,
+                                    size_t workspace_ints, int flags, long long* trace, spk_stream_t stream) {
     if (!steps || n_steps <= 0 || n_steps > SPK_CHAIN_MAX_STEPS || n_atoms < 0 || !workspace) return SPK_ERR_ARG;
     if (n_atoms == 0) return SPK_OK;
     if (n_atoms > (1ll << 31) - 256) return SPK_ERR_UNSUPPORTED;
@@ -474,6 +502,7 @@ extern "C" int spk_atom_chain(const spk_chain_step_t* steps, int n_steps, int64_
     g.n_atoms = n_atoms;
     g.n_tiles = (int)spk_cdiv(n_atoms, TM);
     g.ws = workspace;
+    g.trace = trace;
     auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     int64_t items = 0;
     for (int s = 0; s < n_steps; ++s) {

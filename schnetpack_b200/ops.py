@@ -372,6 +372,7 @@ class Lin:
 # seven.  SPK_B200_CHAIN=0 restores the launch-per-layer pipeline (same kernels as round 1) for A/B measurements.
 CHAIN_IMPL = os.environ.get("SPK_B200_CHAIN", "0") != "0"      # TODO(default on once validated on the GPU in this round)
 CHAIN_NFOLD = os.environ.get("SPK_B200_CHAIN_NFOLD", "0") != "0"    # 2 MMAs per k-step ([W_hi;W_lo] as one operand)
+CHAIN_TRACE = None          # set to a list to collect (stamps, program) of every stage launch
 _CHAIN_WS: "dict[tuple, Tensor]" = {}
 
 
@@ -440,6 +441,13 @@ def atom_chain(steps, n_atoms: int, device):
         if ws is None or ws.numel() < need:
             ws = torch.zeros(max(need, 4096), dtype=torch.int32, device=device)   # zero once; the kernel leaves it zero
             _CHAIN_WS[key] = ws
+    if CHAIN_TRACE is not None:      # development: per-item time stamps of every stage launch (tools/chain_trace.py)
+        items = sum((s.rows_per_atom * (s.N // 128) if s.kind == _lib.CHAIN_GEMM else 1) for s in steps) * ((n_atoms + 127) // 128)
+        tr = torch.zeros((items, 8), dtype=torch.int64, device=device)
+        CHAIN_TRACE.append((tr, [(s.kind, s.K, s.N, s.rows_per_atom) for s in steps]))
+        _lib.call("spk_atom_chain_debug", arr, n, n_atoms, _p(ws), ws.numel(), 1 if CHAIN_NFOLD else 0, _p(tr),
+                  c_void_p(stream.cuda_stream))
+        return
     _lib.call("spk_atom_chain", arr, n, n_atoms, _p(ws), ws.numel(), 1 if CHAIN_NFOLD else 0, c_void_p(stream.cuda_stream))
 
 
