@@ -92,6 +92,19 @@ __device__ __forceinline__ int items_per_tile(const spk_chain_step_t& s) {
     return s.kind == SPK_CHAIN_GEMM ? s.rows_per_atom * (s.N / TN) : 1;
 }
 
+// activation value and derivative for the epilogue of a 128 x 128 tile: 16 k elements on ONE SM, so the instruction count per
+// element is what the tile's latency pays (expf + two IEEE divisions cost 3.3 us per tile; measured).  silu keeps expf
+// (accuracy of the reference's sigmoid) but takes ONE reciprocal; shifted softplus as in common.cuh.
+__device__ __forceinline__ void chain_act_both(float x, int act, float& y, float& dy) {
+    if (act == SPK_ACT_SILU) {
+        const float s = __frcp_rn(1.0f + expf(-x));
+        y = x * s;
+        dy = s * fmaf(x, 1.0f - s, 1.0f);
+    } else {
+        spk_act_both(x, act, y, dy);
+    }
+}
+
 // ---- elementwise glue over the atoms [a0, a1) of one tile: 4 channels per thread, all threads of the CTA ------------------
 __device__ __forceinline__ float4 f4_fma(float4 a, float4 b, float4 c) {
     return make_float4(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y), fmaf(a.z, b.z, c.z), fmaf(a.w, b.w, c.w));
@@ -101,14 +114,19 @@ __device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float
 __device__ __forceinline__ float4 f4_scale(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
+// element t of a tile -> (atom, channel group) with 32-bit arithmetic only
+#define GLUE_LOOP_BEGIN                                                   \
+    for (int t = tid; t < n; t += NTHREADS) {                             \
+        const int ar = t / F4;                                            \
+        const int64_t a = a0 + ar;                                        \
+        const int c = (t - ar * F4) * 4;
+
 __device__ void glue_item(const spk_chain_step_t& s, int64_t a0, int64_t a1, int tid) {
     const int F = s.F, F4 = F >> 2;
-    const int64_t n = (a1 - a0) * F4;
+    const int n = (int)(a1 - a0) * F4;
     if (s.kind == SPK_CHAIN_MIX_CTX) {              // painn.py:104-107   g0 = q, g1 = VW -> o0 = ctx [N,2F]
 #pragma unroll 2
-        for (int64_t t = tid; t < n; t += NTHREADS) {
-            const int64_t a = a0 + t / F4;
-            const int c = (int)(t % F4) * 4;
+        GLUE_LOOP_BEGIN
             const float* v = s.g1 + a * 6 * F + c;
             const float4 v0 = ldcg4(v), v1 = ldcg4(v + 2 * F), v2 = ldcg4(v + 4 * F);
             const float4 q = ldcg4(s.g0 + a * F + c);
@@ -118,10 +136,8 @@ __device__ void glue_item(const spk_chain_step_t& s, int64_t a0, int64_t a1, int
             st4(s.o0 + a * 2 * F + F + c, nn);
         }
     } else if (s.kind == SPK_CHAIN_MIX_UPDATE) {    // painn.py:110-116   g0 = q, g1 = VW, g2 = mu, g3 = s -> o0 = q', o1 = mu'
-#pragma unroll 2
-        for (int64_t t = tid; t < n; t += NTHREADS) {
-            const int64_t a = a0 + t / F4;
-            const int c = (int)(t % F4) * 4;
+#pragma unroll 1
+        GLUE_LOOP_BEGIN
             const float* vw = s.g1 + a * 6 * F + c;
             const float4 v0 = ldcg4(vw), w0 = ldcg4(vw + F), v1 = ldcg4(vw + 2 * F), w1 = ldcg4(vw + 3 * F),
                          v2 = ldcg4(vw + 4 * F), w2 = ldcg4(vw + 5 * F);
@@ -138,10 +154,8 @@ __device__ void glue_item(const spk_chain_step_t& s, int64_t a0, int64_t a1, int
             st4(mo + 2 * F, f4_fma(s2, w2, m2));
         }
     } else if (s.kind == SPK_CHAIN_MIX_UPDATE_BWD) { // g0 = g_q, g1 = VW, g2 = g_mu, g3 = s -> o0 = g_s [N,3F], o1 = g_VW [N,3,2F]
-#pragma unroll 2
-        for (int64_t t = tid; t < n; t += NTHREADS) {
-            const int64_t a = a0 + t / F4;
-            const int c = (int)(t % F4) * 4;
+#pragma unroll 1
+        GLUE_LOOP_BEGIN
             const float* vw = s.g1 + a * 6 * F + c;
             const float4 v0 = ldcg4(vw), w0 = ldcg4(vw + F), v1 = ldcg4(vw + 2 * F), w1 = ldcg4(vw + 3 * F),
                          v2 = ldcg4(vw + 4 * F), w2 = ldcg4(vw + 5 * F);
@@ -165,10 +179,8 @@ __device__ void glue_item(const spk_chain_step_t& s, int64_t a0, int64_t a1, int
             st4(gvw + 5 * F, f4_fma(g2, s2, f4_mul(gqs3, v2)));
         }
     } else if (s.kind == SPK_CHAIN_MIX_CTX_BWD) {   // g0 = g_ctx [N,2F], g1 = VW, g2 = g_q -> o0 = g_q', o1 = g_VW (V third +=)
-#pragma unroll 2
-        for (int64_t t = tid; t < n; t += NTHREADS) {
-            const int64_t a = a0 + t / F4;
-            const int c = (int)(t % F4) * 4;
+#pragma unroll 1
+        GLUE_LOOP_BEGIN
             const float* v = s.g1 + a * 6 * F + c;
             const float4 v0 = ldcg4(v), v1 = ldcg4(v + 2 * F), v2 = ldcg4(v + 4 * F);
             const float4 gc = ldcg4(s.g0 + a * 2 * F + c), gn0 = ldcg4(s.g0 + a * 2 * F + F + c);
@@ -293,20 +305,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_atom_chain(const __grid_constan
                         const uint32_t use = gk / NST;
                         uint8_t* stg = smem + s * STAGE_BYTES;
                         const int k = kt * TK + chunk * 4;
+                        // every load unconditional (clamped row, zeroed afterwards) and the a_pre variant chosen by a
+                        // warp-uniform branch OUTSIDE the batch: loads under a data-dependent branch are serialised by
+                        // the compiler (profiles/FINDINGS.md) -- the first version of this loop cost 2.4 k cycles per K-tile
                         float4 av[16];
+                        const int64_t m_last = M - 1;
 #pragma unroll
                         for (int p = 0; p < 16; ++p) {
                             const int64_t m = m0 + p * 8 + rsubr;
-                            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (m < M) {
-                                v = ldcg4(st.A + m * st.lda + k);
-                                if (st.a_pre) {          // a_pre holds act'(pre) saved by the forward layer (SPK_ACT_GIVEN)
-                                    const float4 d = ldcg4(st.a_pre + m * st.lda + k);
-                                    v.x *= d.x; v.y *= d.y; v.z *= d.z; v.w *= d.w;
+                            av[p] = ldcg4(st.A + (m < M ? m : m_last) * st.lda + k);
+                        }
+                        if (st.a_pre) {              // a_pre holds act'(pre) saved by the forward layer (SPK_ACT_GIVEN)
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {            // two batches of 8: 16 more float4 would spill
+                                float4 dv[8];
+#pragma unroll
+                                for (int p = 0; p < 8; ++p) {
+                                    const int64_t m = m0 + (h * 8 + p) * 8 + rsubr;
+                                    dv[p] = ldcg4(st.a_pre + (m < M ? m : m_last) * st.lda + k);
+                                }
+#pragma unroll
+                                for (int p = 0; p < 8; ++p) {
+                                    float4& v = av[h * 8 + p];
+                                    v.x *= dv[p].x; v.y *= dv[p].y; v.z *= dv[p].z; v.w *= dv[p].w;
                                 }
                             }
-                            av[p] = v;
                         }
+#pragma unroll
+                        for (int p = 0; p < 16; ++p)
+                            if (m0 + p * 8 + rsubr >= M) av[p] = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (use >= 1) mbar_wait(&empty_bar[s], (use - 1) & 1);
                         if (lane == 0) {
                             mbar_expect_tx(&full_bar[s], 2 * OPER_B);
@@ -418,25 +445,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_atom_chain(const __grid_constan
             CTRACE(2, gtime());                                                      // K-loop done, tile staged
             if (live) {
                 // =========================================== epilogue: all warps, coalesced ===========================================
+                // thread -> fixed group of 4 columns (NTHREADS is a multiple of TN / 4), rows tid / 32 + 15 i
                 const float* ept = reinterpret_cast<const float*>(smem);
                 const int act = st.act;
-#pragma unroll 1
-                for (int idx = tid; idx < TM * (TN / 4); idx += NTHREADS) {
-                    const int row = idx / (TN / 4), c4 = idx % (TN / 4);
+                constexpr int RSTEP = NTHREADS / (TN / 4);                   // 15 rows between a thread's elements
+                const int c4 = tid % (TN / 4);
+                const int n = n0 + c4 * 4;
+                float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (st.bias) bv = *reinterpret_cast<const float4*>(st.bias + n);
+#pragma unroll 2
+                for (int row = tid / (TN / 4); row < TM; row += RSTEP) {
                     const int64_t m = m0 + row;
-                    const int n = n0 + c4 * 4;
-                    if (m >= M) continue;
+                    if (m >= M) break;
                     float4 v = *reinterpret_cast<const float4*>(ept + row * EP_LD + c4 * 4);
-                    if (st.bias) {
-                        const float4 bv = *reinterpret_cast<const float4*>(st.bias + n);
-                        v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-                    }
+                    v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
                     if (act != SPK_ACT_NONE) {
                         float4 d;
-                        spk_act_both(v.x, act, v.x, d.x);
-                        spk_act_both(v.y, act, v.y, d.y);
-                        spk_act_both(v.z, act, v.z, d.z);
-                        spk_act_both(v.w, act, v.w, d.w);
+                        chain_act_both(v.x, act, v.x, d.x);
+                        chain_act_both(v.y, act, v.y, d.y);
+                        chain_act_both(v.z, act, v.z, d.z);
+                        chain_act_both(v.w, act, v.w, d.w);
                         if (st.y_pre) *reinterpret_cast<float4*>(st.y_pre + m * st.ldy + n) = d;   // act'(pre) for the reverse sweep
                     }
                     if (st.addend) {

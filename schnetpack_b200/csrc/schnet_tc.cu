@@ -8,6 +8,10 @@
 //
 //   producers   Phi' = [phi | 1 | 0] rows of the chunk (hi/lo TF32 split) -> shared memory (K-major, 64 B swizzle);
 //   MMA 1       H = [W0 | b0] Phi'^T        128 hidden channels (TMEM lanes) x 32 edges (columns), 3xTF32, K = n_rbf + 1;
+//               "N-folded": the hi and lo tiles of an edge operand are adjacent, so [X_hi ; X_lo] is ONE operand of 64 rows
+//               and W_hi [X_hi ; X_lo]^T yields the main product (columns 0..31) and the W_hi X_lo terms (32..63) in one
+//               instruction, W_lo X_hi accumulates onto the latter: 2 MMAs per k-step instead of 3 (an MMA costs ~130 cycles
+//               for any N <= 256, and the chunk's serial MMA chain is what bounds this kernel);
 //   activation  4 warps read H with tcgen05.ld (lane = hidden channel), apply shifted softplus (nn/activations.py:9-22),
 //               split hi/lo and write it back to shared memory as the K-major B operand of the second layer;
 //   MMA 2       D = W1 ssp(H)            128 output channels (lanes) x 32 edges, 3xTF32, K = 128: the main products in one
@@ -44,8 +48,8 @@ constexpr int PHI_STAGE = 2 * 2 * B_TILE;                // [hi,lo][2 k-tiles]
 constexpr int B2_BYTES = 2 * 8 * B_TILE;                 // [hi,lo][8 k-tiles]
 constexpr int META_STAGE = NE * 8;                       // int sender + float fc per row
 constexpr int SMEM_BYTES = W0_BYTES + W1_BYTES + NST * PHI_STAGE + B2_BYTES + NMETA * META_STAGE + 1024;
-constexpr int TMEM_COLS = 256;                           // H[2] x 32 | D[2] x (main 32 | corr 32)
-constexpr int COL_H = 0, COL_D = 64;
+constexpr int TMEM_COLS = 256;                           // H[2] x (main 32 | corr 32) | D[2] x (main 32 | corr 32)
+constexpr int COL_H = 0, COL_D = 128;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
 __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, float (&v)[8]) {
@@ -210,8 +214,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_schnet_cfconv_fwd_tc(
                 hi.x = tf32_rn(v.x); hi.y = tf32_rn(v.y); hi.z = tf32_rn(v.z); hi.w = tf32_rn(v.w);
                 lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
                 const int off = tile_off(r, qc & 3);
-                *reinterpret_cast<float4*>(stP + (0 * 2 + (qc >> 2)) * B_TILE + off) = hi;
-                *reinterpret_cast<float4*>(stP + (1 * 2 + (qc >> 2)) * B_TILE + off) = lo;
+                *reinterpret_cast<float4*>(stP + ((qc >> 2) * 2 + 0) * B_TILE + off) = hi;     // [k-tile][hi | lo]
+                *reinterpret_cast<float4*>(stP + ((qc >> 2) * 2 + 1) * B_TILE + off) = lo;
             }
             st_j[lane] = mj;
             st_fc[lane] = ok0 ? mfc : 0.f;
@@ -230,6 +234,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_schnet_cfconv_fwd_tc(
             tma_load(sW1, wpk + W0_BYTES / 4, W1_BYTES, &w_full);
             const uint32_t idesc =
                 (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NE >> 3) << 17) | ((uint32_t)(F_TC >> 4) << 24);
+            const uint32_t idesc_w =                                       // N = 2 NE: [X_hi ; X_lo] as one operand
+                (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * NE) >> 3) << 17) | ((uint32_t)(F_TC >> 4) << 24);
             mbar_wait(&w_full, 0);
             const uint32_t a0 = smem_u32(sW0), a1 = smem_u32(sW1), bb2 = smem_u32(sB2);
             auto mma1 = [&](int k) {                                      // H(k) = [W0|b0] Phi'(k)^T
@@ -238,16 +244,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_schnet_cfconv_fwd_tc(
                 if (k >= 2) mbar_wait(&h_empty[hb], ((k >> 1) - 1) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t bp = smem_u32(sPhi + st * PHI_STAGE);
-                const uint32_t d = tmem_base + (uint32_t)(COL_H + hb * NE);
+                const uint32_t d = tmem_base + (uint32_t)(COL_H + hb * 2 * NE);
                 for (int s3 = 0; s3 < nks1; ++s3) {
                     const int kt = s3 >> 1, ko = (s3 & 1) * 32;
                     const uint64_t ah = make_desc(a0 + (0 * 2 + kt) * A_TILE + ko);
                     const uint64_t al = make_desc(a0 + (1 * 2 + kt) * A_TILE + ko);
-                    const uint64_t bh = make_desc(bp + (0 * 2 + kt) * B_TILE + ko);
-                    const uint64_t bl = make_desc(bp + (1 * 2 + kt) * B_TILE + ko);
-                    umma_tf32(d, al, bh, idesc, s3 ? 1u : 0u);            // small terms first
-                    umma_tf32(d, ah, bl, idesc, 1u);
-                    umma_tf32(d, ah, bh, idesc, 1u);
+                    const uint64_t bw = make_desc(bp + (kt * 2) * B_TILE + ko);       // hi tile, lo tile follows
+                    umma_tf32(d, ah, bw, idesc_w, s3 ? 1u : 0u);                      // [Wh Xh | Wh Xl]
+                    umma_tf32(d + (uint32_t)NE, al, bw, idesc, 1u);                   // Wl Xh onto the small-term columns
                 }
                 umma_commit(&phi_empty[st]);
                 umma_commit(&h_full[hb]);
@@ -260,17 +264,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_schnet_cfconv_fwd_tc(
                 if (k >= 2) mbar_wait(&d_empty[db], ((k >> 1) - 1) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d_main = tmem_base + (uint32_t)(COL_D + db * 2 * NE);
-                const uint32_t d_corr = d_main + NE;
 #pragma unroll
                 for (int s16 = 0; s16 < 16; ++s16) {                      // D(k) = W1 ssp(H(k)), K = 128
                     const int kt = s16 >> 1, ko = (s16 & 1) * 32;
                     const uint64_t ah = make_desc(a1 + (0 * 8 + kt) * A_TILE + ko);
                     const uint64_t al = make_desc(a1 + (1 * 8 + kt) * A_TILE + ko);
-                    const uint64_t bh = make_desc(bb2 + (0 * 8 + kt) * B_TILE + ko);
-                    const uint64_t bl = make_desc(bb2 + (1 * 8 + kt) * B_TILE + ko);
-                    umma_tf32(d_corr, al, bh, idesc, s16 ? 1u : 0u);
-                    umma_tf32(d_corr, ah, bl, idesc, 1u);
-                    umma_tf32(d_main, ah, bh, idesc, s16 ? 1u : 0u);
+                    const uint64_t bw = make_desc(bb2 + (kt * 2) * B_TILE + ko);      // [act_hi ; act_lo]
+                    umma_tf32(d_main, ah, bw, idesc_w, s16 ? 1u : 0u);
+                    umma_tf32(d_main + (uint32_t)NE, al, bw, idesc, 1u);
                 }
                 umma_commit(&b2_empty);
                 umma_commit(&d_full[db]);
@@ -286,18 +287,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_schnet_cfconv_fwd_tc(
             const int hb = k & 1;
             mbar_wait(&h_full[hb], (k >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            uint32_t r[32];
-            tmem_ld32_nowait(lane_addr + (uint32_t)(COL_H + hb * NE), r);
+            uint32_t r[32], rc[32];
+            tmem_ld32_nowait(lane_addr + (uint32_t)(COL_H + hb * 2 * NE), r);
+            tmem_ld32_nowait(lane_addr + (uint32_t)(COL_H + hb * 2 * NE + NE), rc);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&h_empty[hb]);
             float a[NE];
 #pragma unroll
-            for (int e = 0; e < NE; ++e) a[e] = spk_act(__uint_as_float(r[e]), act);
+            for (int e = 0; e < NE; ++e) a[e] = spk_act(__uint_as_float(r[e]) + __uint_as_float(rc[e]), act);
             if (k >= 1) mbar_wait(&b2_empty, (k - 1) & 1);                // MMA 2 of the previous chunk has read B2
-            uint8_t* hi_t = sB2 + (0 * 8 + kt) * B_TILE;
-            uint8_t* lo_t = sB2 + (1 * 8 + kt) * B_TILE;
+            uint8_t* hi_t = sB2 + (kt * 2 + 0) * B_TILE;                  // [k-tile][hi | lo]
+            uint8_t* lo_t = sB2 + (kt * 2 + 1) * B_TILE;
 #pragma unroll
             for (int e = 0; e < NE; ++e) {
                 const float hi = tf32_rn(a[e]);

@@ -333,6 +333,9 @@ class ScriptForces(nn.Module):
 class ScriptedPotential(nn.Module):
     """model/base.py:132-190 (NeuralNetworkPotential.forward) over the scriptable modules."""
 
+    required_derivatives: List[str]          # class-level annotations: the lists may be empty (energy-only models)
+    model_outputs: List[str]
+
     def __init__(self, input_modules, rep, output_modules, postprocessors, required_derivatives, model_outputs,
                  do_postprocessing: bool):
         super().__init__()
