@@ -370,7 +370,8 @@ class Lin:
 # ------------------------------------------------------------------------------------------------------------ atom chain
 # persistent per-atom stage (csrc/atom_chain.cu): one launch for mixing(t) + context(t+1) (or their reverses) instead of
 # seven.  SPK_B200_CHAIN=0 restores the launch-per-layer pipeline (same kernels as round 1) for A/B measurements.
-CHAIN_IMPL = os.environ.get("SPK_B200_CHAIN", "0") != "0"      # TODO(default on once validated on the GPU in this round)
+CHAIN_IMPL = os.environ.get("SPK_B200_CHAIN", "0") != "0"      # opt-in: measured slower than the launch-per-layer pipeline at the
+#                                                                named sizes (per-SM bandwidth of tile-local items)
 CHAIN_NFOLD = os.environ.get("SPK_B200_CHAIN_NFOLD", "0") != "0"    # 2 MMAs per k-step ([W_hi;W_lo] as one operand)
 CHAIN_TRACE = None          # set to a list to collect (stamps, program) of every stage launch
 _CHAIN_WS: "dict[tuple, Tensor]" = {}
@@ -565,7 +566,7 @@ def cfconv_fwd(h, w_raw, geo, graph: EdgeGraph, F: int):
 
 # fused forward block (csrc/schnet_tc.cu): filter network on tcgen05 inside the edge kernel; F == n_filters == 128, n_rbf <= 31.
 # SPK_B200_CFCONV=mat restores the materialised-filter pipeline (two dense kernels over [E, .] + spk_cfconv_fwd).
-CFCONV_IMPL = os.environ.get("SPK_B200_CFCONV", "mat")           # TODO(default tc once validated on the GPU in this round)
+CFCONV_IMPL = os.environ.get("SPK_B200_CFCONV", "tc")
 CFCONV_TC_MIN_EDGES = 2048
 
 

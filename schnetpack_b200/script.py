@@ -18,8 +18,6 @@ tensors it is handed, without copying them, and calls the same pipelines).  Load
 imported; a pure-C++ host (the LAMMPS pair style, ``interfaces/lammps/pair_schnetpack.cpp:122-132``) would need the same ops
 registered from C++ (``TORCH_LIBRARY``) over the same C ABI -- not provided.
 """
-from __future__ import annotations
-
 from typing import Dict, List, Optional
 
 import torch

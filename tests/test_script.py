@@ -18,16 +18,19 @@ def _model(kind, device="cpu", forces=True):
     return spec, from_spec(spec, S.init_params(spec, seed=5), device)
 
 
-@pytest.mark.parametrize("kind", ["painn", "schnet"])
-def test_scriptable_twin_compiles_saves_and_loads(kind):
+@pytest.mark.parametrize("kind,forces", [("painn", True), ("schnet", True), ("schnet", False)])
+def test_scriptable_twin_compiles_saves_and_loads(kind, forces):
     from schnetpack_b200 import script as SC
 
-    _, model = _model(kind)
+    _, model = _model(kind, forces=forces)
     twin = SC.to_scriptable(model)
     scripted = torch.jit.script(twin)
     g = str(scripted.inlined_graph)
     for op in ("spk_b200::pairwise", "spk_b200::embedding", "spk_b200::representation", "spk_b200::atomwise"):
         assert op in g, op
+    if not forces:            # energy-only model: empty derivative list still types as List[str]
+        assert list(scripted.required_derivatives) == [] and sorted(scripted.model_outputs) == ["energy"]
+        return
     buf = io.BytesIO()
     torch.jit.save(scripted, buf)
     buf.seek(0)
