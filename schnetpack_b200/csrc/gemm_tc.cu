@@ -42,6 +42,13 @@ constexpr int N_DRAIN = 8;                     // drain warps 0-7
 constexpr int W_MMA = 8;
 constexpr int W_PROD0 = 9;
 constexpr int OPER_A = TM * TK * 4;            // 8192 B: A tile, K-major, SWIZZLE_64B
+// K-tiles accumulated in one TMEM main accumulator before it is drained into fp32 registers.  1 (default) is the validated
+// precision scheme; 2 halves the TMEM -> register traffic of the drain warps (the K-loop is drain-bound: ~1000 cycles per
+// K-tile in the round-2 item trace) at the price of 4 instead of 2 truncating accumulations per main accumulator.
+#ifndef SPK_TC_ACC_KT
+#define SPK_TC_ACC_KT 1
+#endif
+constexpr int ACC_KT = SPK_TC_ACC_KT;
 
 template <int TN>
 struct Cfg {
@@ -251,9 +258,11 @@ __global__ void __launch_bounds__(Cfg<TN>::NTHREADS, 1) k_dense_tc(TcArgs g) {
             const uint32_t idesc =
                 (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
             for (int kt = 0; kt < nk; ++kt) {
-                const int s = kt % NST, buf = kt & 1;
+                const int s = kt % NST;
+                const int grp = kt / ACC_KT, buf = grp & 1;                     // accumulator group of ACC_KT K-tiles
+                const bool first = (kt % ACC_KT) == 0, last = (kt % ACC_KT) == ACC_KT - 1 || kt == nk - 1;
                 mbar_wait(&full_bar[s], (kt / NST) & 1);
-                if (kt >= 2) mbar_wait(&acc_empty[buf], ((kt >> 1) - 1) & 1);   // drain warps are done with this buffer
+                if (first && grp >= 2) mbar_wait(&acc_empty[buf], ((grp >> 1) - 1) & 1);   // drain warps are done with it
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
                 const uint32_t d_main = tmem_base + (uint32_t)(buf * TN);
@@ -266,10 +275,10 @@ __global__ void __launch_bounds__(Cfg<TN>::NTHREADS, 1) k_dense_tc(TcArgs g) {
                     const uint64_t bl = make_desc(sa + 2 * OPER_A + OPER_B + 32 * ks);
                     umma_tf32(d_corr, al, bh, idesc, (kt | ks) ? 1u : 0u);   // small terms: accumulate over all of K
                     umma_tf32(d_corr, ah, bl, idesc, 1u);
-                    umma_tf32(d_main, ah, bh, idesc, ks ? 1u : 0u);          // main term: fresh accumulator per K-tile
+                    umma_tf32(d_main, ah, bh, idesc, (ks || !first) ? 1u : 0u);   // main term: fresh accumulator per group
                 }
                 umma_commit(&empty_bar[s]);      // stage reusable once these MMAs have read it
-                umma_commit(&acc_full[buf]);     // main buffer (and, after the last tile, the corrections) ready
+                if (last) umma_commit(&acc_full[buf]);   // main buffer (and, after the last tile, the corrections) ready
                 if (kt < 16) TRACE(48 + kt);     // MMAs of this K-tile issued
             }
         }
@@ -282,7 +291,8 @@ __global__ void __launch_bounds__(Cfg<TN>::NTHREADS, 1) k_dense_tc(TcArgs g) {
         float accr[CW];
 #pragma unroll
         for (int i = 0; i < CW; ++i) accr[i] = 0.f;
-        for (int kt = 0; kt < nk; ++kt) {
+        const int ngrp = (nk + ACC_KT - 1) / ACC_KT;
+        for (int kt = 0; kt < ngrp; ++kt) {                    // kt counts accumulator groups here
             const int buf = kt & 1;
             mbar_wait(&acc_full[buf], (kt >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
