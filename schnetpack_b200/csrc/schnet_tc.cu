@@ -28,6 +28,20 @@
 // the 9-atom cfg1; cfg3 is energy-only inference.
 #include "tcgen05.cuh"
 
+// development aid (build with -DSPK_SCHNET_TRACE, tools/build_variant.sh): clock64 stamps of CTA 0, one row of 16 per chunk
+#ifdef SPK_SCHNET_TRACE
+__device__ long long g_schnet_trace[256 * 16];
+#define STRACE(k, slot)                                                                              \
+    do {                                                                                             \
+        if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (k) < 256) g_schnet_trace[(k) * 16 + (slot)] = clock64(); \
+    } while (0)
+extern "C" int spk_debug_schnet_trace(long long* host) {
+    return (int)cudaMemcpyFromSymbol(host, g_schnet_trace, sizeof(long long) * 256 * 16);
+}
+#else
+#define STRACE(k, slot) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int F_TC = 128;
@@ -225,6 +239,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_schnet_cfconv_fwd_tc(
                 mbar_arrive(&phi_full[st]);
                 mbar_arrive(&meta_full[ms]);
             }
+            STRACE(k, 0);                                   // producer: chunk published
         }
     } else if (warp == W_MMA) {
         // =========================================== MMA issuer ===========================================
@@ -255,13 +270,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_schnet_cfconv_fwd_tc(
                 }
                 umma_commit(&phi_empty[st]);
                 umma_commit(&h_full[hb]);
+                STRACE(k, 1);                               // MMA 1 issued
             };
             if (n_chunks > 0) mma1(0);
             for (int k = 0; k < n_chunks; ++k) {
                 if (k + 1 < n_chunks) mma1(k + 1);                        // keeps the activation warps one chunk ahead
                 const int db = k & 1;
                 mbar_wait(&b2_full, k & 1);
+                STRACE(k, 2);                               // B2 of this chunk available
                 if (k >= 2) mbar_wait(&d_empty[db], ((k >> 1) - 1) & 1);
+                STRACE(k, 3);                               // D buffer free
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d_main = tmem_base + (uint32_t)(COL_D + db * 2 * NE);
 #pragma unroll
@@ -275,6 +293,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_schnet_cfconv_fwd_tc(
                 }
                 umma_commit(&b2_empty);
                 umma_commit(&d_full[db]);
+                STRACE(k, 4);                               // MMA 2 issued
             }
         }
     } else if (warp >= W_ACT0) {
@@ -287,6 +306,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_schnet_cfconv_fwd_tc(
             const int hb = k & 1;
             mbar_wait(&h_full[hb], (k >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (warp == W_ACT0) STRACE(k, 5);              // activation: H ready
             uint32_t r[32], rc[32];
             tmem_ld32_nowait(lane_addr + (uint32_t)(COL_H + hb * 2 * NE), r);
             tmem_ld32_nowait(lane_addr + (uint32_t)(COL_H + hb * 2 * NE + NE), rc);
@@ -297,7 +317,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_schnet_cfconv_fwd_tc(
             float a[NE];
 #pragma unroll
             for (int e = 0; e < NE; ++e) a[e] = spk_act(__uint_as_float(r[e]) + __uint_as_float(rc[e]), act);
+            if (warp == W_ACT0) STRACE(k, 6);              // activation: values computed
             if (k >= 1) mbar_wait(&b2_empty, (k - 1) & 1);                // MMA 2 of the previous chunk has read B2
+            if (warp == W_ACT0) STRACE(k, 7);              // activation: B2 free
             uint8_t* hi_t = sB2 + (kt * 2 + 0) * B_TILE;                  // [k-tile][hi | lo]
             uint8_t* lo_t = sB2 + (kt * 2 + 1) * B_TILE;
 #pragma unroll
@@ -310,6 +332,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_schnet_cfconv_fwd_tc(
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&b2_full);
+            if (warp == W_ACT0) STRACE(k, 8);              // activation: B2 stored
         }
     } else {
         // =========================================== consumers ===========================================
@@ -325,6 +348,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_schnet_cfconv_fwd_tc(
             const int db = k & 1, ms = k % NMETA;
             mbar_wait(&d_full[db], (k >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (warp == 0) STRACE(k, 9);                    // consumer: D ready
             float wm[EG], wc[EG];
             tmem_ld8_nowait(lane_addr + (uint32_t)(db * 2 * NE), wm);
             tmem_ld8_nowait(lane_addr + (uint32_t)(db * 2 * NE + NE), wc);
@@ -359,6 +383,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_schnet_cfconv_fwd_tc(
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&meta_empty[ms]);
+            if (warp == 0) STRACE(k, 10);                   // consumer: chunk done
         }
         for (; i < row_hi; ++i) {
             m[(size_t)i * F + c] = acc;
