@@ -868,6 +868,11 @@ def main():
         return
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
+    # the contract is ONE JSON line on stdout: libraries (NCCL's version banner, symmetric-memory set-up) write to fd 1, so
+    # everything but the final line is diverted to stderr for the duration of the run
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if args.config == "cfg5":
         line = run_spatial(args, rank, world, local_rank)
     else:
@@ -881,8 +886,9 @@ def main():
                 sp = {"error": repr(exc)[:300]}
             if line is not None:
                 line["spatial"] = sp
+    sys.stdout.flush()
     if line is not None:
-        print(json.dumps(line), flush=True)
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         import torch.distributed as dist
 
