@@ -12,8 +12,10 @@
 //               and W_hi [X_hi ; X_lo]^T yields the main product (columns 0..31) and the W_hi X_lo terms (32..63) in one
 //               instruction, W_lo X_hi accumulates onto the latter: 2 MMAs per k-step instead of 3 (an MMA costs ~130 cycles
 //               for any N <= 256, and the chunk's serial MMA chain is what bounds this kernel);
-//   activation  4 warps read H with tcgen05.ld (lane = hidden channel), apply shifted softplus (nn/activations.py:9-22),
-//               split hi/lo and write it back to shared memory as the K-major B operand of the second layer;
+//   activation  the 16 consumer warps (all 512 threads: lane = hidden channel, a group takes its own 8 edges of the NEXT chunk)
+//               read H with tcgen05.ld, apply shifted softplus (nn/activations.py:9-22), split hi/lo and write it to shared
+//               memory as the K-major B operand of the second layer -- 4 dedicated activation warps needed 7.2 k cycles per
+//               chunk for the 32 log1p(exp()) per thread and were the chunk period (phase trace, profiles/);
 //   MMA 2       D = W1 ssp(H)            128 output channels (lanes) x 32 edges, 3xTF32, K = 128: the main products in one
 //               accumulator, the small hi*lo terms in a second one (the tensor core truncates when it accumulates);
 //   consumers   16 warps = 4 groups x 128 channels, thread = channel as in the PaiNN kernels: filter value
@@ -47,12 +49,11 @@ namespace {
 constexpr int F_TC = 128;
 constexpr int EG = 8, NG = 4, NE = EG * NG;              // 32 edge rows per chunk == UMMA N
 constexpr int NCW = NG * 4;                              // 16 consumer warps
-constexpr int W_ACT0 = NCW;                              // 4 activation warps: 16..19 (warp % 4 == TMEM lane quarter)
-constexpr int W_MMA = NCW + 4;
-constexpr int W_PROD0 = NCW + 5;
+constexpr int W_MMA = NCW;
+constexpr int W_PROD0 = NCW + 1;
 constexpr int NPROD = 2, NST = 2;                        // Phi' stages (chunk k -> stage k % 2 -> producer k % 2)
 constexpr int NMETA = 4;                                 // (sender, fc) ring
-constexpr int NTHREADS = (W_PROD0 + NPROD) * 32;         // 736
+constexpr int NTHREADS = (W_PROD0 + NPROD) * 32;         // 608
 constexpr int KT = 16;
 constexpr int A_TILE = F_TC * KT * 4;                    // 8192 B
 constexpr int W0_BYTES = 2 * 2 * A_TILE;                 // [hi,lo][2 k-tiles]
@@ -146,11 +147,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_schnet_cfconv_fwd_tc(
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
             mbar_init(&h_full[b], 1);
-            mbar_init(&h_empty[b], 4);
+            mbar_init(&h_empty[b], NCW);
             mbar_init(&d_full[b], 1);
             mbar_init(&d_empty[b], NCW);
         }
-        mbar_init(&b2_full, 4);
+        mbar_init(&b2_full, NCW);
         mbar_init(&b2_empty, 1);
 #pragma unroll
         for (int s = 0; s < NMETA; ++s) {
@@ -296,44 +297,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_schnet_cfconv_fwd_tc(
                 STRACE(k, 4);                               // MMA 2 issued
             }
         }
-    } else if (warp >= W_ACT0) {
-        // =========================================== activation ===========================================
-        const int qd = warp & 3;                                          // TMEM lane quarter == hidden channels 32qd..
-        const int ch = qd * 32 + lane;
-        const int kt = ch >> 4, kk = ch & 15;
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(qd * 32) << 16);
-        for (int k = 0; k < n_chunks; ++k) {
-            const int hb = k & 1;
-            mbar_wait(&h_full[hb], (k >> 1) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (warp == W_ACT0) STRACE(k, 5);              // activation: H ready
-            uint32_t r[32], rc[32];
-            tmem_ld32_nowait(lane_addr + (uint32_t)(COL_H + hb * 2 * NE), r);
-            tmem_ld32_nowait(lane_addr + (uint32_t)(COL_H + hb * 2 * NE + NE), rc);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&h_empty[hb]);
-            float a[NE];
-#pragma unroll
-            for (int e = 0; e < NE; ++e) a[e] = spk_act(__uint_as_float(r[e]) + __uint_as_float(rc[e]), act);
-            if (warp == W_ACT0) STRACE(k, 6);              // activation: values computed
-            if (k >= 1) mbar_wait(&b2_empty, (k - 1) & 1);                // MMA 2 of the previous chunk has read B2
-            if (warp == W_ACT0) STRACE(k, 7);              // activation: B2 free
-            uint8_t* hi_t = sB2 + (kt * 2 + 0) * B_TILE;                  // [k-tile][hi | lo]
-            uint8_t* lo_t = sB2 + (kt * 2 + 1) * B_TILE;
-#pragma unroll
-            for (int e = 0; e < NE; ++e) {
-                const float hi = tf32_rn(a[e]);
-                const int off = tile_off(e, kk >> 2) + (kk & 3) * 4;
-                *reinterpret_cast<float*>(hi_t + off) = hi;
-                *reinterpret_cast<float*>(lo_t + off) = a[e] - hi;
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&b2_full);
-            if (warp == W_ACT0) STRACE(k, 8);              // activation: B2 stored
-        }
     } else {
         // =========================================== consumers ===========================================
         const int g = warp >> 2, qd = warp & 3;
@@ -344,8 +307,45 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_schnet_cfconv_fwd_tc(
         int next_boundary = i < row_hi ? rowptr[i + 1] : 0x7fffffff;
         float acc = 0.f;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(COL_D + g * EG);
+        // activation of chunk ka for this group's 8 edges: H[lane = hidden channel c, columns g*8..] -> ssp -> B2 rows g*8..
+        const uint32_t lane_h = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(COL_H + g * EG);
+        const int akt = c >> 4, akk = c & 15;
+        auto activate = [&](int ka) {
+            const int hb = ka & 1;
+            mbar_wait(&h_full[hb], (ka >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (warp == 0) STRACE(ka, 5);                  // H ready
+            float hm[EG], hc[EG];
+            tmem_ld8_nowait(lane_h + (uint32_t)(hb * 2 * NE), hm);
+            tmem_ld8_nowait(lane_h + (uint32_t)(hb * 2 * NE + NE), hc);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&h_empty[hb]);
+            float a[EG];
+#pragma unroll
+            for (int e = 0; e < EG; ++e) a[e] = spk_act(hm[e] + hc[e], act);
+            if (warp == 0) STRACE(ka, 6);                  // values computed
+            if (ka >= 1) mbar_wait(&b2_empty, (ka - 1) & 1);              // MMA 2 of the previous chunk has read B2
+            if (warp == 0) STRACE(ka, 7);                  // B2 free
+            uint8_t* hi_t = sB2 + (akt * 2 + 0) * B_TILE;                 // [k-tile][hi | lo]
+            uint8_t* lo_t = sB2 + (akt * 2 + 1) * B_TILE;
+#pragma unroll
+            for (int e = 0; e < EG; ++e) {
+                const float hi = tf32_rn(a[e]);
+                const int off = tile_off(g * EG + e, akk >> 2) + (akk & 3) * 4;
+                *reinterpret_cast<float*>(hi_t + off) = hi;
+                *reinterpret_cast<float*>(lo_t + off) = a[e] - hi;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&b2_full);
+            if (warp == 0) STRACE(ka, 8);                  // B2 stored
+        };
+        if (n_chunks > 0) activate(0);
         for (int k = 0; k < n_chunks; ++k) {
             const int db = k & 1, ms = k % NMETA;
+            if (k + 1 < n_chunks) activate(k + 1);          // the next chunk's hidden layer, while MMA 2 of this one runs
             mbar_wait(&d_full[db], (k >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (warp == 0) STRACE(k, 9);                    // consumer: D ready

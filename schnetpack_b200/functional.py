@@ -336,17 +336,21 @@ class PaiNNContextFunction(torch.autograd.Function):
 
 
 class PaiNNEdgeFunction(torch.autograd.Function):
-    """(x [N,3F], mu [N,3,F] | None, q [N,F], r_ij [E,3]) -> (q + dq, mu + dmu) with the filter evaluated in-kernel from the
-    shared ``EdgeGeometry``; backward returns dE/dx, dE/dmu, dE/dq and this block's contribution to dE/dr_ij."""
+    """(x [N,3F], mu [N,3,F] | None, q [R,F], r_ij [E,3]) -> (q + dq, mu + dmu) [R rows] with the filter evaluated in-kernel
+    from the shared ``EdgeGeometry``; backward returns dE/dx, dE/dmu, dE/dq and this block's contribution to dE/dr_ij.
+    R = number of receiver rows: N, or -- on a partition whose sender tables carry ghost rows after the owned atoms -- the
+    owned count (edges only arrive at owned atoms, so the kernels need not walk the ghost rows)."""
 
     @staticmethod
     def forward(ctx, x, mu, q, r_ij, geom, pk, t):
         g = geom.graph
         xd = x.detach().contiguous()
         mud = mu.detach().contiguous() if mu is not None else None
+        n_rows = int(q.shape[0])
         with ops.device_of(xd):
             q1, mu1 = ops.painn_edge_fwd(xd, mud, q.detach().contiguous(), geom.phi, geom.geo, g, pk.wf[t], pk.bf[t], pk.F,
-                                         geom.n_rbf, wf_packed=_packed_filter(pk, t, geom.n_rbf, g.n_edges))
+                                         geom.n_rbf, wf_packed=_packed_filter(pk, t, geom.n_rbf, g.n_edges), n_rows=n_rows)
+        ctx.n_rows = n_rows
         ctx.h = (xd, mud, geom, pk, t)
         ctx.set_materialize_grads(False)
         return q1, mu1
@@ -358,11 +362,16 @@ class PaiNNEdgeFunction(torch.autograd.Function):
         g = geom.graph
         N, F = g.n_atoms, pk.F
         dev = xd.device
+        R = ctx.n_rows
         with ops.device_of(xd):
-            g_q1 = g_q1.contiguous() if g_q1 is not None else torch.zeros((N, F), dtype=torch.float32, device=dev)
-            g_mu1 = g_mu1.contiguous() if g_mu1 is not None else torch.zeros((N, 3, F), dtype=torch.float32, device=dev)
+            g_q1 = g_q1.contiguous() if g_q1 is not None else torch.zeros((R, F), dtype=torch.float32, device=dev)
+            g_mu1 = g_mu1.contiguous() if g_mu1 is not None else torch.zeros((R, 3, F), dtype=torch.float32, device=dev)
+            g_qk, g_muk = g_q1, g_mu1
+            if R < N:      # the reverse kernel walks SENDER rows (ghosts included) and adds dE/dmu_out row-wise: pad with zeros
+                g_qk = torch.cat([g_q1, g_q1.new_zeros((N - R, F))], dim=0)
+                g_muk = torch.cat([g_mu1, g_mu1.new_zeros((N - R, 3, F))], dim=0)
             g_rij = torch.empty((geom.E, 3), dtype=torch.float32, device=dev)
-            g_x, g_mu0 = ops.painn_edge_bwd(xd, mud, g_q1, g_mu1, geom.phi, geom.dphi, geom.geo, g, pk.wf[t], pk.bf[t], F,
+            g_x, g_mu0 = ops.painn_edge_bwd(xd, mud, g_qk, g_muk, geom.phi, geom.dphi, geom.geo, g, pk.wf[t], pk.bf[t], F,
                                             geom.n_rbf, g_rij, accumulate=False,
                                             wf_packed=_packed_filter(pk, t, geom.n_rbf, g.n_edges))
         return g_x, g_mu0, g_q1, g_rij, None, None, None

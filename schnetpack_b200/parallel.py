@@ -481,7 +481,6 @@ class PartitionedPotential:
             else:
                 raise NotImplementedError("PartitionedPotential: plain nn.Embedding only")
             mu = None
-            ghost_q = q.new_zeros((n_g, F))
             for t in range(pk.T):
                 b = pk.blocks[t]
                 x = K.PaiNNContextFunction.apply(q, b, act)                       # painn.py:54 on the owned atoms
@@ -492,9 +491,9 @@ class PartitionedPotential:
                     gh = _halo(torch.cat([x, mu.reshape(n_o, 3 * F)], dim=1), plan, group, self.peer)
                     x_loc = torch.cat([x, gh[:, :3 * F]], dim=0)
                     mu_loc = torch.cat([mu, gh[:, 3 * F:].reshape(n_g, 3, F)], dim=0)
-                q_loc = torch.cat([q, ghost_q], dim=0)                            # ghost rows receive nothing
-                q1, mu1 = K.PaiNNEdgeFunction.apply(x_loc, mu_loc, q_loc, r_ij, geom, pk, t)     # :55-65
-                q, mu = K.PaiNNMixingFunction.apply(q1[:n_o], mu1[:n_o], b, F, pk.eps, act)      # :103-116
+                # receivers = the n_o owned rows of q; senders = all local rows of x_loc / mu_loc (owned + ghosts)
+                q1, mu1 = K.PaiNNEdgeFunction.apply(x_loc, mu_loc, q, r_ij, geom, pk, t)         # :55-65
+                q, mu = K.PaiNNMixingFunction.apply(q1, mu1, b, F, pk.eps, act)                  # :103-116
             inputs = {"scalar_representation": q, properties.idx_m: self.idx_m,
                       properties.n_atoms: torch.empty(self.n_sys, dtype=torch.int64, device=dev)}
             agg = self.head.aggregation_mode
