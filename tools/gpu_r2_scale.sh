@@ -6,7 +6,7 @@ N=$1
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name --format=csv,noheader | head -$N
 run() { # name, extra env, args
-  env $2 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 295$N\1 \
+  env $2 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500 + N)) \
       bench.py --gpus $N $3 > gpurun_out/r2s_$1_n$N.json 2> gpurun_out/r2s_$1_n$N.err
   echo "$1 N=$N rc=$?"
   python - <<PY
