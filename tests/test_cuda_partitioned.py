@@ -111,3 +111,26 @@ def test_ranks_over_nccl(tmp_path, transport, monkeypatch):
     n_atoms = 3000
     mp.spawn(_worker, args=(world, _free_port(), "nccl", n_atoms, out), nprocs=world, join=True)
     _check(out, n_atoms)
+
+
+def test_model_on_second_device_without_set_device():
+    """A model moved to cuda:1 while cuda:0 stays the current device: streams, launch caches and the >48 KB shared-memory
+    opt-ins follow the tensors' device (ops.device_of, per-device caches in the library)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sys.path.insert(0, ROOT)
+    from conftest import rel_err
+    from schnetpack_b200 import synthetic as S
+    from schnetpack_b200.model import batch_to_device, from_spec
+
+    spec, data = S.make_config("cfg2", batch=24)
+    params = S.init_params(spec, seed=3)
+    torch.cuda.set_device(0)
+    outs = []
+    for d in ("cuda:0", "cuda:1"):
+        model = from_spec(spec, params, torch.device(d))
+        out = model(batch_to_device(data, torch.device(d)))
+        torch.cuda.synchronize(torch.device(d))
+        outs.append({k: v.detach().cpu().numpy() for k, v in out.items()})
+    assert torch.cuda.current_device() == 0
+    assert rel_err(outs[1]["energy"], outs[0]["energy"]) < 1e-6 and rel_err(outs[1]["forces"], outs[0]["forces"]) < 1e-6
