@@ -22,6 +22,7 @@ class PairwiseDistances(nn.Module):
     """Rij = R[idx_j] - R[idx_i] + offsets (distances.py:14-26).  The backward assembles dE/dR per atom from the
     receiver- and sender-grouped edge views (deterministic; the reference uses index_put atomics)."""
 
+    @ops.on_tensor_device
     def forward(self, inputs: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         if self.training and torch.is_grad_enabled():     # training graph: differentiable twice (functional_torch)
             from .. import functional_torch as T
@@ -73,6 +74,7 @@ class Atomwise(nn.Module):
             self._sig = sig
         return self._pk
 
+    @ops.on_tensor_device
     def forward(self, inputs: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         if snn.use_training_path(self):           # training: differentiable ATen path (functional_torch), SURVEY 8 f3
             from .. import functional_torch as T
@@ -106,6 +108,7 @@ class Strain(nn.Module):
     can differentiate the energy with respect to it (response.py:434-464).  Plain tensor algebra on the device; the
     derivative reaches the strain through the positions / offsets gradients of ``PairwiseDistances``."""
 
+    @ops.on_tensor_device
     def forward(self, inputs: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         cell = inputs[properties.cell].reshape(-1, 3, 3)
         eps = torch.zeros_like(cell).requires_grad_()
@@ -142,6 +145,7 @@ class Forces(nn.Module):
         if self.calc_stress:
             self.required_derivatives.append(properties.strain)
 
+    @ops.on_tensor_device
     def forward(self, inputs: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         Epred = inputs[self.energy_key]
         go: List[Optional[torch.Tensor]] = [torch.ones_like(Epred)]

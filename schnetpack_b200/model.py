@@ -12,6 +12,7 @@ import torch.nn as nn
 
 from . import atomistic, representation
 from . import nn as snn
+from . import ops
 
 __all__ = ["AtomisticModel", "NeuralNetworkPotential", "convert_model"]
 
@@ -80,6 +81,7 @@ class NeuralNetworkPotential(AtomisticModel):
     # md/calculators/schnetpack_calculator.py:98): floating inputs are cast to fp32 on entry, results back on exit
     cast_inputs: bool = False
 
+    @ops.on_tensor_device
     def forward(self, inputs: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         out_dtype = None
         if self.cast_inputs:

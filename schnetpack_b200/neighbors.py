@@ -93,6 +93,7 @@ class CellListNeighborList(torch.nn.Module):
         self.capacity = capacity
         self.pad = pad
 
+    @ops.on_tensor_device
     def forward(self, inputs: Dict[str, Tensor]) -> Dict[str, Tensor]:
         R = inputs[P.R]
         res = neighbor_list(R, inputs.get(P.cell), inputs.get(P.pbc), inputs[P.n_atoms], self._cutoff, self.capacity,

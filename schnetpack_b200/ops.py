@@ -44,6 +44,36 @@ def device_of(*tensors):
     return torch.cuda.device(dev)
 
 
+def on_tensor_device(fn):
+    """Decorator for the public ``forward`` methods: run with the CUDA device of the first tensor argument (a tensor, or
+    the first CUDA tensor of an ``inputs`` dict) current.  Everything below -- graph build, weight packing, streams handed
+    to the C ABI, per-device launch caches -- then agrees with the tensors' device even when the caller never called
+    ``torch.cuda.set_device`` (``model.to('cuda:1')``)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *args, **kwargs):
+        dev = None
+        for a in args:
+            if isinstance(a, Tensor):
+                if a.is_cuda:
+                    dev = a.device
+                    break
+            elif isinstance(a, dict):
+                for v in a.values():
+                    if isinstance(v, Tensor) and v.is_cuda:
+                        dev = v.device
+                        break
+                if dev is not None:
+                    break
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(self, *args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(self, *args, **kwargs)
+
+    return wrapped
+
+
 def _chk(t: Tensor, dtype, name: str):
     if not t.is_cuda:
         raise RuntimeError(f"schnetpack_b200: '{name}' must be a CUDA tensor (no CPU fallback); got {t.device}")

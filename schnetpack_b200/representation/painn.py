@@ -33,6 +33,7 @@ class PaiNNInteraction(nn.Module):
             snn.Dense(n_atom_basis, 3 * n_atom_basis, activation=None),
         )
 
+    @ops.on_tensor_device
     def forward(self, q, mu, Wij, dir_ij, idx_i, idx_j, n_atoms: int):
         """painn.py:31-67.  q [N,1,F], mu [N,3,F], Wij [E,1,3F], dir_ij [E,3] -> (q, mu); differentiable w.r.t. q, mu, Wij
         and dir_ij (first order)."""
@@ -73,6 +74,7 @@ class PaiNNMixing(nn.Module):
             self._sig = sig
         return self._blk
 
+    @ops.on_tensor_device
     def forward(self, q, mu):
         """painn.py:92-117.  q [N,1,F], mu [N,3,F] -> (q, mu)."""
         F_ = self.n_atom_basis
@@ -156,6 +158,7 @@ class PaiNN(nn.Module):
         self._pk = K.PaiNNPack()
         return super()._apply(fn, *a, **k)
 
+    @ops.on_tensor_device
     def forward(self, inputs: Dict[str, torch.Tensor]):
         atomic_numbers = inputs[properties.Z]
         r_ij = inputs[properties.Rij]

@@ -32,6 +32,7 @@ class SchNetInteraction(nn.Module):
             Dense(n_rbf, n_filters, activation=activation), Dense(n_filters, n_filters)
         )
 
+    @ops.on_tensor_device
     def forward(self, x, f_ij, idx_i, idx_j, rcut_ij):
         """schnet.py:41-70.  x [N,F], f_ij [E,n_rbf], rcut_ij [E] -> v [N,F]; differentiable w.r.t. x, f_ij, rcut_ij."""
         h = self.in2f(x)                                                           # :60
@@ -104,6 +105,7 @@ class SchNet(nn.Module):
         self._pk = K.SchNetPack()
         return super()._apply(fn, *a, **k)
 
+    @ops.on_tensor_device
     def forward(self, inputs: Dict[str, torch.Tensor]):
         atomic_numbers = inputs[properties.Z]
         r_ij = inputs[properties.Rij]
