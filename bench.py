@@ -72,21 +72,67 @@ def edge_kernel_bytes(E, N, F, has_mu, backward):
 
 
 class ClockSampler:
+    """SM clock + throttle reasons of the benchmarked GPU, sampled WHILE the warm-up and the timed steps run: NVML in a
+    thread (one query every 5 ms: a 50 ms timed region still gets samples), `nvidia-smi -lms` only when NVML is missing."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NVML_REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+                    ("sw_power_cap", 0x4))
 
     def __init__(self, gpu_index: int):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+        self.p = self.f = self.thread = None
+        self.sm, self.reasons, self.mx = [], set(), None
         try:
+            import threading
+
+            import pynvml
+
+            pynvml.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(gpu_index).uuid)
+            try:
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByUUID("GPU-" + uuid)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nv = pynvml
+            self.stop_flag = threading.Event()
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
+        try:
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.QUERY}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
+    def _poll(self):
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                bits = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                for name, bit in self.NVML_REASONS:
+                    if bits & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.005)
+
+    def mark(self):
+        """Start of the timed region: samples from here on are the reported ones (warm-up samples only if there are none)."""
+        self.mark_at = len(self.sm)
+
     def stop(self):
+        if self.thread is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+            sm = self.sm[getattr(self, "mark_at", 0):] or self.sm
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.mx,
+                    "reasons": sorted(self.reasons), "samples": len(sm), "source": "nvml"}
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -110,7 +156,7 @@ class ClockSampler:
                 if len(r) > col and r[col].strip().lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------- reference (CPU) arm
@@ -413,6 +459,8 @@ def run_cuda(args, rank, world, local_rank):
     launches0 = _lib.launch_count
     step_ev = []
     torch.cuda.synchronize()
+    if sampler is not None:
+        sampler.mark()
     t_wall0 = time.perf_counter()
     for _ in range(args.steps):
         flush_l2()
@@ -727,6 +775,8 @@ def run_spatial(args, rank, world, local_rank, steps=None, warmup=None, cpu_leg=
     c0 = _lib.launch_count
     step_ev = []
     torch.cuda.synchronize()
+    if sampler is not None:
+        sampler.mark()
     for _ in range(steps):
         flush_buf.fill_(1)
         s_, e_ = torch.cuda.Event(True), torch.cuda.Event(True)
