@@ -296,6 +296,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_painn_edge_fwd_tc(
                 tmem_ld8_nowait(ta + NE, wb);
                 if (HAS_MU) tmem_ld8_nowait(ta + 2 * NE, wc);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (warp == 0 && k < 16) ETRACE((half ? 144 : 112) + k);   // filter values of this half in registers
                 if (half == 1) {
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
@@ -307,7 +308,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_painn_edge_fwd_tc(
                     float xa[HB], xb[HB], xc[HB], m0[HB], m1[HB], m2[HB];
 #pragma unroll
                     for (int u = 0; u < HB; ++u) {
+#ifdef SPK_EDGE_EXP_JMASK
+                        const int j = st_j[half * HB + u] & 7;     // experiment: all gathers hit L1 (timing only)
+#else
                         const int j = st_j[half * HB + u];
+#endif
                         const float* __restrict__ xj = x + (size_t)j * (3 * F) + c;
                         xa[u] = xj[0];
                         xb[u] = xj[F];
@@ -344,6 +349,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_painn_edge_fwd_tc(
                         }
                     }
                 }
+                if (half == 0 && warp == 0 && k < 16) ETRACE(128 + k);     // first half's edges done
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&meta_empty[st]);
