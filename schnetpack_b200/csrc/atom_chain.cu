@@ -209,7 +209,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_atom_chain(const __grid_constan
     __shared__ __align__(8) uint64_t acc_empty[3];
     __shared__ uint32_t s_tmem;
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // broadcast: the compiler may treat the role index as warp-uniform
     SPK_PDL_LAUNCH_DEPENDENTS();
     if (tid == 0) {
 #pragma unroll

@@ -171,7 +171,8 @@ __global__ void __launch_bounds__(Cfg<TN>::NTHREADS, 1) k_dense_tc(TcArgs g) {
     __shared__ __align__(8) uint64_t acc_empty[2];
     __shared__ uint32_t s_tmem;
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // broadcast: the compiler may treat the role index as warp-uniform
     SPK_PDL_LAUNCH_DEPENDENTS();
     if (tid == 0) TRACE(0);
     const int64_t m0 = (int64_t)blockIdx.x * TM;

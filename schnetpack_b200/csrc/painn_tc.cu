@@ -102,7 +102,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_painn_edge_fwd_tc(
     __shared__ uint32_t s_tmem;
     __shared__ int s_rlo[NG], s_rhi[NG], s_sb[NG], s_se[NG];
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // broadcast: the compiler may treat the role index as warp-uniform
     SPK_PDL_LAUNCH_DEPENDENTS();
     if (tid == 0) ETRACE(0);
     if (tid == 0) {
@@ -259,19 +260,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_painn_edge_fwd_tc(
         int i = s_rlo[g];
         int next_boundary = i < row_hi ? rowptr[i + 1] : 0x7fffffff;
         float dq = 0.f, dm0 = 0.f, dm1 = 0.f, dm2 = 0.f;
-        auto flush = [&](int row) {
-            const size_t o = (size_t)row * F + c;
-            q_out[o] = q[o] + dq;
-            const size_t om = (size_t)row * 3 * F + c;
+        // The residual inputs of the CURRENT receiver row and the row pointer after next are fetched when the row starts,
+        // not when it ends: a row switch then costs four stores instead of two dependent memory latencies (row pointer ->
+        // q / mu rows -> stores) in front of the next edge (measured: the switch, not the gathers, was the consumers'
+        // stall -- the kernel ran as fast with every gather hitting L1).
+        float bq = 0.f, bm0 = 0.f, bm1 = 0.f, bm2 = 0.f;
+        int boundary2 = 0x7fffffff;
+        auto prefetch_row = [&](int row) {                     // row <= row_hi <= n_atoms; clamped reads are never used
+            const int r = row < n_atoms ? row : n_atoms - 1;
+            boundary2 = rowptr[min(row + 2, n_atoms)];
+            bq = q[(size_t)r * F + c];
             if (HAS_MU) {
-                mu_out[om] = mu[om] + dm0;
-                mu_out[om + F] = mu[om + F] + dm1;
-                mu_out[om + 2 * F] = mu[om + 2 * F] + dm2;
-            } else {
-                mu_out[om] = dm0;
-                mu_out[om + F] = dm1;
-                mu_out[om + 2 * F] = dm2;
+                const float* __restrict__ mr = mu + (size_t)r * 3 * F + c;
+                bm0 = mr[0];
+                bm1 = mr[F];
+                bm2 = mr[2 * F];
             }
+        };
+        prefetch_row(i);
+        auto flush = [&](int row) {                            // row == i: its residual inputs are in bq / bm*
+            q_out[(size_t)row * F + c] = bq + dq;
+            const size_t om = (size_t)row * 3 * F + c;
+            mu_out[om] = bm0 + dm0;
+            mu_out[om + F] = bm1 + dm1;
+            mu_out[om + 2 * F] = bm2 + dm2;
             dq = dm0 = dm1 = dm2 = 0.f;
         };
         const uint32_t lane_addr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(g * EG);
@@ -332,7 +344,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_painn_edge_fwd_tc(
                             while (s >= next_boundary) {
                                 flush(i);
                                 ++i;
-                                next_boundary = rowptr[i + 1];
+                                next_boundary = boundary2;
+                                prefetch_row(i);
                             }
                             const float4 uv = st_u[t];
                             dq = fmaf(wa[u], xa[u], dq);
@@ -356,7 +369,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_painn_edge_fwd_tc(
             if (warp == 0 && k < 16) ETRACE(96 + k);           // chunk's edges done
         }
         if (warp == 0) ETRACE(2);
-        for (; i < row_hi; ++i) flush(i);
+        for (; i < row_hi;) {
+            flush(i);
+            ++i;
+            prefetch_row(i);
+        }
         if (warp == 0) ETRACE(3);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -408,7 +425,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_painn_edge_bwd_tc(
     __shared__ int s_rlo[NG], s_rhi[NG], s_sb[NG], s_se[NG];
     __shared__ float s_red[2][NG][EGB][4][4];      // [chunk parity][group][edge][warp][scalar]
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // broadcast: the compiler may treat the role index as warp-uniform
     SPK_PDL_LAUNCH_DEPENDENTS();
     if (tid == 0) {
         mbar_init(&a_full, 1);

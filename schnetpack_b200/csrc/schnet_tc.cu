@@ -135,7 +135,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_schnet_cfconv_fwd_tc(
     __shared__ uint32_t s_tmem;
     __shared__ int s_rlo[NG], s_rhi[NG], s_sb[NG], s_se[NG];
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // broadcast: the compiler may treat the role index as warp-uniform
     SPK_PDL_LAUNCH_DEPENDENTS();
     if (tid == 0) {
         mbar_init(&w_full, 1);
