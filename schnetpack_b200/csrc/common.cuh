@@ -23,8 +23,66 @@ static inline cudaStream_t spk_st(spk_stream_t s) { return reinterpret_cast<cuda
 //     griddepcontrol.wait                -- block until the previous kernel has completed and its writes are visible
 // so the launch latency and CTA ramp-up of kernel n+1 overlap the tail of kernel n while the data dependence through
 // global memory stays exactly that of a serial stream (the wait precedes every global access).  Works under stream capture (programmatic graph edges, CUDA >= 12.3).
+#ifndef SPK_TIMELINE
+#define SPK_TL_PHASE(kind) do { } while (0)
 #define SPK_PDL_LAUNCH_DEPENDENTS() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
 #define SPK_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+#else
+// Debug build (tools/build_variant.sh timeline -DSPK_TIMELINE, tools/timeline.py): thread 0 of block 0 of EVERY kernel stamps
+// %globaltimer at entry and when its griddepcontrol.wait returns (= the previous kernel has completed), tagged with the
+// source line of the macro.  The differences between consecutive wait-return stamps are the kernels' durations INSIDE the
+// programmatic-launch chain of a graph replay -- which neither CUDA events (they break the programmatic edges) nor ncu
+// (serialised, cold) can show.  One buffer per translation unit (no relocatable device code), merged by time on the host.
+static __device__ unsigned long long spk_tl_buf[2048];
+static __device__ unsigned int spk_tl_n;
+__device__ __forceinline__ void spk_tl_stamp(int line, int kind) {
+    if ((blockIdx.x | blockIdx.y | blockIdx.z | threadIdx.x) == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        const unsigned int i = atomicAdd(&spk_tl_n, 1u);
+        if (i < 1024) {
+            spk_tl_buf[2 * i] = t;
+            spk_tl_buf[2 * i + 1] = ((unsigned long long)line << 1) | (unsigned long long)kind;
+        }
+    }
+}
+// phase stamp inside a kernel (call from ONE lane; block 0 only records): kind >= 2, printed relative to the wait-return
+__device__ __forceinline__ void spk_tl_phase(int kind) {
+    if ((blockIdx.x | blockIdx.y | blockIdx.z) == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        const unsigned int i = atomicAdd(&spk_tl_n, 1u);
+        if (i < 1024) {
+            spk_tl_buf[2 * i] = t;
+            spk_tl_buf[2 * i + 1] = (1ull << 40) | (unsigned long long)kind;
+        }
+    }
+}
+#define SPK_TL_PHASE(kind) spk_tl_phase(kind)
+#define SPK_PDL_LAUNCH_DEPENDENTS()                                          \
+    do {                                                                     \
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      \
+        spk_tl_stamp(__LINE__, 0);                                           \
+    } while (0)
+#define SPK_PDL_WAIT()                                                       \
+    do {                                                                     \
+        asm volatile("griddepcontrol.wait;" ::: "memory");                   \
+        spk_tl_stamp(__LINE__, 1);                                           \
+    } while (0)
+#define SPK_TL_CAT2(a, b) a##b
+#define SPK_TL_CAT(a, b) SPK_TL_CAT2(a, b)
+// host: copy this translation unit's stamps out (n = number of stamps) and reset the counter
+extern "C" int SPK_TL_CAT(spk_debug_timeline_, SPK_TU)(unsigned long long* host, unsigned int* n) {
+    cudaDeviceSynchronize();
+    unsigned int cnt = 0, zero = 0;
+    cudaMemcpyFromSymbol(&cnt, spk_tl_n, sizeof(cnt));
+    if (cnt > 1024) cnt = 1024;
+    if (host && cnt) cudaMemcpyFromSymbol(host, spk_tl_buf, sizeof(unsigned long long) * 2 * cnt);
+    cudaMemcpyToSymbol(spk_tl_n, &zero, sizeof(zero));
+    *n = cnt;
+    return 0;
+}
+#endif
 #define SPK_PDL_ENTER()              \
     do {                             \
         SPK_PDL_LAUNCH_DEPENDENTS(); \

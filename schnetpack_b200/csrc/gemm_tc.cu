@@ -49,6 +49,16 @@ constexpr int OPER_A = TM * TK * 4;            // 8192 B: A tile, K-major, SWIZZ
 #define SPK_TC_ACC_KT 1
 #endif
 constexpr int ACC_KT = SPK_TC_ACC_KT;
+// The two small products A_lo*W_hi and A_hi*W_lo share one correction accumulator (0) or get one each (1).  Measured inside
+// the programmatic-launch chain (tools/timeline.py): no difference -- the K-loop's ~400 ns per K-tile of 6 MMAs is the
+// tensor pipe's issue rate for M = 128 tf32 instructions, not a read-modify-write dependence on one TMEM tile.
+#ifndef SPK_TC_DUAL_CORR
+#define SPK_TC_DUAL_CORR 0
+#endif
+#ifndef SPK_TC_STAGGER
+#define SPK_TC_STAGGER 300
+#endif
+constexpr int N_CORR = SPK_TC_DUAL_CORR ? 2 : 1;
 
 template <int TN>
 struct Cfg {
@@ -61,7 +71,7 @@ struct Cfg {
     static constexpr int EP_LD = TN + 4;                    // padded row of the epilogue staging tile (floats)
     static constexpr int SMEM_BYTES = NST * STAGE_BYTES + 1024;   // + slack to align the stages to 1024 B
     static constexpr int NTHREADS = (W_PROD0 + NPROD) * 32;
-    static constexpr int TMEM_COLS = TN == 64 ? 256 : 512;  // main[0] | main[1] | corr | (unused)
+    static constexpr int TMEM_COLS = TN == 64 ? 256 : 512;  // main[0] | main[1] | corr[0] | corr[1]
     static constexpr int CW = TN / 2;                       // columns drained by one warp
     static_assert(NST * STAGE_BYTES >= TM * EP_LD * 4, "epilogue staging tile reuses the pipeline stages");
     static_assert(NST % NPROD == 0, "a stage must be owned by exactly one producer warp");
@@ -212,6 +222,15 @@ __global__ void __launch_bounds__(Cfg<TN>::NTHREADS, 1) k_dense_tc(TcArgs g) {
             uint8_t* st = smem + s * STAGE_BYTES;
             const int k = kt * TK + chunk * 4;
             const bool k_ok = k < g.K;                         // K % 4 == 0: a 16 B chunk is entirely in or out
+#if SPK_TC_STAGGER > 0
+            // The first NPROD K-tiles are requested in K order, SPK_TC_STAGGER cycles apart: issued all at once, 6 x (8 KB of
+            // A + 16 KB of W) share the SM's ~50 B/clk L2 port and K-tile 0 -- which the first MMA waits for -- lands last
+            // as likely as first (measured: first stage published 1.9 us after the wait returned).
+            if (kt < NPROD && kt > 0) {
+                const long long t0 = clock64();
+                while (clock64() - t0 < (long long)kt * SPK_TC_STAGGER) { }
+            }
+#endif
             // ---- issue the global loads first (latency overlaps the wait for the stage) ----
             float4 av[16];
 #pragma unroll
@@ -251,6 +270,7 @@ __global__ void __launch_bounds__(Cfg<TN>::NTHREADS, 1) k_dense_tc(TcArgs g) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&full_bar[s]);
             if (kt < 16) TRACE(32 + kt);                       // stage published
+            if (lane == 0 && (kt == 0 || kt == nk - 1)) SPK_TL_PHASE(kt == 0 ? 2 : 3);   // first / last stage published
         }
     } else if (warp == W_MMA) {
         // =========================================== MMA issuer ===========================================
@@ -268,6 +288,7 @@ __global__ void __launch_bounds__(Cfg<TN>::NTHREADS, 1) k_dense_tc(TcArgs g) {
                 const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
                 const uint32_t d_main = tmem_base + (uint32_t)(buf * TN);
                 const uint32_t d_corr = tmem_base + (uint32_t)(2 * TN);
+                const uint32_t d_corr2 = tmem_base + (uint32_t)((1 + N_CORR) * TN);
 #pragma unroll
                 for (int ks = 0; ks < TK / 8; ++ks) {
                     const uint64_t ah = make_desc(sa + 32 * ks);                     // k-step = 8 floats = 32 B
@@ -275,12 +296,13 @@ __global__ void __launch_bounds__(Cfg<TN>::NTHREADS, 1) k_dense_tc(TcArgs g) {
                     const uint64_t bh = make_desc(sa + 2 * OPER_A + 32 * ks);
                     const uint64_t bl = make_desc(sa + 2 * OPER_A + OPER_B + 32 * ks);
                     umma_tf32(d_corr, al, bh, idesc, (kt | ks) ? 1u : 0u);   // small terms: accumulate over all of K
-                    umma_tf32(d_corr, ah, bl, idesc, 1u);
+                    umma_tf32(d_corr2, ah, bl, idesc, (N_CORR == 1 || (kt | ks)) ? 1u : 0u);
                     umma_tf32(d_main, ah, bh, idesc, (ks || !first) ? 1u : 0u);   // main term: fresh accumulator per group
                 }
                 umma_commit(&empty_bar[s]);      // stage reusable once these MMAs have read it
                 if (last) umma_commit(&acc_full[buf]);   // main buffer (and, after the last tile, the corrections) ready
                 if (kt < 16) TRACE(48 + kt);     // MMAs of this K-tile issued
+                if (kt == 0 || kt == nk - 1) SPK_TL_PHASE(kt == 0 ? 4 : 5);   // first / last K-tile's MMAs issued
             }
         }
     } else {
@@ -316,6 +338,11 @@ __global__ void __launch_bounds__(Cfg<TN>::NTHREADS, 1) k_dense_tc(TcArgs g) {
 #pragma unroll
         for (int c0 = 0; c0 < CW; c0 += 32) {
             uint32_t r[32];
+            if (N_CORR == 2) {
+                tmem_ld32(lane_addr + (uint32_t)(3 * TN + c0), r);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) accr[c0 + j] += __uint_as_float(r[j]);
+            }
             tmem_ld32(lane_addr + (uint32_t)(2 * TN + c0), r);
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
@@ -325,44 +352,64 @@ __global__ void __launch_bounds__(Cfg<TN>::NTHREADS, 1) k_dense_tc(TcArgs g) {
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         if (warp == 0) TRACE(2);                               // tile staged
+        if (warp == 0 && lane == 0) SPK_TL_PHASE(6);
     }
     __syncthreads();
     // =========================================== epilogue: all warps, coalesced ===========================================
     {
+        // Every thread owns ONE float4 column group (NTHREADS is a multiple of TN / 4) and walks down the rows: the bias is
+        // loaded once, pointers advance by constant strides (the index arithmetic of a flat loop was most of the epilogue's
+        // instructions), and the loads of RB rows are issued before their stores (the outputs may alias the inputs as
+        // far as the compiler knows, so it cannot hoist them itself).
+        static_assert(NTHREADS % (TN / 4) == 0, "one column group per thread");
+        constexpr int RSTEP = NTHREADS / (TN / 4), RB = 3;
         const float* ept = reinterpret_cast<const float*>(smem);
+        const int c4 = tid % (TN / 4);
+        const int n = n0 + c4 * 4;
+        const int rows_here = (int)(g.M - m0 < TM ? g.M - m0 : TM);
+        if (n < g.N) {                                           // N % 4 == 0: whole float4 groups only
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (g.bias) bv = *reinterpret_cast<const float4*>(g.bias + n);
+            const bool deriv = g.y_pre && g.save_deriv && ACT != SPK_ACT_NONE;
 #pragma unroll 1
-        for (int idx = tid; idx < TM * (TN / 4); idx += NTHREADS) {
-            const int row = idx / (TN / 4), c4 = idx % (TN / 4);
-            const int64_t m = m0 + row;
-            const int n = n0 + c4 * 4;
-            if (m >= g.M || n >= g.N) continue;                  // N % 4 == 0: whole float4 groups only
-            float4 v = *reinterpret_cast<const float4*>(ept + row * EP_LD + c4 * 4);
-            if (g.bias) {
-                const float4 bv = *reinterpret_cast<const float4*>(g.bias + n);
-                v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+            for (int row0 = tid / (TN / 4); row0 < rows_here; row0 += RSTEP * RB) {
+                float4 v[RB], ad[RB];
+#pragma unroll
+                for (int e = 0; e < RB; ++e) {
+                    const int row = row0 + e * RSTEP;
+                    v[e] = ad[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (row < rows_here) {
+                        v[e] = *reinterpret_cast<const float4*>(ept + row * EP_LD + c4 * 4);
+                        if (g.addend) ad[e] = *reinterpret_cast<const float4*>(g.addend + (m0 + row) * g.ld_add + n);
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < RB; ++e) {
+                    const int row = row0 + e * RSTEP;
+                    if (row >= rows_here) continue;
+                    const int64_t o = (m0 + row) * g.ldy + n;
+                    float4 x = make_float4(v[e].x + bv.x, v[e].y + bv.y, v[e].z + bv.z, v[e].w + bv.w);
+                    if (deriv) {
+                        float4 d;
+                        spk_act_both(x.x, ACT, x.x, d.x);
+                        spk_act_both(x.y, ACT, x.y, d.y);
+                        spk_act_both(x.z, ACT, x.z, d.z);
+                        spk_act_both(x.w, ACT, x.w, d.w);
+                        *reinterpret_cast<float4*>(g.y_pre + o) = d;
+                    } else {
+                        if (g.y_pre)
+                            *reinterpret_cast<float4*>(g.y_pre + o) = g.save_deriv ? make_float4(1.f, 1.f, 1.f, 1.f) : x;
+                        if (ACT != SPK_ACT_NONE)
+                            x = make_float4(spk_act(x.x, ACT), spk_act(x.y, ACT), spk_act(x.z, ACT), spk_act(x.w, ACT));
+                    }
+                    x.x += ad[e].x; x.y += ad[e].y; x.z += ad[e].z; x.w += ad[e].w;
+                    *reinterpret_cast<float4*>(g.Y + o) = x;
+                }
             }
-            if (g.y_pre && g.save_deriv && ACT != SPK_ACT_NONE) {
-                float4 d;
-                spk_act_both(v.x, ACT, v.x, d.x);
-                spk_act_both(v.y, ACT, v.y, d.y);
-                spk_act_both(v.z, ACT, v.z, d.z);
-                spk_act_both(v.w, ACT, v.w, d.w);
-                *reinterpret_cast<float4*>(g.y_pre + m * g.ldy + n) = d;
-            } else {
-                if (g.y_pre)
-                    *reinterpret_cast<float4*>(g.y_pre + m * g.ldy + n) =
-                        g.save_deriv ? make_float4(1.f, 1.f, 1.f, 1.f) : v;
-                if (ACT != SPK_ACT_NONE)
-                    v = make_float4(spk_act(v.x, ACT), spk_act(v.y, ACT), spk_act(v.z, ACT), spk_act(v.w, ACT));
-            }
-            if (g.addend) {
-                const float4 a = *reinterpret_cast<const float4*>(g.addend + m * g.ld_add + n);
-                v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
-            }
-            *reinterpret_cast<float4*>(g.Y + m * g.ldy + n) = v;
         }
     }
     if (tid == 0) TRACE(3);
+    if (tid == 0) SPK_TL_PHASE(7);                                // this CTA's epilogue stores issued
     __syncthreads();
     if (warp == W_MMA) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");

@@ -293,6 +293,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_painn_edge_fwd_tc(
             mbar_wait(&acc_full[buf], (k >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (warp == 0 && k < 16) ETRACE(80 + k);           // accumulators ready
+            if (warp == 0 && lane == 0 && k == 0) SPK_TL_PHASE(2);
             const int* st_j = reinterpret_cast<const int*>(sMeta + st * META_STAGE) + g * EG;
             const float4* st_u = reinterpret_cast<const float4*>(sMeta + st * META_STAGE + NE * 4) + g * EG;
             const int base = s_begin + k * EG;
@@ -369,6 +370,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_painn_edge_fwd_tc(
             if (warp == 0 && k < 16) ETRACE(96 + k);           // chunk's edges done
         }
         if (warp == 0) ETRACE(2);
+        if (warp == 0 && lane == 0) SPK_TL_PHASE(3);           // main loop done
         for (; i < row_hi;) {
             flush(i);
             ++i;
@@ -625,6 +627,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_painn_edge_bwd_tc(
             mbar_wait(&acc_full[buf], (k >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             mbar_wait(&full_bar[st], (k / NST) & 1);           // acquire the producer's metadata writes
+            if (warp == 0 && lane == 0 && k == 0) SPK_TL_PHASE(2);
             const int* st_i = reinterpret_cast<const int*>(sMeta + st * META_B) + g * EGB;
             const int* st_e = reinterpret_cast<const int*>(sMeta + st * META_B) + NEB + g * EGB;
             const float4* st_u = reinterpret_cast<const float4*>(sMeta + st * META_B + 2 * NEB * 4) + g * EGB;
@@ -730,6 +733,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_painn_edge_bwd_tc(
             __syncwarp();
             if (lane == 0) mbar_arrive(&meta_empty[st]);
         }
+        if (warp == 0 && lane == 0) SPK_TL_PHASE(3);           // main loop done
         for (; j < j_hi; ++j) flush(j);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

@@ -7,7 +7,7 @@ cd "$(dirname "$0")/../schnetpack_b200/csrc"
 mkdir -p build_$name
 pids=()
 for f in *.cu; do
-  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr -diag-suppress 550 "$@" -c $f -o build_$name/${f%.cu}.o &
+  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr -diag-suppress 550 "$@" -DSPK_TU=${f%.cu} -c $f -o build_$name/${f%.cu}.o &
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait $p; done
