@@ -89,6 +89,12 @@ extern "C" int SPK_TL_CAT(spk_debug_timeline_, SPK_TU)(unsigned long long* host,
         SPK_PDL_WAIT();              \
     } while (0)
 
+// Kernels that PACK static operands (weights in tensor-core operand layout) use SPK_PDL_WAIT_ONLY: they never trigger their
+// dependents early, so every later kernel of the stream starts after the packed buffer is complete -- which lets the
+// tensor-core kernels fetch those operands by TMA BEFORE their own griddepcontrol.wait (the copy then overlaps the previous
+// kernel instead of sitting at the head of the critical path).
+#define SPK_PDL_WAIT_ONLY() SPK_PDL_WAIT()
+
 // compile with -DSPK_NO_PDL to restore plain launches (A/B builds); the library reads no environment variables
 #ifdef SPK_NO_PDL
 constexpr int SPK_PDL_ATTRS = 0;
@@ -207,6 +213,32 @@ __device__ __forceinline__ int spk_lower_bound(const int32_t* __restrict__ ptr, 
         if (ptr[mid] < target) lo = mid + 1; else hi = mid;
     }
     return lo;
+}
+
+// The same lower bound found by a whole warp: 32 probes per round instead of one, so the chain of DEPENDENT global loads is
+// log32(n) + 1 long instead of log2(n) (5376 rows: 3 instead of 13 -- at ~0.35 us of L2 latency each, the two serial
+// searches per group were ~9 us at the head of every edge kernel, tools/timeline.py).  All lanes must call; all get the result.
+__device__ __forceinline__ int spk_lower_bound_warp(const int32_t* __restrict__ ptr, int n, int target) {
+    const int lane = threadIdx.x & 31;
+    int lo = 0, hi = n;                                        // the answer stays in [lo, hi]; ptr[n] is never read
+    while (hi - lo > 32) {
+        const long long span = hi - lo;
+        const int p = lo + (int)(((lane + 1) * span) / 33);    // strictly increasing in lane, inside (lo, hi)
+        const unsigned m = __ballot_sync(0xffffffffu, ptr[p] >= target);
+        const int f = m ? __ffs(m) - 1 : 32;                   // first lane at or above the target
+        const int new_hi = f == 32 ? hi : lo + (int)(((f + 1) * span) / 33);
+        if (f > 0) lo = lo + (int)((f * span) / 33) + 1;       // lane f - 1 was still below it
+        hi = new_hi;
+    }
+    const int p = lo + lane;
+    const unsigned m = __ballot_sync(0xffffffffu, p < hi ? ptr[p] >= target : true);
+    const int f = m ? __ffs(m) - 1 : 32;
+    return min(lo + f, hi);
+}
+__device__ __forceinline__ int spk_block_row_begin_warp(const int32_t* __restrict__ ptr, int n, int n_edges, int nb, int b) {
+    if (b <= 0) return 0;
+    if (b >= nb) return n;
+    return spk_lower_bound_warp(ptr, n, (int)(((long long)n_edges * b) / nb));
 }
 
 // Edge-balanced split of rows [0,n) over nb blocks: block b gets rows [row_begin(b), row_begin(b+1)).

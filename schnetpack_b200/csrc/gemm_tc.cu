@@ -147,7 +147,7 @@ static inline int tile_n(int64_t M, int N) {
 
 // one-time packing of a weight matrix W [N,K] into per-(n-tile, k-tile) operand tiles [hi | lo]
 __global__ void k_pack_weight(const float* __restrict__ W, int N, int K, int TN, float* __restrict__ out) {
-    SPK_PDL_ENTER();
+    SPK_PDL_WAIT_ONLY();
     const int nkt = (K + TK - 1) / TK;
     const int64_t total = (int64_t)((N + TN - 1) / TN) * nkt * TN * TK;
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -200,6 +200,14 @@ __global__ void __launch_bounds__(Cfg<TN>::NTHREADS, 1) k_dense_tc(TcArgs g) {
         mbar_init(&acc_empty[0], N_DRAIN);
         mbar_init(&acc_empty[1], N_DRAIN);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // the weight tiles of the first NST K-tiles are static operands: their TMA copies are issued here, BEFORE
+        // griddepcontrol.wait, and land while the previous kernel is still running (pack kernels never trigger their
+        // dependents early, common.cuh); after the wait only the A tiles remain to be fetched
+        const float* wp0 = g.Wp + (int64_t)blockIdx.y * nk * (2 * OPER_B / 4);
+        for (int s = 0; s < NST && s < nk; ++s) {
+            mbar_expect_tx(&full_bar[s], 2 * OPER_B);
+            tma_load(smem + s * STAGE_BYTES + 2 * OPER_A, wp0 + (int64_t)s * (2 * OPER_B / 4), 2 * OPER_B, &full_bar[s]);
+        }
     }
     if (warp == W_MMA) {   // the MMA warp owns the TMEM allocation
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
@@ -251,7 +259,7 @@ __global__ void __launch_bounds__(Cfg<TN>::NTHREADS, 1) k_dense_tc(TcArgs g) {
             }
             if (kt < 16) TRACE(16 + kt);                       // loads issued
             if (use >= 1) mbar_wait(&empty_bar[s], (use - 1) & 1);      // MMAs that read this stage have retired
-            if (lane == 0) {   // weight tile (hi|lo, already in operand layout): one TMA bulk copy
+            if (lane == 0 && use >= 1) {   // weight tile (hi|lo, operand layout): one TMA bulk copy (first uses: prefetched above)
                 mbar_expect_tx(&full_bar[s], 2 * OPER_B);
                 tma_load(st + 2 * OPER_A, wp_tile0 + (int64_t)kt * (2 * OPER_B / 4), 2 * OPER_B, &full_bar[s]);
             }

@@ -72,7 +72,7 @@ __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, float (&v)[8]) {
 // [third][hi,lo][k-tile][128 x 16] operand tiles of  [w | b | 0]  (k = n_rbf is the bias column)
 __global__ void k_pack_filter(const float* __restrict__ wf, const float* __restrict__ bf, int n_rbf,
                               float* __restrict__ out) {
-    SPK_PDL_ENTER();
+    SPK_PDL_WAIT_ONLY();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;          // one (third, row, k) element
     if (t >= 3 * F_TC * 32) return;
     const int k = t & 31, row = (t >> 5) % F_TC, third = t / (32 * F_TC);
@@ -119,6 +119,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_painn_edge_fwd_tc(
         mbar_init(&acc_empty[0], NCW);
         mbar_init(&acc_empty[1], NCW);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(&a_full, A_BYTES);          // static operand: fetched BEFORE griddepcontrol.wait (pack kernels never trigger their dependents early, common.cuh)
+        tma_load(sA, wpk, A_BYTES, &a_full);
     }
     if (warp == W_MMA) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
@@ -126,14 +128,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_painn_edge_fwd_tc(
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     SPK_PDL_WAIT();                                // everything below reads memory written by earlier kernels
-    if (tid < NG) {
-        const int nvb = gridDim.x * NG, vb = blockIdx.x * NG + tid;
-        const int lo = spk_block_row_begin(rowptr, n_atoms, n_edges, nvb, vb);
-        const int hi = spk_block_row_begin(rowptr, n_atoms, n_edges, nvb, vb + 1);
-        s_rlo[tid] = lo;
-        s_rhi[tid] = hi;
-        s_sb[tid] = rowptr[lo];
-        s_se[tid] = rowptr[hi];
+    if (warp <= NG) {                              // warp w finds boundary w of this CTA's NG group ranges (warp-wide search)
+        const int bnd = spk_block_row_begin_warp(rowptr, n_atoms, n_edges, gridDim.x * NG, blockIdx.x * NG + warp);
+        if (lane == 0) {
+            const int e = rowptr[bnd];
+            if (warp < NG) {
+                s_rlo[warp] = bnd;
+                s_sb[warp] = e;
+            }
+            if (warp > 0) {
+                s_rhi[warp - 1] = bnd;
+                s_se[warp - 1] = e;
+            }
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -220,8 +227,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_painn_edge_fwd_tc(
     } else if (warp == W_MMA) {
         // =========================================== MMA issuer ===========================================
         if (lane == 0) {
-            mbar_expect_tx(&a_full, A_BYTES);
-            tma_load(sA, wpk, A_BYTES, &a_full);
             const uint32_t idesc =
                 (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NE >> 3) << 17) | ((uint32_t)(F_TC >> 4) << 24);
             mbar_wait(&a_full, 0);
@@ -443,6 +448,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_painn_edge_bwd_tc(
         mbar_init(&acc_empty[0], NCW);
         mbar_init(&acc_empty[1], NCW);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(&a_full, A_BYTES);          // static operand: fetched BEFORE griddepcontrol.wait (pack kernels never trigger their dependents early, common.cuh)
+        tma_load(sA, wpk, A_BYTES, &a_full);
     }
     if (warp == W_MMA) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
@@ -450,14 +457,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_painn_edge_bwd_tc(
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     SPK_PDL_WAIT();
-    if (tid < NG) {
-        const int nvb = gridDim.x * NG, vb = blockIdx.x * NG + tid;
-        const int lo = spk_block_row_begin(sptr, n_atoms, n_edges, nvb, vb);
-        const int hi = spk_block_row_begin(sptr, n_atoms, n_edges, nvb, vb + 1);
-        s_rlo[tid] = lo;
-        s_rhi[tid] = hi;
-        s_sb[tid] = sptr[lo];
-        s_se[tid] = sptr[hi];
+    if (warp <= NG) {                              // warp w finds boundary w of this CTA's NG group ranges (warp-wide search)
+        const int bnd = spk_block_row_begin_warp(sptr, n_atoms, n_edges, gridDim.x * NG, blockIdx.x * NG + warp);
+        if (lane == 0) {
+            const int e = sptr[bnd];
+            if (warp < NG) {
+                s_rlo[warp] = bnd;
+                s_sb[warp] = e;
+            }
+            if (warp > 0) {
+                s_rhi[warp - 1] = bnd;
+                s_se[warp - 1] = e;
+            }
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -555,8 +567,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_painn_edge_bwd_tc(
     } else if (warp == W_MMA) {
         // =========================================== MMA issuer ===========================================
         if (lane == 0) {
-            mbar_expect_tx(&a_full, A_BYTES);
-            tma_load(sA, wpk, A_BYTES, &a_full);
             const uint32_t idesc =
                 (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NE >> 3) << 17) | ((uint32_t)(F_TC >> 4) << 24);
             mbar_wait(&a_full, 0);

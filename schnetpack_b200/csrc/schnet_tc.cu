@@ -90,7 +90,7 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[3
 // packed operands: [W0|b0|0] as [hi,lo][2 k-tiles][128 x 16], then W1 as [hi,lo][8 k-tiles][128 x 16]
 __global__ void k_pack_schnet_filter(const float* __restrict__ w0, const float* __restrict__ b0,
                                      const float* __restrict__ w1, int n_rbf, float* __restrict__ out) {
-    SPK_PDL_ENTER();
+    SPK_PDL_WAIT_ONLY();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     constexpr int N0 = F_TC * 32, N1 = F_TC * F_TC;
     if (t >= N0 + N1) return;
@@ -160,6 +160,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_schnet_cfconv_fwd_tc(
             mbar_init(&meta_empty[s], NCW);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(&w_full, W0_BYTES + W1_BYTES);      // static operand: fetched BEFORE griddepcontrol.wait (pack kernels never trigger their dependents early, common.cuh)
+        tma_load(sW0, wpk, W0_BYTES, &w_full);
+        tma_load(sW1, wpk + W0_BYTES / 4, W1_BYTES, &w_full);
     }
     if (warp == W_MMA) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
@@ -167,15 +170,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_schnet_cfconv_fwd_tc(
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     SPK_PDL_WAIT();
-    if (tid < NG) {
+    if (warp <= NG) {                              // warp w finds boundary w of this CTA's NG group ranges (warp-wide search)
         const int n_act = rowptr[n_atoms];                  // edges in the (possibly active-only) CSR
-        const int nvb = gridDim.x * NG, vb = blockIdx.x * NG + tid;
-        const int lo = spk_block_row_begin(rowptr, n_atoms, n_act, nvb, vb);
-        const int hi = spk_block_row_begin(rowptr, n_atoms, n_act, nvb, vb + 1);
-        s_rlo[tid] = lo;
-        s_rhi[tid] = hi;
-        s_sb[tid] = rowptr[lo];
-        s_se[tid] = rowptr[hi];
+        const int bnd = spk_block_row_begin_warp(rowptr, n_atoms, n_act, gridDim.x * NG, blockIdx.x * NG + warp);
+        if (lane == 0) {
+            const int e = rowptr[bnd];
+            if (warp < NG) {
+                s_rlo[warp] = bnd;
+                s_sb[warp] = e;
+            }
+            if (warp > 0) {
+                s_rhi[warp - 1] = bnd;
+                s_se[warp - 1] = e;
+            }
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -246,9 +254,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_schnet_cfconv_fwd_tc(
     } else if (warp == W_MMA) {
         // =========================================== MMA issuer ===========================================
         if (lane == 0) {
-            mbar_expect_tx(&w_full, W0_BYTES + W1_BYTES);
-            tma_load(sW0, wpk, W0_BYTES, &w_full);
-            tma_load(sW1, wpk + W0_BYTES / 4, W1_BYTES, &w_full);
             const uint32_t idesc =
                 (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NE >> 3) << 17) | ((uint32_t)(F_TC >> 4) << 24);
             const uint32_t idesc_w =                                       // N = 2 NE: [X_hi ; X_lo] as one operand
