@@ -79,28 +79,33 @@ __global__ void k_edge_geometry(const float* __restrict__ r_ij, const int* __res
                                 float rc, const int* __restrict__ n_active, float* __restrict__ phi, float* __restrict__ dphi,
                                 float* __restrict__ geo) {
     SPK_PDL_ENTER();
-    // thread (s, k): k in [0, KP)
-    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (t >= n_edges * KP) return;
-    int64_t s = t / KP;
+    // thread (s, c): slot s, 16-byte chunk c of its KP-float row -> float4 stores, consecutive threads write consecutive
+    // chunks (a thread per scalar spent most of its instructions on 64-bit index arithmetic and re-deriving d)
+    const int C = KP >> 2;
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n_edges * C) return;
+    const int s = (int)(t / C);
     if (n_active && s >= *n_active) return;      // CSR built from the active edges only: slots past its end do not exist
-    int k = (int)(t - s * KP);
-    int64_t e = slot_eid ? (int64_t)slot_eid[s] : s;
-    float x = r_ij[e * 3 + 0], y = r_ij[e * 3 + 1], z = r_ij[e * 3 + 2];
-    float d = sqrtf(x * x + y * y + z * z);  // torch.norm(r_ij, dim=1)
-    float v = 0.0f, dv = 0.0f;
-    if (k < n_rbf) rbf_eval(kind, d, p0[k], p1 ? p1[k] : 0.0f, v, dv);
-    phi[t] = v;
-    if (dphi) dphi[t] = dv;
-    if (k == 0) {
+    const int c = (int)(t - (int64_t)s * C);
+    const int64_t e = slot_eid ? (int64_t)slot_eid[s] : (int64_t)s;
+    const float x = r_ij[e * 3 + 0], y = r_ij[e * 3 + 1], z = r_ij[e * 3 + 2];
+    const float d = sqrtf(x * x + y * y + z * z);  // torch.norm(r_ij, dim=1)
+    float v[4], dv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int k = c * 4 + u;
+        v[u] = dv[u] = 0.0f;
+        if (k < n_rbf) rbf_eval(kind, d, p0[k], p1 ? p1[k] : 0.0f, v[u], dv[u]);
+    }
+    reinterpret_cast<float4*>(phi)[t] = make_float4(v[0], v[1], v[2], v[3]);
+    if (dphi) reinterpret_cast<float4*>(dphi)[t] = make_float4(dv[0], dv[1], dv[2], dv[3]);
+    if (c == 0) {
         float fc, dfc;
         cutoff_eval(d, rc, fc, dfc);
-        float inv = 1.0f / d;  // d == 0 -> inf/NaN exactly like painn.py:228 (r_ij / d_ij)
-        float4 g0 = make_float4(x * inv, y * inv, z * inv, d);
-        float4 g1 = make_float4(fc, dfc, inv, 0.0f);
-        float4* gp = reinterpret_cast<float4*>(geo + s * SPK_GEO_STRIDE);
-        gp[0] = g0;
-        gp[1] = g1;
+        const float inv = 1.0f / d;  // d == 0 -> inf/NaN exactly like painn.py:228 (r_ij / d_ij)
+        float4* gp = reinterpret_cast<float4*>(geo + (int64_t)s * SPK_GEO_STRIDE);
+        gp[0] = make_float4(x * inv, y * inv, z * inv, d);
+        gp[1] = make_float4(fc, dfc, inv, 0.0f);
     }
 }
 
@@ -229,7 +234,7 @@ extern "C" int spk_edge_geometry(const float* r_ij, const int32_t* slot_eid, int
     if (!r_ij || !rbf_p0 || !phi || !geo) return SPK_ERR_ARG;
     if (rbf_kind == SPK_RBF_GAUSSIAN && !rbf_p1) return SPK_ERR_ARG;
     int KP = spk_kp(n_rbf);
-    spk_launch(k_edge_geometry, GRID1D(n_edges * KP, 256), r_ij, slot_eid, n_edges, rbf_kind, n_rbf, KP, rbf_p0, rbf_p1,
+    spk_launch(k_edge_geometry, GRID1D(n_edges * (KP / 4), 256), r_ij, slot_eid, n_edges, rbf_kind, n_rbf, KP, rbf_p0, rbf_p1,
                                                    cutoff, n_active, phi, dphi, geo);
     SPK_LAUNCH_CHECK();
     return SPK_OK;

@@ -23,17 +23,25 @@
 #include "painn_common.cuh"
 #include "tcgen05.cuh"
 
-#ifdef SPK_EDGE_TRACE
+#ifdef SPK_EDGE_TRACE                          // -DSPK_EDGE_TRACE=1: forward kernel stamps, =2: reverse kernel stamps
 __device__ long long g_edge_trace[148 * 256];
-#define ETRACE(slot)                                                                     \
+#define EDGE_STAMP(slot)                                                                 \
     do {                                                                                 \
         if ((threadIdx.x & 31) == 0 && (slot) < 256) g_edge_trace[blockIdx.x * 256 + (slot)] = clock64(); \
     } while (0)
 extern "C" int spk_debug_edge_trace(long long* host) {
     return (int)cudaMemcpyFromSymbol(host, g_edge_trace, sizeof(long long) * 148 * 256);
 }
+#endif
+#if defined(SPK_EDGE_TRACE) && SPK_EDGE_TRACE == 2
+#define ETRACE(slot) do { } while (0)
+#define BTRACE(slot) EDGE_STAMP(slot)
+#elif defined(SPK_EDGE_TRACE)
+#define ETRACE(slot) EDGE_STAMP(slot)
+#define BTRACE(slot) do { } while (0)
 #else
 #define ETRACE(slot) do { } while (0)
+#define BTRACE(slot) do { } while (0)
 #endif
 
 namespace {
@@ -456,7 +464,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_painn_edge_bwd_tc(
                      "n"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
+    if (tid == 0) BTRACE(0);
     SPK_PDL_WAIT();
+    if (tid == 0) BTRACE(1);
     if (warp <= NG) {                              // warp w finds boundary w of this CTA's NG group ranges (warp-wide search)
         const int bnd = spk_block_row_begin_warp(sptr, n_atoms, n_edges, gridDim.x * NG, blockIdx.x * NG + warp);
         if (lane == 0) {
@@ -594,6 +604,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_painn_edge_bwd_tc(
                 }
                 umma_commit(&empty_bar[st]);
                 umma_commit(&acc_full[buf]);
+                if (k < 16) BTRACE(48 + k);                    // MMAs issued
             }
         }
     } else {
@@ -634,9 +645,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_painn_edge_bwd_tc(
         const uint32_t lane_addr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(g * EGB);
         for (int k = 0; k < n_chunks; ++k) {
             const int st = k % NST, buf = k & 1;
+            if (warp == 0 && k < 16) BTRACE(64 + k);           // consumer 0: starts waiting
             mbar_wait(&acc_full[buf], (k >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             mbar_wait(&full_bar[st], (k / NST) & 1);           // acquire the producer's metadata writes
+            if (warp == 0 && k < 16) BTRACE(80 + k);           // accumulators + metadata ready
             if (warp == 0 && lane == 0 && k == 0) SPK_TL_PHASE(2);
             const int* st_i = reinterpret_cast<const int*>(sMeta + st * META_B) + g * EGB;
             const int* st_e = reinterpret_cast<const int*>(sMeta + st * META_B) + NEB + g * EGB;
@@ -712,9 +725,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_painn_edge_bwd_tc(
                 const float tot = butterfly16(red, lane);
                 const int te = half * 4 + (my_idx >> 2);
                 if (!(lane & 1)) s_red[k & 1][g][te][qd][my_idx & 3] = tot;
+                if (warp == 0 && k < 16) BTRACE((half ? 128 : 112) + k);   // half done (4 edges + butterfly)
             }
             // the four warps of the group have published their partial sums of this chunk's 8 edges
             asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+            if (warp == 0 && k < 16) BTRACE(144 + k);          // group barrier passed
             if (qd == 0 && lane < EGB && base + lane < p_end) {
                 const int t = lane;
                 float gd = 0.f, u0 = 0.f, u1 = 0.f, u2 = 0.f;
@@ -742,9 +757,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_painn_edge_bwd_tc(
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&meta_empty[st]);
+            if (warp == 0 && k < 16) BTRACE(96 + k);           // chunk done (incl. the g_rij tail of warp qd == 0)
         }
         if (warp == 0 && lane == 0) SPK_TL_PHASE(3);           // main loop done
+        if (warp == 0) BTRACE(2);
         for (; j < j_hi; ++j) flush(j);
+        if (warp == 0) BTRACE(3);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
