@@ -329,8 +329,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_schnet_cfconv_fwd_tc(
             __syncwarp();
             if (lane == 0) mbar_arrive(&h_empty[hb]);
             float a[EG];
+            if (act == SPK_ACT_SSP) {                      // the block's own activation (schnet.py:45), SFU version
 #pragma unroll
-            for (int e = 0; e < EG; ++e) a[e] = spk_act(hm[e] + hc[e], act);
+                for (int e = 0; e < EG; ++e) a[e] = spk_ssp_fast(hm[e] + hc[e]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < EG; ++e) a[e] = spk_act(hm[e] + hc[e], act);
+            }
             if (warp == 0) STRACE(ka, 6);                  // values computed
             if (ka >= 1) mbar_wait(&b2_empty, (ka - 1) & 1);              // MMA 2 of the previous chunk has read B2
             if (warp == 0) STRACE(ka, 7);                  // B2 free
