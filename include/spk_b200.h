@@ -119,6 +119,10 @@ int spk_dense(const float* A, int64_t M, int K, int64_t lda, const float* a_pre,
               const float* bias, int act, const float* addend, int64_t ld_add, float* Y, int64_t ldy, float* y_pre,
               spk_stream_t stream);
 
+/* Contract of every PACKED operand (spk_tc_pack_weight, spk_painn_pack_filter, spk_schnet_pack_filter): the packed buffer is
+ * a static operand.  The tensor-core kernels fetch it by TMA BEFORE their programmatic-launch dependency wait, so it must be
+ * written only by these pack entry points (whose kernels never release their dependents early) or be complete before the
+ * preceding kernels of the stream were launched; do not overwrite it with other kernels while evaluations are in flight. */
 /* Same layer on the tcgen05 tensor cores with 3xTF32 error compensation (fp32-grade results: split accumulators, K-tile
  * draining; see csrc/gemm_tc.cu).  The weight the A rows are contracted with -- the torch weight [N,K] itself for a
  * forward layer, its transpose for the input-gradient -- is packed once by spk_tc_pack_weight into per-(64-row, 16-column)
