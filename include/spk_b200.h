@@ -135,6 +135,17 @@ int spk_dense_tc(const float* A, int64_t M, int K, int64_t lda, const float* a_p
                  int N, const float* bias, int act, const float* addend, int64_t ld_add, float* Y, int64_t ldy,
                  float* y_pre, spk_stream_t stream);
 
+/* Two Dense layers as ONE launch (csrc/mlp2_tc.cu): H = act(A W0^T + b0) [M,128] stays in shared memory as the tensor-core
+ * operand of Y = H W1^T + b1 [+ addend] [M,N2]; h_deriv (or NULL) receives act'(pre) of the hidden layer [M,128] (what
+ * spk_dense_tc returns with SPK_SAVE_DERIV) for the reverse pass.  Replaces nn.Sequential(Dense(K1, 128, activation),
+ * Dense(128, N2)) of /root/reference/src/schnetpack/representation/painn.py:39-44, 84-91 (PaiNN's context networks).
+ * W0_packed / W1_packed = the 128-column-tile section of spk_tc_pack_weight's output (offset
+ * spk_tc_packed_floats_tn(N, K, 64) floats) for W0 [128,K1] and W1 [N2,128].  Requirements: hidden width 128, N2 % 128 == 0,
+ * K1 % 4 == 0, leading dimensions % 4 == 0, 16 B-aligned pointers; otherwise SPK_ERR_UNSUPPORTED (run two spk_dense_tc). */
+int spk_mlp2_tc(const float* A, int64_t M, int K1, int64_t lda, const float* W0_packed, const float* b0, int act,
+                const float* W1_packed, int N2, const float* b1, const float* addend, int64_t ld_add, float* Y, int64_t ldy,
+                float* h_deriv, spk_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * PaiNN.  representation/painn.py:31-67 (PaiNNInteraction.forward) and :92-117 (PaiNNMixing.forward).
  * ------------------------------------------------------------------------------------------------------------- */

@@ -56,6 +56,7 @@ SIGNATURES = {
     "spk_atom_chain_debug": [POINTER(ChainStep), c_int, c_int64, P, c_size_t, c_int, P, P],
     "spk_tc_pack_weight": [P, c_int, c_int, P, P],
     "spk_dense_tc": [P, c_int64, c_int, c_int64, P, c_int, P, c_int, P, c_int, P, c_int64, P, c_int64, P, P],
+    "spk_mlp2_tc": [P, c_int64, c_int, c_int64, P, P, c_int, P, c_int, P, P, c_int64, P, c_int64, P, P],
     "spk_painn_edge_fwd": [P, P, P, P, P, P, P, P, P, c_int64, c_int64, c_int, c_int, P, P, P],
     "spk_painn_edge_bwd": [P, P, P, P, P, P, P, P, P, P, P, P, P, c_int64, c_int64, c_int, c_int, P, P, P, c_int, P],
     "spk_painn_filter_packed_floats": [],

@@ -86,6 +86,8 @@ def _packed_filter(pk: "PaiNNPack", t: int, n_rbf: int, n_edges: int):
 # ---- per-block pipelines (pure functions over detached fp32 CUDA tensors) -------------------------------------------
 def painn_context_fwd(b, q: Tensor, act: int):
     """x = interatomic_context_net(q) [N,3F] (painn.py:54) and the saved act'(pre) of its first layer."""
+    if ops.mlp2_ok(b["c0"], b["c1"], q):
+        return ops.mlp2(q, b["c0"], b["c1"], act)
     a, hpre = b["c0"].fwd(q, act, save_deriv=True)
     return b["c1"].fwd(a), hpre
 
@@ -101,8 +103,11 @@ def painn_mixing_fwd(b, q1: Tensor, mu1: Tensor, F: int, eps: float, act: int):
     N = q1.shape[0]
     VW = b["mix"].fwd(mu1.view(3 * N, F))                                                    # :103  [3N,2F]
     ctx = ops.painn_mix_ctx(q1, VW, F, eps)                                                  # :104-107
-    c, cpre = b["m0"].fwd(ctx, act, save_deriv=True)                                         # :108
-    s = b["m1"].fwd(c)
+    if ops.mlp2_ok(b["m0"], b["m1"], ctx):
+        s, cpre = ops.mlp2(ctx, b["m0"], b["m1"], act)                                       # :108 as one launch
+    else:
+        c, cpre = b["m0"].fwd(ctx, act, save_deriv=True)                                     # :108
+        s = b["m1"].fwd(c)
     q2, mu2 = ops.painn_mix_update(q1, mu1, s, VW, F)                                        # :110-116
     return q2, mu2, (VW, cpre, s)
 

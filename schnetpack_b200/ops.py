@@ -397,6 +397,28 @@ class Lin:
         return dense(G, self.w, None, ACT_NONE, **kw)
 
 
+# Dense -> Dense pairs as one launch with the hidden tile resident in shared memory (csrc/mlp2_tc.cu).  SPK_B200_MLP2=0 runs the
+# two layers as separate spk_dense_tc launches (A/B measurements; also the path for shapes outside the fused kernel's).
+MLP2_IMPL = os.environ.get("SPK_B200_MLP2", "0") != "0"
+
+
+def mlp2_ok(l0: "Lin", l1: "Lin", A: Tensor) -> bool:
+    return (MLP2_IMPL and l0.w_pk is not None and l1.w_pk is not None and l0.w.shape[0] == 128 and l1.w.shape[1] == 128
+            and l1.w.shape[0] % 128 == 0 and A.shape[1] % 4 == 0 and A.shape[1] == l0.w.shape[1])
+
+
+def mlp2(A: Tensor, l0: "Lin", l1: "Lin", act: int, addend: Optional[Tensor] = None):
+    """(act(A W0^T + b0) W1^T + b1 [+ addend], act'(pre) of the hidden layer) in one launch."""
+    f32(A, "A")
+    M, K1 = A.shape
+    N2 = l1.w.shape[0]
+    Y = torch.empty((M, N2), dtype=torch.float32, device=A.device)
+    deriv = torch.empty((M, 128), dtype=torch.float32, device=A.device)
+    _lib.call("spk_mlp2_tc", _p(A), M, K1, K1, _p(l0.fwd_wide()), _p(l0.b), act, _p(l1.fwd_wide()), N2, _p(l1.b),
+              _p(addend), N2, _p(Y), N2, _p(deriv), _stream())
+    return Y, deriv
+
+
 # ------------------------------------------------------------------------------------------------------------ atom chain
 # persistent per-atom stage (csrc/atom_chain.cu): one launch for mixing(t) + context(t+1) (or their reverses) instead of
 # seven.  SPK_B200_CHAIN=0 restores the launch-per-layer pipeline (same kernels as round 1) for A/B measurements.
